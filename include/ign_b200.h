@@ -1,0 +1,148 @@
+/*
+ * ign_b200.h — C ABI of the B200-native InterpGN shapelet hot path (libign_b200.so).
+ *
+ * Drop-in boundary for the reference path
+ *   InterpretGatedNetwork/model/Shapelet.py:46-238   (Shapelet, DistThresholdShapelet, ShapeBottleneckModel)
+ *   InterpretGatedNetwork/model/InterpGN.py:39-60    (Gini gate + mixture)
+ * The reference has no FFI (it is eager PyTorch); these entry points are what a ctypes binding for that
+ * path binds (INTEGRATION.md shows the stub).  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - Pointers named *_dev are CUDA device pointers on the current device; the caller owns all memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are asynchronous
+ *     on that stream, allocate nothing, and are re-entrant per device.
+ *   - Every function returns ign_status_t; on failure ign_last_error() gives a thread-local message.
+ *   - The library is CUDA-only by design (sm_100a): there is no CPU fallback.
+ *   - Shapes use the reference's names: B batch, T seq_len, M channels (enc_in), K shapelets per length,
+ *     L shapelet length, stride, T' = (T-L)/stride + 1 windows, C classes.
+ *     Pooled outputs are [B,K,M] row-major, i.e. feature index k*M+m of Shapelet.py:84 after flatten.
+ */
+#ifndef IGN_B200_H_
+#define IGN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGN_ABI_VERSION 1
+
+typedef enum {
+  IGN_OK = 0,
+  IGN_ERR_INVALID = 1,     /* bad shape / null pointer / bad enum (reference: torch raises RuntimeError) */
+  IGN_ERR_CUDA = 2,        /* a CUDA runtime call failed */
+  IGN_ERR_UNSUPPORTED = 3, /* combination not implemented */
+  IGN_ERR_ARCH = 4         /* device is not sm_100 */
+} ign_status_t;
+
+/* distance arithmetic, as dispatched by Shapelet.forward (Shapelet.py:64-74) */
+typedef enum {
+  IGN_DIST_L1 = 0,      /* distance_func='euclidean': mean_l |x-w|            Shapelet.py:74 */
+  IGN_DIST_SQL2 = 1,    /* 'euclidean' + memory_efficient: mean_l (w-x)^2     Shapelet.py:28 */
+  IGN_DIST_COSINE = 2,  /* 1 - cos(x_w, w), per-vector norm clamp 1e-8        Shapelet.py:64-66 */
+  IGN_DIST_PEARSON = 3  /* 1 - corr(x_w, w), +1e-8 on the denominator         Shapelet.py:11-19,67-69 */
+} ign_dist_t;
+
+/* pooling over time */
+typedef enum {
+  IGN_POOL_RBF_MAX = 0, /* p=exp(-(eps d)^2); straight-through soft/hard max  Shapelet.py:77-84 */
+  IGN_POOL_LTS_MIN = 1  /* straight-through soft/hard min; sigmoid(thr-min)   Shapelet.py:105-111 */
+} ign_pool_t;
+
+/* engine / operand precision of the cross term <x_w, w> (ignored for IGN_DIST_L1, which has none) */
+typedef enum {
+  IGN_PREC_FP32 = 0,    /* CUDA-core FFMA, exact fp32 products                                     */
+  IGN_PREC_3XTF32 = 1,  /* tcgen05 kind::tf32, hi*hi + hi*lo + lo*hi split: fp32-equivalent         */
+  IGN_PREC_TF32 = 2,    /* tcgen05 kind::tf32 single pass (own, looser tolerance)                   */
+  IGN_PREC_BF16 = 3     /* tcgen05 kind::f16 bf16 operands (own, looser tolerance)                  */
+} ign_precision_t;
+
+typedef struct {
+  int32_t B, M, T;      /* batch, channels, series length                                          */
+  int32_t Tp;           /* row pitch of xn in floats, = ign_padded_len(T)                          */
+  int32_t K, L, stride; /* shapelets per channel, shapelet length, window stride (Shapelet.py:47)  */
+  float eps;            /* RBF width  (Shapelet.eps)                                               */
+  int32_t dist;         /* ign_dist_t                                                              */
+  int32_t pool;         /* ign_pool_t                                                              */
+  int32_t precision;    /* ign_precision_t                                                         */
+} ign_shapelet_desc;
+
+int32_t ign_abi_version(void);
+const char* ign_last_error(void);
+/* IGN_OK iff `device` (or the current device when < 0) is compute capability 10.x */
+int32_t ign_device_check(int32_t device);
+
+/* pitch (floats) of one normalised series row: T rounded up to a multiple of 4 (16-byte rows) */
+int32_t ign_padded_len(int32_t T);
+/* number of windows T' (0 when T < L: the reference's unfold raises there) and its padded pitch */
+int32_t ign_num_windows(int32_t T, int32_t L, int32_t stride);
+int32_t ign_padded_windows(int32_t T, int32_t L, int32_t stride);
+
+/* ShapeBottleneckModel.forward instance norm (Shapelet.py:186-187):
+ *   x_dev [B,T,M] -> xn_dev [B,M,Tp],  xn = (x-mean_T)/(std_T(unbiased)+1e-8), pad columns zeroed.
+ *   Optional (may be NULL) per-series statistics mean_dev/rstd_dev [B,M] (rstd = 1/(std+1e-8)). */
+int32_t ign_instnorm_forward(const float* x_dev, float* xn_dev, float* mean_dev, float* rstd_dev,
+                             int32_t B, int32_t T, int32_t M, void* stream);
+
+/* Sliding-window statistics for the norm terms of cosine / pearson / sql2:
+ *   pre1_dev[b,m,j] = sum_{i<j} xn[b,m,i], pre2_dev[b,m,j] = sum_{i<j} xn[b,m,i]^2, j in [0,T], fp64,
+ *   row pitch T+1.  ||x_w||^2 of window t = pre2[t*stride+L]-pre2[t*stride] (stride 1) — for stride>1
+ *   the same identity holds on the contiguous window. */
+int32_t ign_window_prefix(const float* xn_dev, double* pre1_dev, double* pre2_dev,
+                          int32_t B, int32_t M, int32_t T, void* stream);
+
+/* Shapelet.forward / DistThresholdShapelet.forward for one length group.
+ *   xn_dev [B,M,Tp]; pre1/pre2 [B,M,T+1] (required unless dist==L1); W_dev [K,M,L];
+ *   threshold_dev [K,M] (required for LTS_MIN).
+ * Outputs, all [B,K,M]:
+ *   p_dev       pooled predicate  (max_t RBF prob | sigmoid(thr - min_t d))          Shapelet.py:82 | :109
+ *   dmin_dev    min_t d                                                              Shapelet.py:84
+ *   arg_hard_dev index chosen by the straight-through one-hot (argmax_t p | argmin_t d), first on ties
+ *   argmin_dev  argmin_t d, first on ties (may be NULL)
+ *   Z_dev,S1_dev softmax statistics saved for backward:
+ *                rbf_max: Z=sum_t e^{p_t},            S1=sum_t e^{p_t} p_t
+ *                lts_min: Z=sum_t e^{-(d_t-dmin)},    S1=sum_t e^{-(d_t-dmin)} d_t
+ *   dstore_dev  optional [B,M,K,Tw] (Tw = ign_padded_windows) all window distances, kept for backward;
+ *               NULL in inference. */
+int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev, const double* pre1_dev,
+                             const double* pre2_dev, const float* W_dev, const float* threshold_dev,
+                             float* p_dev, float* dmin_dev, int32_t* arg_hard_dev, int32_t* argmin_dev,
+                             float* Z_dev, float* S1_dev, float* dstore_dev, void* stream);
+
+/* bytes of scratch ign_shapelet_backward needs for this problem */
+size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* desc);
+
+/* Gradient of the pooled output w.r.t. the shapelets, through the saved soft-max weights / argmax:
+ *   g_dev [B,K,M] = dLoss/d(max_p)  (rbf_max)   or   dLoss/d(min_d)  (lts_min; the caller folds the
+ *   sigmoid: g_min = -g_p * p * (1-p), dthreshold = sum_b g_p * p * (1-p))
+ *   dW_dev [K,M,L] is overwritten (not accumulated).  Deterministic (no float atomics). */
+int32_t ign_shapelet_backward(const ign_shapelet_desc* desc, const float* xn_dev, const double* pre1_dev,
+                              const double* pre2_dev, const float* W_dev, const float* g_dev,
+                              const int32_t* arg_hard_dev, const float* dmin_dev, const float* Z_dev,
+                              const float* S1_dev, const float* dstore_dev, float* dW_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* InterpGN gate + mixture (InterpGN.py:44-52): q=softmax(s), eta=(C*sum q^2-1)/(C-1),
+ * if use_gate: eta=1 where eta>gating_value; out=eta*s+(1-eta)*z.  s,z,out [B,C]; eta [B]. */
+int32_t ign_gate_forward(const float* sbm_out_dev, const float* deep_out_dev, float* out_dev,
+                         float* eta_dev, int32_t B, int32_t C, int32_t use_gate, float gating_value,
+                         void* stream);
+/* Backward of the above (eta is NOT detached in the reference).  g_eta_dev may be NULL. */
+int32_t ign_gate_backward(const float* sbm_out_dev, const float* deep_out_dev, const float* g_out_dev,
+                          const float* g_eta_dev, float* g_sbm_dev, float* g_deep_dev, int32_t B,
+                          int32_t C, int32_t use_gate, float gating_value, void* stream);
+
+/* Host-buffer convenience call (inference): the whole shapelet transform of ShapeBottleneckModel.forward
+ * (Shapelet.py:186-196) for G length groups with HOST pointers; copies in, launches, copies out and
+ * synchronises.  x_host [B,T,M]; W_host[g] [K[g],M,L[g]]; probs_host/dists_host [B, sum_g K[g]*M]. */
+int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_t M, int32_t G,
+                               const float* const* W_host, const int32_t* K, const int32_t* L,
+                               const int32_t* stride, float eps, int32_t dist, int32_t precision,
+                               float* probs_host, float* dists_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGN_B200_H_ */

@@ -1,0 +1,202 @@
+// extern "C" entry points of libign_b200.so — see include/ign_b200.h for the contract.
+#include "ign_common.cuh"
+
+#include <string.h>
+#include <vector>
+
+namespace ign {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int max_optin_smem() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0)
+      cached = v;
+    else { cudaGetLastError(); return 227 * 1024; }   // B200 value; used for planning without a device
+  }
+  return cached;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      cached = v;
+    else { cudaGetLastError(); return 148; }
+  }
+  return cached;
+}
+
+static int check_desc(const ign_shapelet_desc* d, const char* who) {
+  IGN_REQUIRE(d != nullptr, "%s: null descriptor", who);
+  IGN_REQUIRE(d->B > 0 && d->M > 0 && d->T > 0 && d->K > 0 && d->L > 0 && d->stride > 0,
+              "%s: non-positive dimension (B=%d M=%d T=%d K=%d L=%d stride=%d)", who, d->B, d->M, d->T,
+              d->K, d->L, d->stride);
+  IGN_REQUIRE(d->Tp == padded_len(d->T), "%s: Tp=%d must equal ign_padded_len(T)=%d", who, d->Tp, padded_len(d->T));
+  IGN_REQUIRE(d->T >= d->L, "%s: maximum size for tensor at dimension 2 is %d but size is %d (T < L)", who, d->T, d->L);
+  IGN_REQUIRE(d->dist >= IGN_DIST_L1 && d->dist <= IGN_DIST_PEARSON, "%s: bad dist %d", who, d->dist);
+  IGN_REQUIRE(d->pool == IGN_POOL_RBF_MAX || d->pool == IGN_POOL_LTS_MIN, "%s: bad pool %d", who, d->pool);
+  IGN_REQUIRE(d->precision >= IGN_PREC_FP32 && d->precision <= IGN_PREC_BF16, "%s: bad precision %d", who, d->precision);
+  IGN_REQUIRE(d->B <= 65535 * 64, "%s: batch too large", who);
+  return IGN_OK;
+}
+
+}  // namespace ign
+
+using namespace ign;
+
+extern "C" {
+
+int32_t ign_abi_version(void) { return IGN_ABI_VERSION; }
+const char* ign_last_error(void) { return g_err; }
+
+int32_t ign_device_check(int32_t device) {
+  int dev = device;
+  if (dev < 0) IGN_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  IGN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) { set_error("device %d is compute capability %d.x; libign_b200 is built for sm_100a only", dev, major); return IGN_ERR_ARCH; }
+  return IGN_OK;
+}
+
+int32_t ign_padded_len(int32_t T) { return padded_len(T); }
+int32_t ign_num_windows(int32_t T, int32_t L, int32_t stride) { return (L <= 0 || stride <= 0) ? 0 : num_windows(T, L, stride); }
+int32_t ign_padded_windows(int32_t T, int32_t L, int32_t stride) { return (L <= 0 || stride <= 0) ? 0 : padded_windows(T, L, stride); }
+
+int32_t ign_instnorm_forward(const float* x, float* xn, float* mean, float* rstd, int32_t B, int32_t T,
+                             int32_t M, void* stream) {
+  IGN_REQUIRE(x && xn, "instnorm_forward: null pointer");
+  IGN_REQUIRE(B > 0 && T > 0 && M > 0 && B <= 65535, "instnorm_forward: bad shape B=%d T=%d M=%d", B, T, M);
+  return launch_instnorm(x, xn, mean, rstd, B, T, M, (cudaStream_t)stream);
+}
+
+int32_t ign_window_prefix(const float* xn, double* pre1, double* pre2, int32_t B, int32_t M, int32_t T, void* stream) {
+  IGN_REQUIRE(xn && pre1 && pre2, "window_prefix: null pointer");
+  IGN_REQUIRE(B > 0 && T > 0 && M > 0, "window_prefix: bad shape B=%d T=%d M=%d", B, T, M);
+  return launch_prefix(xn, pre1, pre2, B, M, T, (cudaStream_t)stream);
+}
+
+int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const double* pre1, const double* pre2,
+                             const float* W, const float* thr, float* p, float* dmin, int32_t* arg_hard,
+                             int32_t* argmin, float* Z, float* S1, float* dstore, void* stream) {
+  int rc = check_desc(d, "shapelet_forward");
+  if (rc) return rc;
+  IGN_REQUIRE(xn && W && p && dmin && arg_hard && Z && S1, "shapelet_forward: null pointer");
+  IGN_REQUIRE(d->dist == IGN_DIST_L1 || (pre1 && pre2), "shapelet_forward: dist %d needs the window prefix sums", d->dist);
+  IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || thr, "shapelet_forward: LTS pooling needs threshold");
+  IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || d->dist <= IGN_DIST_SQL2,
+              "shapelet_forward: DistThresholdShapelet ignores distance_func (Shapelet.py:100-103); use L1 or SQL2");
+  if (d->precision != IGN_PREC_FP32 && d->dist != IGN_DIST_L1) {
+    set_error("shapelet_forward: tcgen05 precision modes are not built into this library yet");
+    return IGN_ERR_UNSUPPORTED;
+  }
+  return launch_shapelet_fwd_simt(*d, xn, pre1, pre2, W, thr, p, dmin, arg_hard, argmin, Z, S1, dstore, (cudaStream_t)stream);
+}
+
+size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
+  if (check_desc(d, "shapelet_backward_workspace")) return 0;
+  return shapelet_bwd_workspace_simt(*d);
+}
+
+int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const double* pre1, const double* pre2,
+                              const float* W, const float* g, const int32_t* arg_hard, const float* dmin,
+                              const float* Z, const float* S1, const float* dstore, float* dW, void* ws,
+                              size_t ws_bytes, void* stream) {
+  int rc = check_desc(d, "shapelet_backward");
+  if (rc) return rc;
+  IGN_REQUIRE(xn && W && g && arg_hard && dmin && Z && S1 && dW && ws, "shapelet_backward: null pointer");
+  IGN_REQUIRE(dstore, "shapelet_backward: dstore (window distances saved by forward) is required");
+  IGN_REQUIRE(d->dist == IGN_DIST_L1 || (pre1 && pre2), "shapelet_backward: dist %d needs the window prefix sums", d->dist);
+  return launch_shapelet_bwd_simt(*d, xn, pre1, pre2, W, g, arg_hard, dmin, Z, S1, dstore, dW, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int32_t ign_gate_forward(const float* s, const float* z, float* out, float* eta, int32_t B, int32_t C,
+                         int32_t use_gate, float gv, void* stream) {
+  IGN_REQUIRE(s && z && out && eta, "gate_forward: null pointer");
+  IGN_REQUIRE(B > 0 && C > 1, "gate_forward: bad shape B=%d C=%d (needs C>1)", B, C);
+  return launch_gate_fwd(s, z, out, eta, B, C, use_gate, gv, (cudaStream_t)stream);
+}
+
+int32_t ign_gate_backward(const float* s, const float* z, const float* go, const float* ge, float* gs, float* gz,
+                          int32_t B, int32_t C, int32_t use_gate, float gv, void* stream) {
+  IGN_REQUIRE(s && z && go && gs && gz, "gate_backward: null pointer");
+  IGN_REQUIRE(B > 0 && C > 1, "gate_backward: bad shape B=%d C=%d (needs C>1)", B, C);
+  return launch_gate_bwd(s, z, go, ge, gs, gz, B, C, use_gate, gv, (cudaStream_t)stream);
+}
+
+int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_t M, int32_t G,
+                               const float* const* W_host, const int32_t* K, const int32_t* L, const int32_t* stride,
+                               float eps, int32_t dist, int32_t precision, float* probs_host, float* dists_host) {
+  IGN_REQUIRE(x_host && W_host && K && L && stride && probs_host && dists_host, "sbm_transform_host: null pointer");
+  IGN_REQUIRE(B > 0 && T > 0 && M > 0 && G > 0, "sbm_transform_host: bad shape");
+  int rc = ign_device_check(-1);
+  if (rc) return rc;
+  const int Tp = padded_len(T);
+  int F = 0, Kmax = 0;
+  size_t wmax = 0;
+  for (int g = 0; g < G; ++g) {
+    IGN_REQUIRE(K[g] > 0 && L[g] > 0 && stride[g] > 0 && T >= L[g], "sbm_transform_host: bad group %d", g);
+    F += K[g] * M; Kmax = K[g] > Kmax ? K[g] : Kmax;
+    size_t w = (size_t)K[g] * M * L[g];
+    wmax = w > wmax ? w : wmax;
+  }
+  cudaStream_t st;
+  IGN_CUDA(cudaStreamCreate(&st));
+  float *x = nullptr, *xn = nullptr, *W = nullptr, *out = nullptr, *Z = nullptr;
+  double* pre = nullptr;
+  int* idx = nullptr;
+  const size_t nx = (size_t)B * T * M, nxn = (size_t)B * M * Tp, nf = (size_t)B * Kmax * M;
+  auto cleanup = [&]() {
+    cudaFree(x); cudaFree(xn); cudaFree(W); cudaFree(out); cudaFree(Z); cudaFree(pre); cudaFree(idx);
+    cudaStreamDestroy(st);
+  };
+#define IGN_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return IGN_ERR_CUDA; } } while (0)
+  IGN_TRY(cudaMalloc(&x, nx * 4));
+  IGN_TRY(cudaMalloc(&xn, nxn * 4));
+  IGN_TRY(cudaMalloc(&W, wmax * 4));
+  IGN_TRY(cudaMalloc(&out, nf * 2 * 4));
+  IGN_TRY(cudaMalloc(&Z, nf * 2 * 4));
+  IGN_TRY(cudaMalloc(&idx, nf * 4));
+  if (dist != IGN_DIST_L1) IGN_TRY(cudaMalloc(&pre, (size_t)B * M * (T + 1) * 2 * sizeof(double)));
+  IGN_TRY(cudaMemcpyAsync(x, x_host, nx * 4, cudaMemcpyHostToDevice, st));
+  rc = launch_instnorm(x, xn, nullptr, nullptr, B, T, M, st);
+  double* pre2 = pre ? pre + (size_t)B * M * (T + 1) : nullptr;
+  if (!rc && pre) rc = launch_prefix(xn, pre, pre2, B, M, T, st);
+  std::vector<float> hp, hd;
+  int col = 0;
+  for (int g = 0; g < G && !rc; ++g) {
+    ign_shapelet_desc d{B, M, T, Tp, K[g], L[g], stride[g], eps, dist, IGN_POOL_RBF_MAX, precision};
+    const size_t n = (size_t)B * K[g] * M;
+    IGN_TRY(cudaMemcpyAsync(W, W_host[g], (size_t)K[g] * M * L[g] * 4, cudaMemcpyHostToDevice, st));
+    rc = ign_shapelet_forward(&d, xn, pre, pre2, W, nullptr, out, out + nf, idx, nullptr, Z, Z + nf, nullptr, st);
+    if (rc) break;
+    hp.resize(n); hd.resize(n);
+    IGN_TRY(cudaMemcpyAsync(hp.data(), out, n * 4, cudaMemcpyDeviceToHost, st));
+    IGN_TRY(cudaMemcpyAsync(hd.data(), out + nf, n * 4, cudaMemcpyDeviceToHost, st));
+    IGN_TRY(cudaStreamSynchronize(st));
+    const int w = K[g] * M;
+    for (int b = 0; b < B; ++b) {   // torch.cat(dim=-1) over groups (Shapelet.py:195-196)
+      memcpy(probs_host + (size_t)b * F + col, hp.data() + (size_t)b * w, (size_t)w * 4);
+      memcpy(dists_host + (size_t)b * F + col, hd.data() + (size_t)b * w, (size_t)w * 4);
+    }
+    col += w;
+  }
+  if (!rc) IGN_TRY(cudaStreamSynchronize(st));
+#undef IGN_TRY
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

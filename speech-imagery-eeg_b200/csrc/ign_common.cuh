@@ -1,0 +1,60 @@
+// Shared declarations for libign_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/ign_b200.h"
+
+namespace ign {
+
+void set_error(const char* fmt, ...);
+
+#define IGN_REQUIRE(cond, ...)                         \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ::ign::set_error(__VA_ARGS__);                   \
+      return IGN_ERR_INVALID;                          \
+    }                                                  \
+  } while (0)
+
+#define IGN_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      ::ign::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                       __LINE__);                                                        \
+      return IGN_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+inline int padded_len(int T) { return round_up(T, 4); }
+inline int num_windows(int T, int L, int s) { return T < L ? 0 : (T - L) / s + 1; }
+inline int padded_windows(int T, int L, int s) { return round_up(num_windows(T, L, s), 4); }
+
+// ---- launchers implemented in the .cu files (all asynchronous on `st`) ----
+int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, int T, int M,
+                    cudaStream_t st);
+int launch_prefix(const float* xn, double* pre1, double* pre2, int B, int M, int T, cudaStream_t st);
+int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
+                             const double* pre2, const float* W, const float* thr, float* p, float* dmin,
+                             int* arg_hard, int* argmin, float* Z, float* S1, float* dstore,
+                             cudaStream_t st);
+size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d);
+int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
+                             const double* pre2, const float* W, const float* g, const int* arg_hard,
+                             const float* dmin, const float* Z, const float* S1, const float* dstore,
+                             float* dW, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int B, int C, int use_gate,
+                    float gv, cudaStream_t st);
+int launch_gate_bwd(const float* s, const float* z, const float* go, const float* ge, float* gs,
+                    float* gz, int B, int C, int use_gate, float gv, cudaStream_t st);
+
+int max_optin_smem();  // per-block opt-in shared memory of the current device (cached)
+int sm_count();
+
+}  // namespace ign

@@ -1,0 +1,810 @@
+// CUDA-core (FP32 pipe) shapelet distance + pooling, forward and backward, all distance modes.
+//
+// This is the engine for IGN_DIST_L1 (the reference default, Shapelet.py:74 — it has no cross term, so
+// it can never run on tensor cores; its roofline is the FP32 ALU pipe) and the exact-fp32 engine
+// (IGN_PREC_FP32) for the cross-term modes.  Reference semantics: Shapelet.py:60-84, :96-111.
+//
+// Data layout
+//   xn     [B,M,Tp]   one series row per (sample, channel), time contiguous
+//   W      [K,M,L]
+//   dstore [B,M,K,Tw] all window distances (training only), time contiguous
+//   pooled outputs [B,K,M]
+//
+// Decomposition: one CTA owns a channel m, a block of KB shapelets and a chunk of the batch.  The
+// K-block's shapelets for that channel stay in shared memory for the CTA's lifetime; series rows
+// stream through NB at a time.
+//   phase 1  register-tiled distance: each thread owns TT consecutive windows x KK shapelets and slides
+//            along the lag axis with a 12-register ring (1 LDS.128 of x + KK broadcast LDS.128 of w per
+//            4 lags for 4*TT*KK accumulate pairs), raw sums go to a shared staging tile
+//   phase 2  one warp per (sample, shapelet) row: raw -> distance (norm terms from the prefix pass),
+//            RBF, soft-max statistics, arg-max/min with first-index ties, warp-shuffle reductions,
+//            coalesced write of d for backward
+// Strides > 1 (only when seq_len >= 3000, Shapelet.py:162) are handled by de-interleaving series and
+// shapelet into `stride` residue classes: sum_l f(x[t*s+l], w[l]) = sum_r sum_q f(x_r[t+q], w_r[q]),
+// i.e. `stride` unit-stride correlations, so the same sliding-window code runs for every stride.
+//
+// Backward (stored-d): phase A turns d + saved statistics into the per-window coefficient
+// a_t = dLoss/dd_t (times the mode's norm factor), phase B contracts it with the series:
+//   L1 : dW[l] = -(1/L) sum_t a_t sign(x[t+l]-w[l])     (sign(0)=0, exact)
+//   dot: G[l]  = sum_t a_t x[t+l], then dW from G and two per-shapelet scalars (finalize kernel)
+// Each thread owns 8 lags x KK shapelets of dW in registers for the whole batch chunk; partial sums are
+// combined in a fixed order (shared memory, then a per-chunk workspace, then the finalize kernel) so the
+// result is bit-reproducible run to run.
+#include "ign_common.cuh"
+
+#include <math.h>
+
+namespace ign {
+namespace {
+
+constexpr int OP_L1 = 0;
+constexpr int OP_DOT = 1;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int LT = 8;  // lags per thread in backward
+
+struct Geo {  // geometry shared by forward and backward
+  int B, M, T, Tp, K, L, s;
+  int Tw;      // number of windows
+  int Ts;      // pitch of dstore rows (Tw rounded to 4)
+  int DP;      // pitch of smem d/c rows (Tw rounded to 8)
+  int XQ;      // pitch of one residue row of x in smem
+  int LQ;      // pitch of one residue row of w in smem (ceil(L/s) rounded to 8)
+  int KK, KB, nkb;
+  int NB;      // series rows resident per pass
+  int bpc;     // samples per batch chunk
+  int dist, pool;
+  float eps;
+};
+
+struct FwdArgs {
+  const float* xn; const double* pre1; const double* pre2; const float* W; const float* thr;
+  float* p; float* dmin; int* arg_hard; int* argmin; float* Z; float* S1; float* dstore;
+};
+
+struct BwdArgs {
+  const float* xn; const double* pre1; const double* pre2; const float* W; const float* g;
+  const int* arg_hard; const float* dmin; const float* Z; const float* S1; const float* dstore;
+  float* part;   // [nchunk][K][M][L]
+  float* scal;   // [nchunk][K][M][2]
+  int nseg, nlb, tlb;   // t-segments per row, l-blocks, l-tiles per l-block
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory staging helpers
+// ------------------------------------------------------------------------------------------------
+
+// Shapelet slab for channel m, shapelets [k0,k0+KB): ws[kl][r][q] = W[k0+kl][m][q*s+r] (centred for
+// pearson), zero padded; wstat[kl] = mode-specific shapelet statistic.
+__device__ void load_shapelets(const Geo& g, const float* __restrict__ W, int m, int k0, float* ws,
+                               float* wstat) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rowlen = g.s * g.LQ;
+  for (int kl = warp; kl < g.KB; kl += kWarps) {
+    const int k = k0 + kl;
+    float* dst = ws + (size_t)kl * rowlen;
+    for (int i = lane; i < rowlen; i += 32) dst[i] = 0.f;
+    float stat = 0.f;
+    if (k < g.K) {
+      const float* src = W + ((size_t)k * g.M + m) * g.L;
+      float s1 = 0.f, s2 = 0.f;
+      for (int l = lane; l < g.L; l += 32) { float w = __ldg(src + l); s1 += w; s2 = fmaf(w, w, s2); }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      float mean = 0.f;
+      if (g.dist == IGN_DIST_PEARSON) {
+        mean = s1 / (float)g.L;
+        float c2 = 0.f;
+        for (int l = lane; l < g.L; l += 32) { float w = __ldg(src + l) - mean; c2 = fmaf(w, w, c2); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        stat = c2;                                   // sum (w-mean)^2
+      } else if (g.dist == IGN_DIST_COSINE) {
+        stat = 1.f / fmaxf(sqrtf(s2), 1e-8f);        // 1/max(||w||,eps)
+      } else {
+        stat = s2;                                   // ||w||^2 (sql2)
+      }
+      __syncwarp();
+      for (int l = lane; l < g.L; l += 32) {
+        const int r = l % g.s, q = l / g.s;
+        dst[r * g.LQ + q] = __ldg(src + l) - mean;
+      }
+    }
+    if (lane == 0) wstat[kl] = stat;
+  }
+}
+
+// Series rows for samples [b0,b0+nb) of channel m, de-interleaved by residue; window statistics.
+__device__ void load_series(const Geo& g, const float* __restrict__ xn, const double* __restrict__ pre1,
+                            const double* __restrict__ pre2, int m, int b0, int nb, float* xs, float* st0,
+                            float* st1) {
+  const int rowlen = g.s * g.XQ;
+  const int total = g.NB * rowlen;
+  if (g.s == 1) {
+    for (int i = threadIdx.x * 4; i < total; i += kThreads * 4) {   // XQ % 4 == 0
+      const int bl = i / rowlen, q = i - bl * rowlen;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bl < nb && q < g.Tp) v = *reinterpret_cast<const float4*>(xn + ((size_t)(b0 + bl) * g.M + m) * g.Tp + q);
+      *reinterpret_cast<float4*>(xs + i) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+      const int bl = i / rowlen, rem = i - bl * rowlen;
+      const int r = rem / g.XQ, q = rem - r * g.XQ;
+      const int t = q * g.s + r;
+      float v = 0.f;
+      if (bl < nb && t < g.T) v = __ldg(xn + ((size_t)(b0 + bl) * g.M + m) * g.Tp + t);
+      xs[i] = v;
+    }
+  }
+  if (g.dist != IGN_DIST_L1) {
+    for (int i = threadIdx.x; i < g.NB * g.DP; i += kThreads) {
+      const int bl = i / g.DP, t = i - bl * g.DP;
+      float a = 0.f, c = 0.f;
+      if (bl < nb && t < g.Tw) {
+        const size_t row = ((size_t)(b0 + bl) * g.M + m) * (g.T + 1);
+        const int j0 = t * g.s;
+        const double sxx = pre2[row + j0 + g.L] - pre2[row + j0];
+        if (g.dist == IGN_DIST_SQL2) {
+          a = (float)sxx;
+        } else if (g.dist == IGN_DIST_COSINE) {
+          a = 1.f / fmaxf(sqrtf((float)sxx), 1e-8f);
+        } else {
+          const double sx = pre1[row + j0 + g.L] - pre1[row + j0];
+          a = (float)fmax(sxx - sx * sx / (double)g.L, 0.0);   // sum (x-mu)^2
+          c = (float)(sx / (double)g.L);                       // mu
+        }
+      }
+      st0[i] = a;
+      if (st1) st1[i] = c;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 1: register-tiled sliding distance
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ float acc_op(float acc, float x, float w) {
+  if (OP == OP_L1) return acc + fabsf(x - w);
+  return fmaf(x, w, acc);
+}
+
+template <int OP, int KK, int TT>
+__device__ __forceinline__ void distance_item(const Geo& g, const float* __restrict__ xrow,
+                                              const float* __restrict__ wbase, float* __restrict__ dout,
+                                              int t0) {
+  constexpr int RING = TT + 4;
+  float acc[TT][KK];
+#pragma unroll
+  for (int j = 0; j < TT; ++j)
+#pragma unroll
+    for (int k = 0; k < KK; ++k) acc[j][k] = 0.f;
+  const int wpitch = g.s * g.LQ;
+
+  for (int r = 0; r < g.s; ++r) {
+    const int Lr = (g.L - r + g.s - 1) / g.s;
+    const float* xr = xrow + r * g.XQ + t0;
+    const float* wr = wbase + r * g.LQ;
+    float xv[RING];
+#pragma unroll
+    for (int j = 0; j < TT; j += 4) {
+      float4 v = *reinterpret_cast<const float4*>(xr + j);
+      xv[j] = v.x; xv[j + 1] = v.y; xv[j + 2] = v.z; xv[j + 3] = v.w;
+    }
+    const int Lr4 = Lr & ~3;
+    int q = 0;
+#define IGN_FWD_STEP(BASE, QQ)                                                              \
+    {                                                                                       \
+      float4 nx = *reinterpret_cast<const float4*>(xr + (QQ) + TT);                         \
+      xv[((BASE) + TT + 0) % RING] = nx.x; xv[((BASE) + TT + 1) % RING] = nx.y;             \
+      xv[((BASE) + TT + 2) % RING] = nx.z; xv[((BASE) + TT + 3) % RING] = nx.w;             \
+      float4 w4[KK];                                                                        \
+      _Pragma("unroll") for (int k = 0; k < KK; ++k)                                        \
+        w4[k] = *reinterpret_cast<const float4*>(wr + k * wpitch + (QQ));                   \
+      _Pragma("unroll") for (int j = 0; j < TT; ++j) {                                      \
+        _Pragma("unroll") for (int k = 0; k < KK; ++k) {                                    \
+          acc[j][k] = acc_op<OP>(acc[j][k], xv[((BASE) + j + 0) % RING], w4[k].x);          \
+          acc[j][k] = acc_op<OP>(acc[j][k], xv[((BASE) + j + 1) % RING], w4[k].y);          \
+          acc[j][k] = acc_op<OP>(acc[j][k], xv[((BASE) + j + 2) % RING], w4[k].z);          \
+          acc[j][k] = acc_op<OP>(acc[j][k], xv[((BASE) + j + 3) % RING], w4[k].w);          \
+        }                                                                                   \
+      }                                                                                     \
+    }
+    if (TT == 8) {
+      for (; q + 12 <= Lr4; q += 12) {
+        IGN_FWD_STEP(0, q) IGN_FWD_STEP(4, q + 4) IGN_FWD_STEP(8, q + 8)
+      }
+      if (q + 4 <= Lr4) { IGN_FWD_STEP(0, q) q += 4; if (q + 4 <= Lr4) { IGN_FWD_STEP(4, q) q += 4; } }
+    } else {
+      for (; q + 8 <= Lr4; q += 8) {
+        IGN_FWD_STEP(0, q) IGN_FWD_STEP(4, q + 4)
+      }
+      if (q + 4 <= Lr4) { IGN_FWD_STEP(0, q) q += 4; }
+    }
+#undef IGN_FWD_STEP
+    for (; q < Lr; ++q) {   // scalar tail (< 4 lags)
+#pragma unroll
+      for (int k = 0; k < KK; ++k) {
+        const float w = wr[k * wpitch + q];
+#pragma unroll
+        for (int j = 0; j < TT; ++j) acc[j][k] = acc_op<OP>(acc[j][k], xr[q + j], w);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KK; ++k)
+#pragma unroll
+    for (int j = 0; j < TT; j += 4)
+      *reinterpret_cast<float4*>(dout + k * g.DP + j) =
+          make_float4(acc[j][k], acc[j + 1][k], acc[j + 2][k], acc[j + 3][k]);
+}
+
+// raw accumulator -> distance
+__device__ __forceinline__ float finish_distance(int dist, float raw, float L, float xstat, float wstat) {
+  switch (dist) {
+    case IGN_DIST_L1: return raw / L;
+    case IGN_DIST_SQL2: return fmaxf((xstat + wstat - 2.f * raw) / L, 0.f);
+    case IGN_DIST_COSINE: return 1.f - raw * xstat * wstat;
+    default: return 1.f - raw / (sqrtf(xstat * wstat) + 1e-8f);
+  }
+}
+
+struct ArgVal { float v; int i; };
+__device__ __forceinline__ ArgVal warp_argmax_first(float v, int i) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  return {v, i};
+}
+__device__ __forceinline__ ArgVal warp_argmin_first(float v, int i) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  return {v, i};
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------------
+template <int OP, int KK, int TT>
+__global__ void __launch_bounds__(kThreads, 2) shapelet_fwd_kernel(const Geo g, const FwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int m = blockIdx.x, k0 = blockIdx.y * g.KB;
+  const int bbeg = blockIdx.z * g.bpc, bend = min(g.B, bbeg + g.bpc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  float* xs = smem;
+  float* ws = xs + g.NB * g.s * g.XQ;
+  float* dbuf = ws + g.KB * g.s * g.LQ;
+  float* st0 = dbuf + g.NB * g.KB * g.DP;
+  float* wstat = st0 + (g.dist != IGN_DIST_L1 ? g.NB * g.DP : 0);
+
+  load_shapelets(g, a.W, m, k0, ws, wstat);
+
+  const int ntile = g.DP / TT;
+  const int nkc = g.KB / KK;
+  const int nitem = g.NB * ntile * nkc;
+  const float Lf = (float)g.L;
+  const float eps = g.eps;
+
+  for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
+    const int nb = min(g.NB, bend - b0);
+    __syncthreads();   // previous pass finished reading xs/dbuf (and ws is written on the first pass)
+    load_series(g, a.xn, a.pre1, a.pre2, m, b0, nb, xs, st0, nullptr);
+    __syncthreads();
+    // ---- phase 1 ----
+    for (int item = threadIdx.x; item < nitem; item += kThreads) {
+      const int tt = item % ntile;
+      const int rest = item / ntile;
+      const int bl = rest % g.NB, kc = rest / g.NB;
+      if (bl >= nb || k0 + kc * KK >= g.K) continue;
+      distance_item<OP, KK, TT>(g, xs + bl * g.s * g.XQ, ws + kc * KK * g.s * g.LQ,
+                                dbuf + ((size_t)bl * g.KB + kc * KK) * g.DP + tt * TT, tt * TT);
+    }
+    __syncthreads();
+    // ---- phase 2: one warp per (sample, shapelet) row ----
+    for (int row = warp; row < g.NB * g.KB; row += kWarps) {
+      const int bl = row / g.KB, kl = row - bl * g.KB;
+      const int b = b0 + bl, k = k0 + kl;
+      if (bl >= nb || k >= g.K) continue;
+      const float* dr = dbuf + (size_t)row * g.DP;
+      const float* xstat = st0 + bl * g.DP;
+      const float wst = wstat[kl];
+      float* dg = a.dstore ? a.dstore + (((size_t)b * g.M + m) * g.K + k) * g.Ts : nullptr;
+      const size_t o = ((size_t)b * g.K + k) * g.M + m;
+
+      float dmn = INFINITY; int imn = 0x7fffffff;
+      if (g.pool == IGN_POOL_RBF_MAX) {
+        float pmx = -1.f; int imx = 0x7fffffff; float Zs = 0.f, S1s = 0.f;
+        for (int t = lane; t < g.Tw; t += 32) {
+          const float d = finish_distance(g.dist, dr[t], Lf, g.dist != IGN_DIST_L1 ? xstat[t] : 0.f, wst);
+          if (dg) dg[t] = d;
+          const float ed = eps * d;
+          const float p = expf(-(ed * ed));              // Shapelet.py:77
+          const float e = expf(p);
+          Zs += e; S1s = fmaf(e, p, S1s);
+          if (p > pmx) { pmx = p; imx = t; }
+          if (d < dmn) { dmn = d; imn = t; }
+        }
+        ArgVal mx = warp_argmax_first(pmx, imx);
+        ArgVal mn = warp_argmin_first(dmn, imn);
+        Zs = warp_sum(Zs); S1s = warp_sum(S1s);
+        if (lane == 0) {
+          a.p[o] = mx.v; a.dmin[o] = mn.v; a.arg_hard[o] = mx.i;
+          if (a.argmin) a.argmin[o] = mn.i;
+          a.Z[o] = Zs; a.S1[o] = S1s;
+        }
+      } else {
+        for (int t = lane; t < g.Tw; t += 32) {
+          const float d = finish_distance(g.dist, dr[t], Lf, g.dist != IGN_DIST_L1 ? xstat[t] : 0.f, wst);
+          if (dg) dg[t] = d;
+          if (d < dmn) { dmn = d; imn = t; }
+        }
+        ArgVal mn = warp_argmin_first(dmn, imn);
+        float Zs = 0.f, S1s = 0.f;
+        for (int t = lane; t < g.Tw; t += 32) {
+          const float d = finish_distance(g.dist, dr[t], Lf, g.dist != IGN_DIST_L1 ? xstat[t] : 0.f, wst);
+          const float e = expf(-(d - mn.v));             // softmin weights, Shapelet.py:106
+          Zs += e; S1s = fmaf(e, d, S1s);
+        }
+        Zs = warp_sum(Zs); S1s = warp_sum(S1s);
+        if (lane == 0) {
+          const float th = a.thr[(size_t)k * g.M + m];
+          a.p[o] = 1.f / (1.f + expf(-(th - mn.v)));     // Shapelet.py:109
+          a.dmin[o] = mn.v; a.arg_hard[o] = mn.i;
+          if (a.argmin) a.argmin[o] = mn.i;
+          a.Z[o] = Zs; a.S1[o] = S1s;
+        }
+      }
+      if (dg && lane < g.Ts - g.Tw) dg[g.Tw + lane] = 0.f;   // pad columns
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward kernel
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__device__ __forceinline__ float bwd_op(float acc, float c, float x, float w) {
+  if (OP == OP_L1) {
+    // acc += c * sign(x - w), sign(0) = 0 (torch abs backward)
+    if (x > w) acc += c;
+    if (x < w) acc -= c;
+    return acc;
+  }
+  return fmaf(c, x, acc);
+}
+
+template <int OP, int KK>
+__global__ void __launch_bounds__(kThreads, 1) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int m = blockIdx.x;
+  const int kblk = blockIdx.y / a.nlb, lblk = blockIdx.y - kblk * a.nlb;
+  const int k0 = kblk * g.KB;
+  const int chunk = blockIdx.z;
+  const int bbeg = chunk * g.bpc, bend = min(g.B, bbeg + g.bpc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  const int nkc = g.KB / KK;
+  const int ntl_all = g.s * g.LQ / LT;                    // l-tiles over all residues
+  const int lt_beg = lblk * a.tlb;
+  const int ntl = min(a.tlb, ntl_all - lt_beg);           // l-tiles of this CTA
+  const int nslot = g.NB * a.nseg;
+  const int nitem = nslot * ntl * nkc;                    // <= kThreads by construction
+
+  float* xs = smem;
+  float* ws = xs + g.NB * g.s * g.XQ;
+  float* cbuf = ws + g.KB * g.s * g.LQ;                   // also reused as the final reduction buffer
+  const int cred = max(g.NB * g.KB * g.DP, kThreads * LT * KK);
+  float* st0 = cbuf + cred;
+  float* st1 = st0 + (g.dist != IGN_DIST_L1 ? g.NB * g.DP : 0);
+  float* wstat = st1 + (g.dist == IGN_DIST_PEARSON ? g.NB * g.DP : 0);
+  float* rowsc = wstat + g.KB;                            // [NB][KB][2]
+  float* scal = rowsc + g.NB * g.KB * 2;                  // [KB][2]
+
+  load_shapelets(g, a.W, m, k0, ws, wstat);
+  if (threadIdx.x < g.KB * 2) scal[threadIdx.x] = 0.f;
+
+  // this thread's fixed tile
+  const bool active = threadIdx.x < nitem;
+  int lt = 0, seg = 0, bl = 0, kc = 0;
+  if (active) {
+    int it = threadIdx.x;
+    lt = it % ntl; it /= ntl;
+    seg = it % a.nseg; it /= a.nseg;
+    bl = it % g.NB; kc = it / g.NB;
+  }
+  const int ltg = lt_beg + lt;
+  const int tiles_per_res = g.LQ / LT;
+  const int r = ltg / tiles_per_res, q0 = (ltg - r * tiles_per_res) * LT;
+  // t-segment [ta,tb), multiples of 4
+  const int seg_len = round_up(ceil_div(g.DP, a.nseg), 4);
+  const int ta = min(seg * seg_len, g.DP), tb = min(ta + seg_len, g.DP);
+
+  float acc[LT][KK];
+  float wreg[LT][KK];
+#pragma unroll
+  for (int i = 0; i < LT; ++i)
+#pragma unroll
+    for (int k = 0; k < KK; ++k) acc[i][k] = 0.f;
+  __syncthreads();
+  if (OP == OP_L1) {
+#pragma unroll
+    for (int i = 0; i < LT; ++i)
+#pragma unroll
+      for (int k = 0; k < KK; ++k)
+        wreg[i][k] = active ? ws[((size_t)(kc * KK + k) * g.s + r) * g.LQ + q0 + i] : 0.f;
+  }
+
+  const float eps = g.eps;
+  const float m2e2 = -2.f * eps * eps;
+
+  for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
+    const int nb = min(g.NB, bend - b0);
+    __syncthreads();
+    load_series(g, a.xn, a.pre1, a.pre2, m, b0, nb, xs, st0, g.dist == IGN_DIST_PEARSON ? st1 : nullptr);
+    __syncthreads();
+    // ---- phase A: coefficients a_t = dLoss/dd_t * (mode factor), one warp per (sample, shapelet) row
+    for (int row = warp; row < g.NB * g.KB; row += kWarps) {
+      const int rbl = row / g.KB, kl = row - rbl * g.KB;
+      const int b = b0 + rbl, k = k0 + kl;
+      float* cr = cbuf + (size_t)row * g.DP;
+      float sc0 = 0.f, sc1 = 0.f;
+      if (rbl < nb && k < g.K) {
+        const size_t o = ((size_t)b * g.K + k) * g.M + m;
+        const float gk = a.g[o];
+        const int ih = a.arg_hard[o];
+        const float Zr = a.Z[o];
+        const float bar = a.S1[o] / Zr;
+        const float dm = a.dmin[o];
+        const float wst = wstat[kl];
+        const float* dg = a.dstore + (((size_t)b * g.M + m) * g.K + k) * g.Ts;
+        for (int t = lane; t < g.DP; t += 32) {
+          float coef = 0.f;
+          if (t < g.Tw) {
+            const float d = dg[t];
+            float c;
+            if (g.pool == IGN_POOL_RBF_MAX) {
+              const float ed = eps * d;
+              const float p = expf(-(ed * ed));
+              const float soft = expf(p) / Zr;
+              c = gk * ((t == ih ? 1.f : 0.f) + soft * (p - bar)) * p * (m2e2 * d);
+            } else {
+              const float soft = expf(-(d - dm)) / Zr;
+              c = gk * ((t == ih ? 1.f : 0.f) - soft * (d - bar));
+            }
+            if (g.dist == IGN_DIST_L1) {
+              coef = c;
+            } else if (g.dist == IGN_DIST_SQL2) {
+              coef = c; sc0 += c;
+            } else if (g.dist == IGN_DIST_COSINE) {
+              coef = c * st0[rbl * g.DP + t];
+              sc0 = fmaf(c, 1.f - d, sc0);
+            } else {
+              const float sxc = st0[rbl * g.DP + t], mu = st1[rbl * g.DP + t];
+              const float root = sqrtf(sxc * wst), D = root + 1e-8f;
+              coef = c / D;
+              sc0 = fmaf(coef, mu, sc0);
+              sc1 += c * (1.f - d) * sxc / (root * D);
+            }
+          }
+          cr[t] = coef;
+        }
+      } else {
+        for (int t = lane; t < g.DP; t += 32) cr[t] = 0.f;
+      }
+      sc0 = warp_sum(sc0); sc1 = warp_sum(sc1);
+      if (lane == 0) { rowsc[row * 2] = sc0; rowsc[row * 2 + 1] = sc1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < g.KB * 2) {   // fixed-order accumulation of the per-shapelet scalars
+      const int kl = threadIdx.x >> 1, j = threadIdx.x & 1;
+      float s = scal[threadIdx.x];
+      for (int rbl = 0; rbl < g.NB; ++rbl) s += rowsc[(rbl * g.KB + kl) * 2 + j];
+      scal[threadIdx.x] = s;
+    }
+    // ---- phase B: contraction over windows, sliding along t with a 12-register ring of x
+    if (active && bl < nb && ta < tb) {
+      const float* xr = xs + ((size_t)bl * g.s + r) * g.XQ + q0;
+      const float* cb = cbuf + ((size_t)bl * g.KB + kc * KK) * g.DP;
+      float xv[12];
+      {
+        float4 v0 = *reinterpret_cast<const float4*>(xr + ta);
+        float4 v1 = *reinterpret_cast<const float4*>(xr + ta + 4);
+        xv[0] = v0.x; xv[1] = v0.y; xv[2] = v0.z; xv[3] = v0.w;
+        xv[4] = v1.x; xv[5] = v1.y; xv[6] = v1.z; xv[7] = v1.w;
+      }
+#define IGN_BWD_STEP(BASE, TQ)                                                               \
+      {                                                                                      \
+        float4 nx = *reinterpret_cast<const float4*>(xr + (TQ) + 8);                         \
+        xv[((BASE) + 8) % 12] = nx.x; xv[((BASE) + 9) % 12] = nx.y;                          \
+        xv[((BASE) + 10) % 12] = nx.z; xv[((BASE) + 11) % 12] = nx.w;                        \
+        float4 c4[KK];                                                                       \
+        _Pragma("unroll") for (int k = 0; k < KK; ++k)                                       \
+          c4[k] = *reinterpret_cast<const float4*>(cb + k * g.DP + (TQ));                    \
+        _Pragma("unroll") for (int i = 0; i < LT; ++i) {                                     \
+          _Pragma("unroll") for (int k = 0; k < KK; ++k) {                                   \
+            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].x, xv[((BASE) + i + 0) % 12], wreg[i][k]); \
+            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].y, xv[((BASE) + i + 1) % 12], wreg[i][k]); \
+            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].z, xv[((BASE) + i + 2) % 12], wreg[i][k]); \
+            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].w, xv[((BASE) + i + 3) % 12], wreg[i][k]); \
+          }                                                                                  \
+        }                                                                                    \
+      }
+      int t = ta;
+      for (; t + 12 <= tb; t += 12) {
+        IGN_BWD_STEP(0, t) IGN_BWD_STEP(4, t + 4) IGN_BWD_STEP(8, t + 8)
+      }
+      if (t + 4 <= tb) { IGN_BWD_STEP(0, t) t += 4; if (t + 4 <= tb) { IGN_BWD_STEP(4, t) t += 4; } }
+#undef IGN_BWD_STEP
+    }
+  }
+
+  // ---- fixed-order reduction over (sample slot, t-segment), then one partial per chunk ----
+  __syncthreads();
+  float* red = cbuf;
+  if (active) {
+    const int slot = bl * a.nseg + seg;
+    float* dst = red + (((size_t)(kc * ntl + lt)) * nslot + slot) * (LT * KK);
+#pragma unroll
+    for (int i = 0; i < LT; ++i)
+#pragma unroll
+      for (int k = 0; k < KK; ++k) dst[i * KK + k] = acc[i][k];
+  }
+  __syncthreads();
+  const int nout = nkc * ntl * LT * KK;
+  for (int oidx = threadIdx.x; oidx < nout; oidx += kThreads) {
+    const int ik = oidx % (LT * KK);
+    const int tile = oidx / (LT * KK);            // kc*ntl + lt
+    const int okc = tile / ntl, olt = tile - okc * ntl;
+    const int i = ik / KK, kk = ik - i * KK;
+    const float* src = red + (size_t)tile * nslot * (LT * KK) + ik;
+    float s = 0.f;
+    for (int sl = 0; sl < nslot; ++sl) s += src[(size_t)sl * (LT * KK)];
+    const int oltg = lt_beg + olt;
+    const int orr = oltg / tiles_per_res, oq = (oltg - orr * tiles_per_res) * LT + i;
+    const int l = oq * g.s + orr;
+    const int k = k0 + okc * KK + kk;
+    if (k < g.K && l < g.L && oq < (g.L - orr + g.s - 1) / g.s)
+      a.part[(((size_t)chunk * g.K + k) * g.M + m) * g.L + l] = s;
+  }
+  if (lblk == 0 && threadIdx.x < g.KB * 2) {
+    const int kl = threadIdx.x >> 1, j = threadIdx.x & 1;
+    if (k0 + kl < g.K) a.scal[(((size_t)chunk * g.K + k0 + kl) * g.M + m) * 2 + j] = scal[threadIdx.x];
+  }
+}
+
+// dW[k,m,:] from the per-chunk partial contractions and scalars.  One warp per (k,m) row.
+__global__ void __launch_bounds__(256) shapelet_bwd_finalize(const float* __restrict__ W,
+                                                            const float* __restrict__ part,
+                                                            const float* __restrict__ scal,
+                                                            float* __restrict__ dW, int K, int M, int L,
+                                                            int nchunk, int dist) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= K * M) return;
+  const float* w = W + (size_t)row * L;
+  float s0 = 0.f, s1 = 0.f;
+  if (dist != IGN_DIST_L1) {
+    for (int c = 0; c < nchunk; ++c) {
+      s0 += scal[((size_t)c * K * M + row) * 2];
+      s1 += scal[((size_t)c * K * M + row) * 2 + 1];
+    }
+  }
+  float mean = 0.f, inv_nw = 0.f;
+  if (dist == IGN_DIST_COSINE || dist == IGN_DIST_PEARSON) {
+    float a = 0.f, b2 = 0.f;
+    for (int l = lane; l < L; l += 32) { float v = w[l]; a += v; b2 = fmaf(v, v, b2); }
+    a = warp_sum(a); b2 = warp_sum(b2);
+    mean = a / (float)L;
+    inv_nw = 1.f / fmaxf(sqrtf(b2), 1e-8f);
+  }
+  const float Lf = (float)L;
+  for (int l = lane; l < L; l += 32) {
+    float G = 0.f;
+    for (int c = 0; c < nchunk; ++c) G += part[((size_t)c * K * M + row) * L + l];
+    float o;
+    if (dist == IGN_DIST_L1) o = -G / Lf;
+    else if (dist == IGN_DIST_SQL2) o = (2.f / Lf) * (w[l] * s0 - G);
+    else if (dist == IGN_DIST_COSINE) o = -G * inv_nw + w[l] * s0 * inv_nw * inv_nw;
+    else o = -(G - s0) + (w[l] - mean) * s1;
+    dW[(size_t)row * L + l] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side planning
+// ------------------------------------------------------------------------------------------------
+int pick_kk(int K) {
+  if (K % 5 == 0) return 5;
+  if (K % 4 == 0 || K < 4) return 4;
+  return (round_up(K, 5) - K <= round_up(K, 4) - K) ? 5 : 4;
+}
+
+bool base_geo(const ign_shapelet_desc& d, Geo& g) {
+  g.B = d.B; g.M = d.M; g.T = d.T; g.Tp = d.Tp; g.K = d.K; g.L = d.L; g.s = d.stride;
+  g.Tw = num_windows(d.T, d.L, d.stride);
+  g.Ts = round_up(g.Tw, 4);
+  g.DP = round_up(g.Tw, 8);
+  const int Lq = ceil_div(d.L, d.stride);
+  g.LQ = round_up(Lq, 8);
+  g.XQ = round_up(max(g.DP + g.LQ + 8, ceil_div(d.T, d.stride) + 8), 4);
+  g.KK = pick_kk(d.K);
+  g.dist = d.dist; g.pool = d.pool; g.eps = d.eps;
+  return g.Tw > 0;
+}
+
+size_t fwd_smem_floats(const Geo& g, int NB, int KB) {
+  size_t f = (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + (size_t)NB * KB * g.DP + KB;
+  if (g.dist != IGN_DIST_L1) f += (size_t)NB * g.DP;
+  return f;
+}
+
+// fraction of issued lanes doing useful work when `nitem` items are spread over 32-lane warps
+double lane_eff(int nitem) { return (double)nitem / (double)(ceil_div(nitem, 32) * 32); }
+
+int plan_chunks(const Geo& g, int ctas_per_bchunk, int NB) {
+  const int target = 16 * sm_count();
+  int nchunk = max(1, ceil_div(target, max(1, ctas_per_bchunk)));
+  nchunk = min(nchunk, ceil_div(g.B, NB));
+  int bpc = round_up(ceil_div(g.B, nchunk), NB);
+  return bpc;
+}
+
+bool plan_fwd(Geo& g, int TT, size_t& smem_bytes) {
+  const size_t cap_soft = 100 * 1024, cap_hard = (size_t)max_optin_smem() - 1024;
+  const int Kpad = round_up(g.K, g.KK);
+  int KB = min(Kpad, 8 * g.KK);
+  while (KB > g.KK && fwd_smem_floats(g, 1, KB) * 4 > cap_soft) KB -= g.KK;
+  if (fwd_smem_floats(g, 1, KB) * 4 > cap_hard) return false;
+  const size_t cap = fwd_smem_floats(g, 1, KB) * 4 > cap_soft ? cap_hard : cap_soft;
+  const int ntile = g.DP / TT, nkc = KB / g.KK;
+  int best = 1; double beff = -1.0;
+  for (int NB = 1; NB <= min(g.B, 64); ++NB) {
+    if (fwd_smem_floats(g, NB, KB) * 4 > cap) break;
+    double e = lane_eff(NB * ntile * nkc);
+    if (e > beff + 0.005) { beff = e; best = NB; }
+  }
+  g.KB = KB; g.nkb = ceil_div(Kpad, KB); g.NB = best;
+  g.bpc = plan_chunks(g, g.M * g.nkb, best);
+  smem_bytes = fwd_smem_floats(g, best, KB) * 4;
+  return true;
+}
+
+struct BwdPlan { int nseg, nlb, tlb, nchunk; size_t smem_bytes; };
+
+size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
+  size_t cred = (size_t)NB * KB * g.DP;
+  if (cred < (size_t)kThreads * LT * g.KK) cred = (size_t)kThreads * LT * g.KK;
+  size_t f = (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + cred + KB + (size_t)NB * KB * 2 + KB * 2;
+  if (g.dist != IGN_DIST_L1) f += (size_t)NB * g.DP;
+  if (g.dist == IGN_DIST_PEARSON) f += (size_t)NB * g.DP;
+  return f;
+}
+
+bool plan_bwd(Geo& g, BwdPlan& bp) {
+  const size_t cap = (size_t)max_optin_smem() - 1024;
+  const size_t cap_soft = 100 * 1024;
+  const int Kpad = round_up(g.K, g.KK);
+  const int ntl_all = g.s * g.LQ / LT;
+  // shapelet block: as many as fit the thread budget with at least one full l sweep, capped by smem
+  int KB = min(Kpad, 8 * g.KK);
+  while (KB > g.KK && ((KB / g.KK) * min(ntl_all, kThreads) > kThreads ||
+                       bwd_smem_floats(g, 1, KB) * 4 > cap_soft)) KB -= g.KK;
+  if (bwd_smem_floats(g, 1, KB) * 4 > cap) return false;
+  const int nkc = KB / g.KK;
+  int tlb = min(ntl_all, kThreads / nkc);
+  int nlb = ceil_div(ntl_all, tlb);
+  tlb = ceil_div(ntl_all, nlb);   // balance l-blocks
+  const int slots = max(1, kThreads / (tlb * nkc));   // (sample, t-segment) slots per CTA
+  // split slots between resident samples and t-segments: prefer more samples until smem runs out
+  int bestNB = 1, bestSeg = 1; double beff = -1.0;
+  for (int NB = 1; NB <= min(min(g.B, slots), 32); ++NB) {
+    if (bwd_smem_floats(g, NB, KB) * 4 > (NB == 1 ? cap : cap_soft)) break;
+    int nseg = max(1, slots / NB);
+    nseg = min(nseg, max(1, g.DP / 32));            // keep segments >= 32 windows
+    double e = lane_eff(NB * nseg * tlb * nkc) * ((double)(NB * nseg * tlb * nkc) / kThreads);
+    if (e > beff + 0.005) { beff = e; bestNB = NB; bestSeg = nseg; }
+  }
+  g.KB = KB; g.nkb = ceil_div(Kpad, KB); g.NB = bestNB;
+  bp.nseg = bestSeg; bp.nlb = nlb; bp.tlb = tlb;
+  g.bpc = plan_chunks(g, g.M * g.nkb * nlb, bestNB);
+  bp.nchunk = ceil_div(g.B, g.bpc);
+  bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
+  return true;
+}
+
+template <typename Kern>
+int set_smem(Kern kern, size_t bytes) {
+  IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return IGN_OK;
+}
+
+template <int OP, int KK, int TT>
+int run_fwd(const Geo& g, const FwdArgs& a, size_t smem, cudaStream_t st) {
+  int rc = set_smem(shapelet_fwd_kernel<OP, KK, TT>, smem);
+  if (rc) return rc;
+  dim3 grid(g.M, g.nkb, ceil_div(g.B, g.bpc));
+  shapelet_fwd_kernel<OP, KK, TT><<<grid, kThreads, smem, st>>>(g, a);
+  IGN_CUDA(cudaGetLastError());
+  return IGN_OK;
+}
+
+template <int OP, int KK>
+int run_bwd(const Geo& g, const BwdArgs& a, const BwdPlan& bp, cudaStream_t st) {
+  int rc = set_smem(shapelet_bwd_kernel<OP, KK>, bp.smem_bytes);
+  if (rc) return rc;
+  dim3 grid(g.M, g.nkb * bp.nlb, bp.nchunk);
+  shapelet_bwd_kernel<OP, KK><<<grid, kThreads, bp.smem_bytes, st>>>(g, a);
+  IGN_CUDA(cudaGetLastError());
+  return IGN_OK;
+}
+
+}  // namespace
+
+int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
+                             const double* pre2, const float* W, const float* thr, float* p, float* dmin,
+                             int* arg_hard, int* argmin, float* Z, float* S1, float* dstore,
+                             cudaStream_t st) {
+  Geo g;
+  if (!base_geo(d, g)) { set_error("shapelet_forward: T=%d < L=%d (unfold would raise)", d.T, d.L); return IGN_ERR_INVALID; }
+  const int TT = g.Tw >= 64 ? 8 : 4;
+  if (TT == 4) g.DP = round_up(g.Tw, 8);   // pitch stays a multiple of 8 (also a multiple of 4)
+  size_t smem = 0;
+  if (!plan_fwd(g, TT, smem)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  FwdArgs a{xn, pre1, pre2, W, thr, p, dmin, arg_hard, argmin, Z, S1, dstore};
+  const bool l1 = d.dist == IGN_DIST_L1;
+#define IGN_DISPATCH(OPV, KKV, TTV) return run_fwd<OPV, KKV, TTV>(g, a, smem, st)
+  if (l1) {
+    if (g.KK == 5) { if (TT == 8) IGN_DISPATCH(OP_L1, 5, 8); else IGN_DISPATCH(OP_L1, 5, 4); }
+    else           { if (TT == 8) IGN_DISPATCH(OP_L1, 4, 8); else IGN_DISPATCH(OP_L1, 4, 4); }
+  } else {
+    if (g.KK == 5) { if (TT == 8) IGN_DISPATCH(OP_DOT, 5, 8); else IGN_DISPATCH(OP_DOT, 5, 4); }
+    else           { if (TT == 8) IGN_DISPATCH(OP_DOT, 4, 8); else IGN_DISPATCH(OP_DOT, 4, 4); }
+  }
+#undef IGN_DISPATCH
+  return IGN_OK;
+}
+
+size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
+  Geo g; BwdPlan bp;
+  if (!base_geo(d, g) || !plan_bwd(g, bp)) return 0;
+  return ((size_t)bp.nchunk * d.K * d.M * d.L + (size_t)bp.nchunk * d.K * d.M * 2) * sizeof(float);
+}
+
+int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
+                             const double* pre2, const float* W, const float* gr, const int* arg_hard,
+                             const float* dmin, const float* Z, const float* S1, const float* dstore,
+                             float* dW, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Geo g; BwdPlan bp;
+  if (!base_geo(d, g)) { set_error("shapelet_backward: T=%d < L=%d", d.T, d.L); return IGN_ERR_INVALID; }
+  if (!plan_bwd(g, bp)) { set_error("shapelet_backward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  const size_t npart = (size_t)bp.nchunk * d.K * d.M * d.L;
+  const size_t need = (npart + (size_t)bp.nchunk * d.K * d.M * 2) * sizeof(float);
+  if (ws_bytes < need) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, need); return IGN_ERR_INVALID; }
+  BwdArgs a{xn, pre1, pre2, W, gr, arg_hard, dmin, Z, S1, dstore,
+            reinterpret_cast<float*>(ws), reinterpret_cast<float*>(ws) + npart, bp.nseg, bp.nlb, bp.tlb};
+  int rc;
+  const bool l1 = d.dist == IGN_DIST_L1;
+  if (l1) rc = g.KK == 5 ? run_bwd<OP_L1, 5>(g, a, bp, st) : run_bwd<OP_L1, 4>(g, a, bp, st);
+  else    rc = g.KK == 5 ? run_bwd<OP_DOT, 5>(g, a, bp, st) : run_bwd<OP_DOT, 4>(g, a, bp, st);
+  if (rc) return rc;
+  shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, a.part, a.scal, dW, d.K, d.M, d.L,
+                                                              bp.nchunk, d.dist);
+  IGN_CUDA(cudaGetLastError());
+  return IGN_OK;
+}
+
+}  // namespace ign

@@ -1,0 +1,248 @@
+"""torch.autograd glue over the C ABI (include/ign_b200.h).  PyTorch owns every buffer; the kernels are
+launched on torch's current CUDA stream through ctypes.  CUDA-only: CPU tensors raise.
+
+Replaces the eager op chains of the reference:
+  instance_norm      <- Shapelet.py:186-187
+  shapelet_transform <- Shapelet.py:61-84 (Shapelet.forward) and :97-111 (DistThresholdShapelet.forward)
+  gini_gate          <- InterpGN.py:44-52
+"""
+from __future__ import annotations
+
+from ctypes import byref
+from typing import Optional, Tuple
+
+import torch
+
+from . import ign_cabi as C
+
+_DIST_OF_FLAG = {"cosine": "cosine", "pearson": "pearson"}
+
+
+def resolve_dist(distance_func: str, memory_efficient: bool) -> str:
+    """Flag -> arithmetic exactly as Shapelet.forward dispatches (Shapelet.py:64-74):
+    'cosine' / 'pearson' by name; anything else is the L1 mean ('euclidean' in the reference's
+    vocabulary) unless memory_efficient selects the squared-L2 arithmetic of Shapelet.py:28."""
+    if distance_func in _DIST_OF_FLAG:
+        return _DIST_OF_FLAG[distance_func]
+    return "sql2" if memory_efficient else "l1"
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: the ign_b200 hot path has no CPU fallback "
+                           "(got device %s)" % (name, t.device))
+
+
+_checked_devices = set()
+
+
+def _check_device(dev: torch.device):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        C.check(C.lib.ign_device_check(idx), "ign_device_check")
+        _checked_devices.add(idx)
+
+
+class SeriesPack:
+    """Instance-normalised series in the kernels' layout: xn [B,M,Tp] fp32 (time contiguous, zero padded
+    to a multiple of 4) plus lazily built fp64 window prefix sums shared by all length groups."""
+
+    def __init__(self, xn: torch.Tensor, T: int):
+        self.xn = xn
+        self.T = T
+        self._pre = None
+
+    @property
+    def B(self):
+        return self.xn.shape[0]
+
+    @property
+    def M(self):
+        return self.xn.shape[1]
+
+    @property
+    def Tp(self):
+        return self.xn.shape[2]
+
+    def prefix(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._pre is None:
+            B, M, T = self.B, self.M, self.T
+            pre = torch.empty((2, B, M, T + 1), dtype=torch.float64, device=self.xn.device)
+            with torch.cuda.device(self.xn.device):
+                C.check(C.lib.ign_window_prefix(_ptr(self.xn), _ptr(pre[0]), _ptr(pre[1]), B, M, T, _stream()),
+                        "ign_window_prefix")
+            self._pre = (pre[0], pre[1])
+        return self._pre
+
+    @staticmethod
+    def from_channel_major(x: torch.Tensor) -> "SeriesPack":
+        """Wrap an already-normalised [B,M,T] tensor (what Shapelet.forward receives, Shapelet.py:60)."""
+        _require_cuda(x, "x")
+        B, M, T = x.shape
+        Tp = C.padded_len(T)
+        xn = x.detach().to(torch.float32)
+        if Tp != T or not xn.is_contiguous():
+            buf = torch.zeros((B, M, Tp), dtype=torch.float32, device=x.device)
+            buf[:, :, :T] = xn
+            xn = buf
+        return SeriesPack(xn, T)
+
+
+def instance_norm(x: torch.Tensor) -> SeriesPack:
+    """x [B,T,M] -> SeriesPack(xn [B,M,Tp]).  Shapelet.py:186-187.  No gradient w.r.t. x is produced:
+    in the reference's training loop the raw batch never requires grad (experiment_classification.py:315)."""
+    _require_cuda(x, "x")
+    if x.dim() != 3:
+        raise RuntimeError("instance_norm expects [B,T,M], got %s" % (tuple(x.shape),))
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("ign_b200: gradient w.r.t. the input series is not implemented")
+    _check_device(x.device)
+    x = x.detach().to(torch.float32).contiguous()
+    B, T, M = x.shape
+    xn = torch.empty((B, M, C.padded_len(T)), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        C.check(C.lib.ign_instnorm_forward(_ptr(x), _ptr(xn), None, None, B, T, M, _stream()),
+                "ign_instnorm_forward")
+    return SeriesPack(xn, T)
+
+
+class _ShapeletTransform(torch.autograd.Function):
+    """One length group: window distance + pooling over time, with the saved-statistics backward."""
+
+    @staticmethod
+    def forward(ctx, W, threshold, pack: SeriesPack, stride, eps, dist, pool, precision):
+        xn = pack.xn
+        B, M, T, Tp = pack.B, pack.M, pack.T, pack.Tp
+        K, M2, L = W.shape
+        if M2 != M:
+            raise RuntimeError("shapelet channels %d != series channels %d" % (M2, M))
+        Wc = W.detach().to(torch.float32).contiguous()
+        thr = None
+        if pool == "lts_min":
+            thr = threshold.detach().to(torch.float32).reshape(K, M).contiguous()
+        desc = C.ShapeletDesc(B, M, T, Tp, K, L, int(stride), float(eps), C.DIST[dist], C.POOL[pool],
+                              C.PRECISION[precision])
+        pre1 = pre2 = None
+        if dist != "l1":
+            pre1, pre2 = pack.prefix()
+        need_grad = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        dev = xn.device
+        out = torch.empty((4, B, K, M), dtype=torch.float32, device=dev)     # p, dmin, Z, S1
+        idx = torch.empty((2, B, K, M), dtype=torch.int32, device=dev)      # arg_hard, argmin
+        dstore = None
+        if need_grad:
+            Tw = C.padded_windows(T, L, int(stride))
+            dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            C.check(C.lib.ign_shapelet_forward(byref(desc), _ptr(xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(thr),
+                                               _ptr(out[0]), _ptr(out[1]), _ptr(idx[0]), _ptr(idx[1]),
+                                               _ptr(out[2]), _ptr(out[3]), _ptr(dstore), _stream()),
+                    "ign_shapelet_forward")
+        ctx.set_materialize_grads(False)
+        ctx.desc = desc
+        ctx.pool = pool
+        ctx.pack = pack
+        ctx.thr_shape = None if threshold is None else threshold.shape
+        if need_grad:
+            ctx.save_for_backward(Wc, out, idx, dstore)
+        ctx.mark_non_differentiable(idx)
+        return out[0], out[1], idx
+
+    @staticmethod
+    def backward(ctx, g_p, g_dmin, _g_idx):
+        Wc, out, idx, dstore = ctx.saved_tensors
+        desc, pack = ctx.desc, ctx.pack
+        # d.min() (Shapelet.py:84) feeds reporting only; a gradient arriving there follows the hard argmin
+        # and is not produced by any loss of the reference (experiment_classification.py:325-329).
+        # (grads are not materialised, so None here means "unused" and costs no host sync.)
+        if g_dmin is not None:
+            raise NotImplementedError("ign_b200: gradient through the reported min distance is not implemented")
+        if g_p is None:
+            return (None,) * 8
+        g = g_p.to(torch.float32).contiguous()
+        dthr = None
+        if ctx.pool == "lts_min":
+            p = out[0]
+            sig = p * (1.0 - p)                         # d sigmoid(thr - min_d)
+            if ctx.needs_input_grad[1]:
+                dthr = (g * sig).sum(dim=0).reshape(ctx.thr_shape)
+            g = (-g * sig).contiguous()                 # dLoss/d(min_d)
+        dW = None
+        if ctx.needs_input_grad[0]:
+            pre1 = pre2 = None
+            if desc.dist != C.DIST["l1"]:
+                pre1, pre2 = pack.prefix()
+            nbytes = C.lib.ign_shapelet_backward_workspace(byref(desc))
+            ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=g.device)
+            dW = torch.empty_like(Wc)
+            with torch.cuda.device(g.device):
+                C.check(C.lib.ign_shapelet_backward(byref(desc), _ptr(pack.xn), _ptr(pre1), _ptr(pre2), _ptr(Wc),
+                                                    _ptr(g), _ptr(idx[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
+                                                    _ptr(dstore), _ptr(dW), _ptr(ws), int(nbytes), _stream()),
+                        "ign_shapelet_backward")
+        return dW, dthr, None, None, None, None, None, None
+
+
+def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: float = 1.0, dist: str = "l1",
+                       pool: str = "rbf_max", threshold: Optional[torch.Tensor] = None, precision: str = "fp32"):
+    """Returns (p [B,K,M], dmin [B,K,M], idx [2,B,K,M] int32 = (hard index, argmin_t d))."""
+    _require_cuda(W, "shapelet weights")
+    _check_device(W.device)
+    if pool == "lts_min" and threshold is None:
+        raise RuntimeError("lts_min pooling needs a threshold")
+    # fp32 in / fp32 out regardless of autocast: the reference's distance math stays fp32 under bf16
+    # autocast as well.
+    with torch.autocast(device_type="cuda", enabled=False):
+        return _ShapeletTransform.apply(W, threshold, pack, stride, eps, dist, pool, precision)
+
+
+class _GiniGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sbm_out, deep_out, gating_value):
+        s = sbm_out.detach().to(torch.float32).contiguous()
+        z = deep_out.detach().to(torch.float32).contiguous()
+        B, Cn = s.shape
+        out = torch.empty_like(s)
+        eta = torch.empty((B, 1), dtype=torch.float32, device=s.device)
+        use_gate = gating_value is not None
+        gv = float(gating_value) if use_gate else 0.0
+        with torch.cuda.device(s.device):
+            C.check(C.lib.ign_gate_forward(_ptr(s), _ptr(z), _ptr(out), _ptr(eta), B, Cn, int(use_gate), gv, _stream()),
+                    "ign_gate_forward")
+        ctx.save_for_backward(s, z)
+        ctx.gate = (use_gate, gv)
+        ctx.in_dtypes = (sbm_out.dtype, deep_out.dtype)
+        return out, eta
+
+    @staticmethod
+    def backward(ctx, g_out, g_eta):
+        s, z = ctx.saved_tensors
+        B, Cn = s.shape
+        go = g_out.to(torch.float32).contiguous()
+        ge = None if g_eta is None else g_eta.to(torch.float32).contiguous()
+        gs = torch.empty_like(s)
+        gz = torch.empty_like(z)
+        use_gate, gv = ctx.gate
+        with torch.cuda.device(s.device):
+            C.check(C.lib.ign_gate_backward(_ptr(s), _ptr(z), _ptr(go), _ptr(ge), _ptr(gs), _ptr(gz), B, Cn,
+                                            int(use_gate), gv, _stream()), "ign_gate_backward")
+        return gs.to(ctx.in_dtypes[0]), gz.to(ctx.in_dtypes[1]), None
+
+
+def gini_gate(sbm_out: torch.Tensor, deep_out: torch.Tensor, gating_value: Optional[float] = None):
+    """InterpGN.py:44-52 fused: returns (out [B,C], eta [B,1]); computed in fp32."""
+    _require_cuda(sbm_out, "sbm_out")
+    _require_cuda(deep_out, "deep_out")
+    if sbm_out.shape != deep_out.shape or sbm_out.dim() != 2:
+        raise RuntimeError("gini_gate expects two [B,C] tensors, got %s and %s"
+                           % (tuple(sbm_out.shape), tuple(deep_out.shape)))
+    _check_device(sbm_out.device)
+    return _GiniGate.apply(sbm_out, deep_out, gating_value)

@@ -1,0 +1,67 @@
+"""GPU: the C ABI driven with plain host buffers (numpy + ctypes only — no torch types cross the
+boundary), checked against the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import ign_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("flag,dist", [("euclidean", 0), ("cosine", 2), ("pearson", 3)])
+def test_sbm_transform_host(flag, dist):
+    from layers import ign_cabi as C
+    rng = np.random.default_rng(7)
+    B, T, M = 5, 120, 7
+    Ks, Ls, strides = [5, 5, 3], [12, 24, 60], [1, 1, 1]
+    x = rng.standard_normal((B, T, M)).astype(np.float32)
+    Ws = [rng.standard_normal((k, M, l)).astype(np.float32) for k, l in zip(Ks, Ls)]
+    F = sum(k * M for k in Ks)
+    probs = np.zeros((B, F), np.float32)
+    dists = np.zeros((B, F), np.float32)
+    ptrs = (ctypes.c_void_p * len(Ws))(*[w.ctypes.data for w in Ws])
+    i32 = lambda a: (ctypes.c_int32 * len(a))(*a)
+    rc = C.lib.ign_sbm_transform_host(x.ctypes.data, B, T, M, len(Ws), ptrs, i32(Ks), i32(Ls), i32(strides),
+                                      1.0, dist, 0, probs.ctypes.data, dists.ctypes.data)
+    assert rc == 0, C.last_error()
+    mode = {"euclidean": O.DIST_L1, "cosine": O.DIST_COS, "pearson": O.DIST_PEARSON}[flag]
+    xn = O.instance_norm(torch.from_numpy(x))
+    ps, ds = [], []
+    for W, s in zip(Ws, strides):
+        o = O.shapelet_forward(xn, torch.from_numpy(W), s, 1.0, mode)
+        ps.append(o.p); ds.append(o.dmin)
+    np.testing.assert_allclose(probs, torch.cat(ps, -1).numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(dists, torch.cat(ds, -1).numpy(), rtol=2e-5, atol=2e-6)
+
+
+def test_instnorm_and_prefix_kernels():
+    from layers.shapelet_ops import instance_norm
+    torch.manual_seed(3)
+    for (B, T, M) in [(3, 29, 12), (2, 1000, 125), (4, 130, 33)]:
+        x = torch.randn(B, T, M) * 3 + 1.5
+        pack = instance_norm(x.cuda())
+        ref = O.instance_norm(x)
+        torch.testing.assert_close(pack.xn[:, :, :T].cpu(), ref, rtol=2e-5, atol=2e-6)
+        assert float(pack.xn[:, :, T:].abs().sum()) == 0.0
+        p1, p2 = pack.prefix()
+        r1 = torch.cumsum(ref.double(), -1)
+        r2 = torch.cumsum(ref.double() ** 2, -1)
+        torch.testing.assert_close(p1[:, :, 1:].cpu(), r1, rtol=1e-6, atol=1e-5)
+        torch.testing.assert_close(p2[:, :, 1:].cpu(), r2, rtol=1e-6, atol=1e-5)
+        assert float(p1[:, :, 0].abs().sum()) == 0.0
+
+
+def test_bad_arguments_return_status_not_crash():
+    from ctypes import byref
+    from layers import ign_cabi as C
+    d = C.ShapeletDesc(2, 3, 10, 12, 4, 11, 1, 1.0, 0, 0, 0)
+    rc = C.lib.ign_shapelet_forward(byref(d), *([None] * 13))
+    assert rc == 1 and "T < L" in C.last_error()
+    d = C.ShapeletDesc(2, 3, 16, 16, 4, 5, 1, 1.0, 2, 0, 0)
+    x = torch.zeros(2, 3, 16, device="cuda")
+    rc = C.lib.ign_shapelet_forward(byref(d), x.data_ptr(), None, None, x.data_ptr(), None, x.data_ptr(),
+                                    x.data_ptr(), x.data_ptr(), None, x.data_ptr(), x.data_ptr(), None, None)
+    assert rc == 1 and "prefix" in C.last_error()

@@ -1,0 +1,217 @@
+"""GPU parity: the CUDA shapelet layer (through the C ABI) against the CPU oracle and the golden vectors
+frozen from the reference.  Tolerances: distances / probabilities within 1e-4 relative (north-star bound;
+we assert 2e-5), gradients 1e-4 relative to the largest entry, indices bit-exact barring near-ties."""
+import numpy as np
+import pytest
+import torch
+
+import ign_oracle as O
+from helpers import MODES, assert_close, index_parity, load_golden, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+RTOL, ATOL = 2e-5, 2e-6          # forward values (fp32 path)
+
+
+def run_layer(xn, W, stride, eps, dist, pool="rbf_max", thr=None, g=None):
+    from layers.shapelet_ops import SeriesPack, shapelet_transform
+    Wd = W.to(DEV).requires_grad_(g is not None)
+    thd = None if thr is None else thr.to(DEV).requires_grad_(g is not None)
+    pack = SeriesPack.from_channel_major(xn.to(DEV))
+    p, dmin, idx = shapelet_transform(pack, Wd, stride, eps, dist, pool, thd)
+    dW = dthr = None
+    if g is not None:
+        (p * g.to(DEV)).sum().backward()
+        dW = Wd.grad
+        dthr = None if thd is None else thd.grad
+    torch.cuda.synchronize()
+    return p, dmin, idx, dW, dthr
+
+
+LAYER_CASES = ["layer_l1", "layer_l1_stride", "layer_cosine", "layer_pearson", "layer_cosine_stride",
+               "layer_l1_struct", "layer_lts", "layer_l1_min", "layer_pearson_k12", "layer_sql2"]
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_layer_matches_reference_golden(name):
+    g = load_golden(name)
+    dist = MODES[str(g["dfunc"])][1]
+    thr = t(g["threshold"]) if "threshold" in g else None
+    p, dmin, idx, dW, dthr = run_layer(t(g["xn"]), t(g["W"]), int(g["stride"]), float(g["eps"]), dist,
+                                       str(g["pool"]), thr, t(g["g"]))
+    B = g["xn"].shape[0]
+    assert_close(p.reshape(B, -1), t(g["p"]).reshape(B, -1), RTOL, ATOL, name + " p")
+    assert_close(dmin.reshape(B, -1), t(g["dmin"]).reshape(B, -1), RTOL, ATOL, name + " dmin")
+    scale = float(np.abs(g["dW"]).max())
+    assert_close(dW, t(g["dW"]), 1e-4, 1e-4 * scale, name + " dW")
+    if dthr is not None:
+        assert_close(dthr, t(g["dthreshold"]), 1e-4, 1e-5, name + " dthreshold")
+
+
+def test_known_answer_vectors():
+    g = load_golden("kat")
+    x = torch.tensor([[[0., 1., 2., 3., 4.]]])
+    for flag in ("euclidean", "cosine", "pearson"):
+        W = t(g[flag + "_W"]).reshape(1, 1, 3)
+        p, dmin, idx, dW, _ = run_layer(x, W, 1, 1.0, MODES[flag][1], g=torch.ones(1, 1, 1))
+        assert abs(float(p) - float(g[flag + "_p"].ravel()[0])) < 2e-6, flag
+        assert abs(float(dmin) - float(g[flag + "_dmin"].ravel()[0])) < 2e-6, flag
+        np.testing.assert_allclose(dW.cpu().numpy().ravel(), g[flag + "_dW"].ravel(), atol=3e-6, err_msg=flag)
+    # L1 case has exact ties x == w (sign(0) = 0 must hold); argmin of L1 is window 0
+    p, dmin, idx, _, _ = run_layer(x, torch.ones(1, 1, 3), 1, 1.0, "l1")
+    assert int(idx[1]) == 0 and int(idx[0]) == 0
+    # cosine: best window is the last one
+    p, dmin, idx, _, _ = run_layer(x, torch.ones(1, 1, 3), 1, 1.0, "cosine")
+    assert int(idx[1]) == 2
+
+
+SHAPES = [
+    # B, M, T, K, L, stride
+    (3, 4, 64, 5, 9, 1),
+    (2, 3, 200, 10, 37, 1),       # two k-chunks of 5, TT=8 path
+    (2, 5, 130, 7, 16, 1),        # K not a multiple of 4 or 5
+    (2, 2, 96, 3, 96, 1),         # T == L: a single window
+    (1, 1, 17, 1, 3, 1),          # minimum sizes
+    (2, 3, 400, 4, 50, 3),        # strided windows
+    (2, 2, 600, 5, 120, 7),       # stride as used for seq_len >= 3000
+    (2, 2, 300, 45, 20, 1),       # K > 40: several shapelet blocks per channel
+    (5, 3, 120, 5, 30, 1),        # odd batch vs resident rows
+]
+
+
+@pytest.mark.parametrize("flag", ["euclidean", "sql2", "cosine", "pearson"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_layer_vs_oracle(flag, shape):
+    B, M, T, K, L, stride = shape
+    mode, dist = MODES[flag]
+    torch.manual_seed(1234 + B + M + T)
+    xn = torch.randn(B, M, T)
+    W = torch.randn(K, M, L)
+    g = torch.randn(B, K, M)
+    eps = 0.8
+    ref = O.shapelet_forward(xn, W, stride, eps, mode)
+    p, dmin, idx, dW, _ = run_layer(xn, W, stride, eps, dist, g=g)
+    assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, f"{flag} p")
+    assert_close(dmin.reshape(B, -1), ref.dmin, RTOL, ATOL, f"{flag} dmin")
+    index_parity(idx[1], ref.argmin_d, ref.d, False, L, f"{flag} argmin")
+    index_parity(idx[0], ref.arg_hard, O.rbf(ref.d, eps), True, L, f"{flag} argmax p")
+    dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), stride, eps, mode)
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag} dW")
+
+
+@pytest.mark.parametrize("flag", ["euclidean", "sql2"])
+@pytest.mark.parametrize("shape", [(3, 4, 64, 5, 9, 1), (2, 3, 300, 6, 40, 2)])
+def test_lts_layer_vs_oracle(flag, shape):
+    B, M, T, K, L, stride = shape
+    mode, dist = MODES[flag]
+    torch.manual_seed(99)
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    thr = torch.rand(1, K, M)
+    ref = O.shapelet_forward(xn, W, stride, 1.0, mode, O.POOL_LTS_MIN, thr)
+    p, dmin, idx, dW, dthr = run_layer(xn, W, stride, 1.0, dist, "lts_min", thr, g)
+    assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, "lts p")
+    assert_close(dmin.reshape(B, -1), ref.dmin, RTOL, ATOL, "lts dmin")
+    dW_ref, dthr_ref = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), stride, 1.0, mode,
+                                                   O.POOL_LTS_MIN, thr.double())
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), "lts dW")
+    assert_close(dthr, dthr_ref, 1e-4, 1e-5, "lts dthreshold")
+
+
+def test_long_shapelet_needs_lag_blocks():
+    """L = 2100 -> more lag tiles than threads: the backward splits the lag axis over CTAs."""
+    torch.manual_seed(5)
+    B, M, T, K, L = 2, 2, 2400, 5, 2100
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    for flag in ("euclidean", "cosine"):
+        mode, dist = MODES[flag]
+        ref = O.shapelet_forward(xn, W, 1, 1.0, mode)
+        p, dmin, idx, dW, _ = run_layer(xn, W, 1, 1.0, dist, g=g)
+        assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, flag + " p")
+        dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 1.0, mode)
+        assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), flag + " dW")
+
+
+@pytest.mark.parametrize("flag", ["euclidean", "cosine"])
+def test_chisco_shaped_rows_vs_oracle(flag):
+    """CHISCO geometry (T=1000, L in {100,200,300,500}, K=5) on a channel subset the oracle can afford."""
+    mode, dist = MODES[flag]
+    torch.manual_seed(42)
+    B, M, T, K = 2, 6, 1000, 5
+    xn = torch.randn(B, M, T)
+    for L in (100, 200, 300, 500):
+        W, g = torch.randn(K, M, L), torch.randn(B, K, M)
+        ref = O.shapelet_forward(xn, W, 1, 1.0, mode)
+        p, dmin, idx, dW, _ = run_layer(xn, W, 1, 1.0, dist, g=g)
+        assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, f"{flag} L={L} p")
+        assert_close(dmin.reshape(B, -1), ref.dmin, RTOL, ATOL, f"{flag} L={L} dmin")
+        index_parity(idx[1], ref.argmin_d, ref.d, False, L, f"{flag} L={L} argmin")
+        dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 1.0, mode)
+        assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag} L={L} dW")
+
+
+@pytest.mark.parametrize("flag", ["euclidean", "pearson"])
+def test_full_size_properties(flag):
+    """BASELINE config 2 at full size (B=256, M=125, T=1000): size-independent properties, determinism,
+    batch-permutation equivariance, and a sampled row check against the oracle."""
+    mode, dist = MODES[flag]
+    torch.manual_seed(0)
+    B, M, T, K, L = 256, 125, 1000, 5, 100
+    xn = torch.randn(B, M, T, device=DEV)
+    W = torch.randn(K, M, L, device=DEV)
+    g = torch.randn(B, K, M, device=DEV)
+    p, dmin, idx, dW, _ = run_layer(xn, W, 1, 1.0, dist, g=g)
+    assert bool(((p > 0) & (p <= 1)).all())
+    Tw = T - L + 1
+    assert int(idx.min()) >= 0 and int(idx.max()) < Tw
+    # where argmax p == argmin d (no ties), p_max == exp(-(dmin)^2) up to fp32 rounding
+    same = idx[0] == idx[1]
+    assert float(same.float().mean()) > 0.999
+    assert_close(p[same], torch.exp(-dmin[same] ** 2), 1e-6, 1e-7, "p_max == rbf(d_min)")
+    # determinism: bit-identical on a second run
+    p2, dmin2, idx2, dW2, _ = run_layer(xn, W, 1, 1.0, dist, g=g)
+    assert torch.equal(p, p2) and torch.equal(dmin, dmin2) and torch.equal(idx, idx2) and torch.equal(dW, dW2)
+    # permuting the batch permutes the outputs (samples are independent) and leaves dW unchanged up to order
+    perm = torch.randperm(B, device=DEV)
+    p3, dmin3, idx3, dW3, _ = run_layer(xn[perm], W, 1, 1.0, dist, g=g[perm])
+    assert torch.equal(p3, p[perm]) and torch.equal(idx3, idx[:, perm])
+    assert_close(dW3, dW, 1e-4, 1e-4 * float(dW.abs().max()), "dW under batch permutation")
+    # linearity of the backward in the upstream gradient
+    _, _, _, dW4, _ = run_layer(xn, W, 1, 1.0, dist, g=2.0 * g)
+    assert_close(dW4, 2.0 * dW, 1e-5, 1e-6 * float(dW.abs().max()), "dW linear in g")
+    # sampled (b, m) rows against the oracle
+    bs, ms = [3, 200], [0, 77, 124]
+    sub = xn[bs][:, ms].cpu()
+    ref = O.shapelet_forward(sub, W[:, ms].cpu(), 1, 1.0, mode)
+    assert_close(p[bs][:, :, ms].reshape(len(bs), -1), ref.p, RTOL, ATOL, "sampled p")
+    assert_close(dmin[bs][:, :, ms].reshape(len(bs), -1), ref.dmin, RTOL, ATOL, "sampled dmin")
+
+
+def test_error_behaviour_matches_reference():
+    from layers.shapelet_ops import SeriesPack, shapelet_transform
+    from models.Shapelet import Shapelet
+    layer = Shapelet(3, 40, 4).to(DEV)
+    with pytest.raises(RuntimeError, match="maximum size for tensor at dimension 2"):
+        layer(torch.randn(2, 3, 30, device=DEV))           # T < L: unfold raises in the reference
+    with pytest.raises(RuntimeError, match="channels"):
+        shapelet_transform(SeriesPack.from_channel_major(torch.randn(2, 5, 64, device=DEV)),
+                           torch.randn(4, 3, 8, device=DEV))
+
+
+def test_gate_kernel_vs_oracle():
+    from layers.shapelet_ops import gini_gate
+    torch.manual_seed(8)
+    for C in (3, 9, 39, 70):
+        for gv in (None, 0.0, 0.3, 1.0):
+            s = torch.randn(33, C)
+            z = torch.randn(33, C)
+            go, ge = torch.randn(33, C), torch.randn(33, 1)
+            sd, zd = s.to(DEV).requires_grad_(True), z.to(DEV).requires_grad_(True)
+            out, eta = gini_gate(sd, zd, gv)
+            ((out * go.to(DEV)).sum() + (eta * ge.to(DEV)).sum()).backward()
+            ro, re = O.gate_forward(s, z, gv)
+            assert_close(out, ro, 1e-5, 1e-6, "gate out")
+            assert_close(eta, re, 1e-5, 1e-6, "gate eta")
+            gs, gz = O.gate_backward_formula(s.double(), z.double(), go.double(), ge.double(), gv)
+            assert_close(sd.grad, gs, 1e-4, 1e-5, "gate d/ds")
+            assert_close(zd.grad, gz, 1e-4, 1e-5, "gate d/dz")

@@ -1,0 +1,101 @@
+"""GPU parity of the whole models against golden vectors frozen from the reference (same weights via
+load_state_dict, same inputs): logits, eta, predicates, regulariser, loss and parameter gradients."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, load_golden, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build(name):
+    from models.InterpGN import InterpGN
+    from models.Shapelet import DistThresholdSBM, ShapeBottleneckModel
+    g = load_golden(name)
+    kw = dict(zip(g["cfg_keys"].tolist(), g["cfg_vals"].tolist()))
+    cfg = SimpleNamespace(epsilon=1., distance_func=kw.get("distance_func", "euclidean"), memory_efficient=False,
+                          sbm_cls="linear", dropout=0., lambda_reg=0.1, lambda_div=0.1, dnn_type="FCN",
+                          enc_in=int(kw["enc_in"]), num_class=int(kw["num_class"]), seq_len=int(kw["seq_len"]))
+    cls = DistThresholdSBM if name.endswith("lts") else ShapeBottleneckModel if name.endswith("sbm") else InterpGN
+    model = cls(cfg)
+    model.load_state_dict({k[4:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("sd::")})
+    return model.to(DEV).train(), g
+
+
+@pytest.mark.parametrize("name", ["model_jv_interpgn", "model_jv_interpgn_gate", "model_jv_interpgn_cos",
+                                  "model_jv_sbm", "model_jv_lts", "model_small_chisco"])
+def test_model_matches_reference_golden(name):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    model, g = build(name)
+    x, y = t(g["x"], DEV), torch.as_tensor(g["y"]).to(DEV)
+    mask = torch.ones(x.shape[0], x.shape[1], device=DEV)
+    is_ign = "eta" in g
+    if is_ign:
+        gv = None if np.isnan(g["gating_value"]) else float(g["gating_value"])
+        logits, info = model(x, mask, None, None, gating_value=gv)
+    else:
+        logits, info = model(x, mask, None, None)
+    loss = torch.nn.functional.cross_entropy(logits, y) + info.loss.mean()
+    if is_ign:
+        loss = loss + torch.nn.functional.cross_entropy(info.shapelet_preds, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert_close(info.p, t(g["p"]), 2e-5, 2e-6, name + " p")
+    assert_close(info.d, t(g["d"]), 2e-5, 2e-6, name + " d")
+    assert_close(info.shapelet_preds, t(g["shapelet_preds"]), 1e-4, 1e-5, name + " shapelet logits")
+    assert_close(logits, t(g["logits"]), 1e-4, 2e-5, name + " logits")
+    assert torch.equal(logits.argmax(-1).cpu(), torch.as_tensor(g["logits"]).argmax(-1)), "predicted classes"
+    assert_close(info.loss, t(g["reg_loss"]), 1e-5, 1e-7, name + " regulariser")
+    assert_close(loss.reshape(()), t(g["loss"]).reshape(()), 1e-4, 1e-5, name + " loss")
+    if is_ign:
+        assert_close(info.eta, t(g["eta"]), 1e-4, 1e-6, name + " eta")
+        assert_close(info.dnn_preds, t(g["dnn_preds"]), 1e-3, 1e-4, name + " deep logits (cuDNN)")
+    for k, p in model.named_parameters():
+        if "grad::" + k in g:
+            ref = t(g["grad::" + k])
+            assert_close(p.grad, ref, 1e-3, 2e-4 * float(ref.abs().max()) + 1e-7, name + " grad " + k)
+        elif "gradsum::" + k in g:
+            s, a = g["gradsum::" + k]
+            assert abs(float(p.grad.double().abs().sum()) - a) <= 2e-2 * a + 1e-4, name + " |grad| checksum " + k
+
+
+def test_eval_path_with_test_time_gating_and_amp():
+    """test() calls forward with gating_value (experiment_classification.py:974); under bf16 autocast the
+    shapelet maths stays fp32 as in the reference."""
+    model, g = build("model_jv_interpgn")
+    model.eval()
+    x = t(g["x"], DEV)
+    with torch.no_grad():
+        out1, info1 = model(x, None, None, None, gating_value=1.0)
+        out0, info0 = model(x, None, None, None, gating_value=None)
+        assert torch.allclose(out1, out0)                       # eta <= 1: gate at 1.0 never fires
+        outg, infog = model(x, None, None, None, gating_value=0.0)
+        assert torch.allclose(outg, infog.shapelet_preds, atol=1e-6) and bool((infog.eta == 1).all())
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outa, infoa = model(x, None, None, None)
+        assert infoa.p.dtype == torch.float32 and infoa.d.dtype == torch.float32
+        assert_close(infoa.p, info0.p, 1e-6, 1e-7, "p under autocast")
+
+
+def test_training_reduces_loss_and_pos_weight_step():
+    model, g = build("model_jv_interpgn")
+    x, y = t(g["x"], DEV), torch.as_tensor(g["y"]).to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-3)
+    losses = []
+    for _ in range(12):
+        logits, info = model(x, None, None, None)
+        loss = torch.nn.functional.cross_entropy(logits, y) + info.loss.mean() + \
+            torch.nn.functional.cross_entropy(info.shapelet_preds, y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        model.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
+    assert float(model.sbm.output_layer.weight.min()) >= 0.0
