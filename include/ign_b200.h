@@ -97,32 +97,31 @@ int32_t ign_window_prefix(const float* xn_dev, double* pre1_dev, double* pre2_de
  *   xn_dev [B,M,Tp]; pre1/pre2 [B,M,T+1] (required unless dist==L1); W_dev [K,M,L];
  *   threshold_dev [K,M] (required for LTS_MIN).
  * Outputs, all [B,K,M]:
- *   p_dev       pooled predicate  (max_t RBF prob | sigmoid(thr - min_t d))          Shapelet.py:82 | :109
- *   dmin_dev    min_t d                                                              Shapelet.py:84
- *   arg_hard_dev index chosen by the straight-through one-hot (argmax_t p | argmin_t d), first on ties
- *   argmin_dev  argmin_t d, first on ties (may be NULL)
- *   Z_dev,S1_dev softmax statistics saved for backward:
- *                rbf_max: Z=sum_t e^{p_t},            S1=sum_t e^{p_t} p_t
- *                lts_min: Z=sum_t e^{-(d_t-dmin)},    S1=sum_t e^{-(d_t-dmin)} d_t
- *   dstore_dev  optional [B,M,K,Tw] (Tw = ign_padded_windows) all window distances, kept for backward;
- *               NULL in inference. */
+ *   p_dev       pooled predicate: max_t exp(-(eps d_t)^2) = exp(-(eps min_t d_t)^2)   Shapelet.py:77-82
+ *               | sigmoid(thr - min_t d_t)                                            Shapelet.py:105-109
+ *   dmin_dev    min_t d_t                                                             Shapelet.py:84
+ *   argmin_dev  argmin_t d_t, first index on ties (may be NULL).  It is also the arg-max of p barring
+ *               ties of p in fp32; backward re-derives the reference's arg-max-of-p one-hot itself.
+ *   dstore_dev  optional [B,M,K,Tw] (Tw = ign_padded_windows) all window distances, kept for backward
+ *               (the soft-max statistics are recomputed from it); NULL in inference. */
 int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev, const double* pre1_dev,
                              const double* pre2_dev, const float* W_dev, const float* threshold_dev,
-                             float* p_dev, float* dmin_dev, int32_t* arg_hard_dev, int32_t* argmin_dev,
-                             float* Z_dev, float* S1_dev, float* dstore_dev, void* stream);
+                             float* p_dev, float* dmin_dev, int32_t* argmin_dev, float* dstore_dev,
+                             void* stream);
 
 /* bytes of scratch ign_shapelet_backward needs for this problem */
 size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* desc);
 
-/* Gradient of the pooled output w.r.t. the shapelets, through the saved soft-max weights / argmax:
+/* Gradient of the pooled output w.r.t. the shapelets, through the straight-through soft/hard pooling
+ * (Shapelet.py:79-82 | :105-108): every window receives soft_t*(p_t - pbar) (+1 at the hard index).
  *   g_dev [B,K,M] = dLoss/d(max_p)  (rbf_max)   or   dLoss/d(min_d)  (lts_min; the caller folds the
  *   sigmoid: g_min = -g_p * p * (1-p), dthreshold = sum_b g_p * p * (1-p))
+ *   dstore_dev [B,M,K,Tw] as written by ign_shapelet_forward on the same inputs.
  *   dW_dev [K,M,L] is overwritten (not accumulated).  Deterministic (no float atomics). */
 int32_t ign_shapelet_backward(const ign_shapelet_desc* desc, const float* xn_dev, const double* pre1_dev,
                               const double* pre2_dev, const float* W_dev, const float* g_dev,
-                              const int32_t* arg_hard_dev, const float* dmin_dev, const float* Z_dev,
-                              const float* S1_dev, const float* dstore_dev, float* dW_dev,
-                              void* workspace_dev, size_t workspace_bytes, void* stream);
+                              const float* dstore_dev, float* dW_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream);
 
 /* InterpGN gate + mixture (InterpGN.py:44-52): q=softmax(s), eta=(C*sum q^2-1)/(C-1),
  * if use_gate: eta=1 where eta>gating_value; out=eta*s+(1-eta)*z.  s,z,out [B,C]; eta [B]. */

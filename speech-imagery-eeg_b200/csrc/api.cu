@@ -89,11 +89,11 @@ int32_t ign_window_prefix(const float* xn, double* pre1, double* pre2, int32_t B
 }
 
 int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const double* pre1, const double* pre2,
-                             const float* W, const float* thr, float* p, float* dmin, int32_t* arg_hard,
-                             int32_t* argmin, float* Z, float* S1, float* dstore, void* stream) {
+                             const float* W, const float* thr, float* p, float* dmin, int32_t* argmin,
+                             float* dstore, void* stream) {
   int rc = check_desc(d, "shapelet_forward");
   if (rc) return rc;
-  IGN_REQUIRE(xn && W && p && dmin && arg_hard && Z && S1, "shapelet_forward: null pointer");
+  IGN_REQUIRE(xn && W && p && dmin, "shapelet_forward: null pointer");
   IGN_REQUIRE(d->dist == IGN_DIST_L1 || (pre1 && pre2), "shapelet_forward: dist %d needs the window prefix sums", d->dist);
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || thr, "shapelet_forward: LTS pooling needs threshold");
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || d->dist <= IGN_DIST_SQL2,
@@ -102,7 +102,7 @@ int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const 
     set_error("shapelet_forward: tcgen05 precision modes are not built into this library yet");
     return IGN_ERR_UNSUPPORTED;
   }
-  return launch_shapelet_fwd_simt(*d, xn, pre1, pre2, W, thr, p, dmin, arg_hard, argmin, Z, S1, dstore, (cudaStream_t)stream);
+  return launch_shapelet_fwd_simt(*d, xn, pre1, pre2, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
 }
 
 size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
@@ -111,15 +111,14 @@ size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
 }
 
 int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const double* pre1, const double* pre2,
-                              const float* W, const float* g, const int32_t* arg_hard, const float* dmin,
-                              const float* Z, const float* S1, const float* dstore, float* dW, void* ws,
+                              const float* W, const float* g, const float* dstore, float* dW, void* ws,
                               size_t ws_bytes, void* stream) {
   int rc = check_desc(d, "shapelet_backward");
   if (rc) return rc;
-  IGN_REQUIRE(xn && W && g && arg_hard && dmin && Z && S1 && dW && ws, "shapelet_backward: null pointer");
+  IGN_REQUIRE(xn && W && g && dW && ws, "shapelet_backward: null pointer");
   IGN_REQUIRE(dstore, "shapelet_backward: dstore (window distances saved by forward) is required");
   IGN_REQUIRE(d->dist == IGN_DIST_L1 || (pre1 && pre2), "shapelet_backward: dist %d needs the window prefix sums", d->dist);
-  return launch_shapelet_bwd_simt(*d, xn, pre1, pre2, W, g, arg_hard, dmin, Z, S1, dstore, dW, ws, ws_bytes, (cudaStream_t)stream);
+  return launch_shapelet_bwd_simt(*d, xn, pre1, pre2, W, g, dstore, dW, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int32_t ign_gate_forward(const float* s, const float* z, float* out, float* eta, int32_t B, int32_t C,
@@ -154,12 +153,11 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
   }
   cudaStream_t st;
   IGN_CUDA(cudaStreamCreate(&st));
-  float *x = nullptr, *xn = nullptr, *W = nullptr, *out = nullptr, *Z = nullptr;
+  float *x = nullptr, *xn = nullptr, *W = nullptr, *out = nullptr;
   double* pre = nullptr;
-  int* idx = nullptr;
   const size_t nx = (size_t)B * T * M, nxn = (size_t)B * M * Tp, nf = (size_t)B * Kmax * M;
   auto cleanup = [&]() {
-    cudaFree(x); cudaFree(xn); cudaFree(W); cudaFree(out); cudaFree(Z); cudaFree(pre); cudaFree(idx);
+    cudaFree(x); cudaFree(xn); cudaFree(W); cudaFree(out); cudaFree(pre);
     cudaStreamDestroy(st);
   };
 #define IGN_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return IGN_ERR_CUDA; } } while (0)
@@ -167,8 +165,6 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
   IGN_TRY(cudaMalloc(&xn, nxn * 4));
   IGN_TRY(cudaMalloc(&W, wmax * 4));
   IGN_TRY(cudaMalloc(&out, nf * 2 * 4));
-  IGN_TRY(cudaMalloc(&Z, nf * 2 * 4));
-  IGN_TRY(cudaMalloc(&idx, nf * 4));
   if (dist != IGN_DIST_L1) IGN_TRY(cudaMalloc(&pre, (size_t)B * M * (T + 1) * 2 * sizeof(double)));
   IGN_TRY(cudaMemcpyAsync(x, x_host, nx * 4, cudaMemcpyHostToDevice, st));
   rc = launch_instnorm(x, xn, nullptr, nullptr, B, T, M, st);
@@ -180,7 +176,7 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
     ign_shapelet_desc d{B, M, T, Tp, K[g], L[g], stride[g], eps, dist, IGN_POOL_RBF_MAX, precision};
     const size_t n = (size_t)B * K[g] * M;
     IGN_TRY(cudaMemcpyAsync(W, W_host[g], (size_t)K[g] * M * L[g] * 4, cudaMemcpyHostToDevice, st));
-    rc = ign_shapelet_forward(&d, xn, pre, pre2, W, nullptr, out, out + nf, idx, nullptr, Z, Z + nf, nullptr, st);
+    rc = ign_shapelet_forward(&d, xn, pre, pre2, W, nullptr, out, out + nf, nullptr, nullptr, st);
     if (rc) break;
     hp.resize(n); hd.resize(n);
     IGN_TRY(cudaMemcpyAsync(hp.data(), out, n * 4, cudaMemcpyDeviceToHost, st));

@@ -42,12 +42,10 @@ int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, 
 int launch_prefix(const float* xn, double* pre1, double* pre2, int B, int M, int T, cudaStream_t st);
 int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
                              const double* pre2, const float* W, const float* thr, float* p, float* dmin,
-                             int* arg_hard, int* argmin, float* Z, float* S1, float* dstore,
-                             cudaStream_t st);
+                             int* argmin, float* dstore, cudaStream_t st);
 size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d);
 int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
-                             const double* pre2, const float* W, const float* g, const int* arg_hard,
-                             const float* dmin, const float* Z, const float* S1, const float* dstore,
+                             const double* pre2, const float* W, const float* g, const float* dstore,
                              float* dW, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int B, int C, int use_gate,
                     float gv, cudaStream_t st);

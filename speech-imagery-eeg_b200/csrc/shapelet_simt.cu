@@ -10,26 +10,31 @@
 //   dstore [B,M,K,Tw] all window distances (training only), time contiguous
 //   pooled outputs [B,K,M]
 //
-// Decomposition: one CTA owns a channel m, a block of KB shapelets and a chunk of the batch.  The
-// K-block's shapelets for that channel stay in shared memory for the CTA's lifetime; series rows
-// stream through NB at a time.
+// Forward.  One CTA owns a channel m, a block of KB shapelets and a chunk of the batch; the shapelets of
+// that channel stay in shared memory for the CTA's lifetime, series rows stream through NB at a time.
 //   phase 1  register-tiled distance: each thread owns TT consecutive windows x KK shapelets and slides
 //            along the lag axis with a 12-register ring (1 LDS.128 of x + KK broadcast LDS.128 of w per
-//            4 lags for 4*TT*KK accumulate pairs), raw sums go to a shared staging tile
-//   phase 2  one warp per (sample, shapelet) row: raw -> distance (norm terms from the prefix pass),
-//            RBF, soft-max statistics, arg-max/min with first-index ties, warp-shuffle reductions,
-//            coalesced write of d for backward
+//            4 lags for 4*TT*KK accumulate pairs).  The epilogue stays in registers: raw sum -> distance
+//            (norm terms from the prefix pass), coalesced store of d for backward, per-thread min/argmin.
+//   phase 2  one warp per (sample, shapelet) row reduces the per-tile candidates with shuffles (first
+//            index on ties) and applies the pooling non-linearity once per row:
+//            max_t exp(-(eps d_t)^2) = exp(-(eps min_t d_t)^2), so no exp per window is needed.
 // Strides > 1 (only when seq_len >= 3000, Shapelet.py:162) are handled by de-interleaving series and
 // shapelet into `stride` residue classes: sum_l f(x[t*s+l], w[l]) = sum_r sum_q f(x_r[t+q], w_r[q]),
 // i.e. `stride` unit-stride correlations, so the same sliding-window code runs for every stride.
 //
-// Backward (stored-d): phase A turns d + saved statistics into the per-window coefficient
-// a_t = dLoss/dd_t (times the mode's norm factor), phase B contracts it with the series:
-//   L1 : dW[l] = -(1/L) sum_t a_t sign(x[t+l]-w[l])     (sign(0)=0, exact)
-//   dot: G[l]  = sum_t a_t x[t+l], then dW from G and two per-shapelet scalars (finalize kernel)
-// Each thread owns 8 lags x KK shapelets of dW in registers for the whole batch chunk; partial sums are
-// combined in a fixed order (shared memory, then a per-chunk workspace, then the finalize kernel) so the
-// result is bit-reproducible run to run.
+// Backward (stored-d).  One CTA owns a channel, a block of shapelets, a block of lags and a batch chunk.
+//   phase A  the d rows are copied to shared memory cooperatively; one warp per row recomputes the
+//            soft-max statistics (Z, S1, arg-max of p with first-index ties — exactly the reference's
+//            hard one-hot, Shapelet.py:79) and turns d into a_t = dLoss/dd_t (times the mode's norm
+//            factor) in place
+//   phase B  contraction with the series; each thread owns 8 lags of ONE shapelet in registers for the
+//            whole batch chunk and slides along the window axis with the same 12-register ring:
+//              L1 : dW[l] = -(1/L) sum_t a_t sign(x[t+l]-w[l])     (sign(0)=0, exact)
+//              dot: G[l]  = sum_t a_t x[t+l], then dW from G and two per-shapelet scalars (finalize)
+// ~64 registers per thread, so several CTAs share an SM and one CTA's phase A hides under another's
+// phase B.  Partial sums are combined in a fixed order (shared memory, then a per-chunk workspace, then
+// the finalize kernel) so the result is bit-reproducible run to run — no float atomics.
 #include "ign_common.cuh"
 
 #include <math.h>
@@ -39,8 +44,7 @@ namespace {
 
 constexpr int OP_L1 = 0;
 constexpr int OP_DOT = 1;
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kMaxThreads = 256;
 constexpr int LT = 8;  // lags per thread in backward
 
 struct Geo {  // geometry shared by forward and backward
@@ -59,12 +63,12 @@ struct Geo {  // geometry shared by forward and backward
 
 struct FwdArgs {
   const float* xn; const double* pre1; const double* pre2; const float* W; const float* thr;
-  float* p; float* dmin; int* arg_hard; int* argmin; float* Z; float* S1; float* dstore;
+  float* p; float* dmin; int* argmin; float* dstore;
 };
 
 struct BwdArgs {
   const float* xn; const double* pre1; const double* pre2; const float* W; const float* g;
-  const int* arg_hard; const float* dmin; const float* Z; const float* S1; const float* dstore;
+  const float* dstore;
   float* part;   // [nchunk][K][M][L]
   float* scal;   // [nchunk][K][M][2]
   int nseg, nlb, tlb;   // t-segments per row, l-blocks, l-tiles per l-block
@@ -78,9 +82,9 @@ struct BwdArgs {
 // pearson), zero padded; wstat[kl] = mode-specific shapelet statistic.
 __device__ void load_shapelets(const Geo& g, const float* __restrict__ W, int m, int k0, float* ws,
                                float* wstat) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int rowlen = g.s * g.LQ;
-  for (int kl = warp; kl < g.KB; kl += kWarps) {
+  for (int kl = warp; kl < g.KB; kl += nwarp) {
     const int k = k0 + kl;
     float* dst = ws + (size_t)kl * rowlen;
     for (int i = lane; i < rowlen; i += 32) dst[i] = 0.f;
@@ -120,15 +124,16 @@ __device__ void load_series(const Geo& g, const float* __restrict__ xn, const do
                             float* st1) {
   const int rowlen = g.s * g.XQ;
   const int total = g.NB * rowlen;
+  const int nthr = blockDim.x;
   if (g.s == 1) {
-    for (int i = threadIdx.x * 4; i < total; i += kThreads * 4) {   // XQ % 4 == 0
+    for (int i = threadIdx.x * 4; i < total; i += nthr * 4) {   // XQ % 4 == 0
       const int bl = i / rowlen, q = i - bl * rowlen;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bl < nb && q < g.Tp) v = *reinterpret_cast<const float4*>(xn + ((size_t)(b0 + bl) * g.M + m) * g.Tp + q);
       *reinterpret_cast<float4*>(xs + i) = v;
     }
   } else {
-    for (int i = threadIdx.x; i < total; i += kThreads) {
+    for (int i = threadIdx.x; i < total; i += nthr) {
       const int bl = i / rowlen, rem = i - bl * rowlen;
       const int r = rem / g.XQ, q = rem - r * g.XQ;
       const int t = q * g.s + r;
@@ -138,7 +143,7 @@ __device__ void load_series(const Geo& g, const float* __restrict__ xn, const do
     }
   }
   if (g.dist != IGN_DIST_L1) {
-    for (int i = threadIdx.x; i < g.NB * g.DP; i += kThreads) {
+    for (int i = threadIdx.x; i < g.NB * g.DP; i += nthr) {
       const int bl = i / g.DP, t = i - bl * g.DP;
       float a = 0.f, c = 0.f;
       if (bl < nb && t < g.Tw) {
@@ -172,10 +177,8 @@ __device__ __forceinline__ float acc_op(float acc, float x, float w) {
 
 template <int OP, int KK, int TT>
 __device__ __forceinline__ void distance_item(const Geo& g, const float* __restrict__ xrow,
-                                              const float* __restrict__ wbase, float* __restrict__ dout,
-                                              int t0) {
+                                              const float* __restrict__ wbase, int t0, float (&acc)[TT][KK]) {
   constexpr int RING = TT + 4;
-  float acc[TT][KK];
 #pragma unroll
   for (int j = 0; j < TT; ++j)
 #pragma unroll
@@ -232,22 +235,15 @@ __device__ __forceinline__ void distance_item(const Geo& g, const float* __restr
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < KK; ++k)
-#pragma unroll
-    for (int j = 0; j < TT; j += 4)
-      *reinterpret_cast<float4*>(dout + k * g.DP + j) =
-          make_float4(acc[j][k], acc[j + 1][k], acc[j + 2][k], acc[j + 3][k]);
 }
 
 // raw accumulator -> distance
+template <int OP>
 __device__ __forceinline__ float finish_distance(int dist, float raw, float L, float xstat, float wstat) {
-  switch (dist) {
-    case IGN_DIST_L1: return raw / L;
-    case IGN_DIST_SQL2: return fmaxf((xstat + wstat - 2.f * raw) / L, 0.f);
-    case IGN_DIST_COSINE: return 1.f - raw * xstat * wstat;
-    default: return 1.f - raw / (sqrtf(xstat * wstat) + 1e-8f);
-  }
+  if (OP == OP_L1) return raw / L;
+  if (dist == IGN_DIST_SQL2) return fmaxf((xstat + wstat - 2.f * raw) / L, 0.f);
+  if (dist == IGN_DIST_COSINE) return 1.f - raw * xstat * wstat;
+  return 1.f - raw / (sqrtf(xstat * wstat) + 1e-8f);
 }
 
 struct ArgVal { float v; int i; };
@@ -279,96 +275,92 @@ __device__ __forceinline__ float warp_sum(float v) {
 // forward kernel
 // ------------------------------------------------------------------------------------------------
 template <int OP, int KK, int TT>
-__global__ void __launch_bounds__(kThreads, 2) shapelet_fwd_kernel(const Geo g, const FwdArgs a) {
+__global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo g, const FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int m = blockIdx.x, k0 = blockIdx.y * g.KB;
   const int bbeg = blockIdx.z * g.bpc, bend = min(g.B, bbeg + g.bpc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  float* xs = smem;
-  float* ws = xs + g.NB * g.s * g.XQ;
-  float* dbuf = ws + g.KB * g.s * g.LQ;
-  float* st0 = dbuf + g.NB * g.KB * g.DP;
-  float* wstat = st0 + (g.dist != IGN_DIST_L1 ? g.NB * g.DP : 0);
-
-  load_shapelets(g, a.W, m, k0, ws, wstat);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
 
   const int ntile = g.DP / TT;
   const int nkc = g.KB / KK;
+  float* xs = smem;
+  float* ws = xs + g.NB * g.s * g.XQ;
+  float* st0 = ws + g.KB * g.s * g.LQ;
+  float* wstat = st0 + (OP != OP_L1 ? g.NB * g.DP : 0);
+  float* cand_d = wstat + g.KB;                                   // [NB][KB][ntile]
+  int* cand_i = reinterpret_cast<int*>(cand_d + g.NB * g.KB * ntile);
+
+  load_shapelets(g, a.W, m, k0, ws, wstat);
+
   const int nitem = g.NB * ntile * nkc;
   const float Lf = (float)g.L;
-  const float eps = g.eps;
 
   for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
-    __syncthreads();   // previous pass finished reading xs/dbuf (and ws is written on the first pass)
+    __syncthreads();   // previous pass finished with xs/cand (and ws is written on the first pass)
     load_series(g, a.xn, a.pre1, a.pre2, m, b0, nb, xs, st0, nullptr);
     __syncthreads();
-    // ---- phase 1 ----
-    for (int item = threadIdx.x; item < nitem; item += kThreads) {
+    // ---- phase 1: distances + register epilogue ----
+    for (int item = threadIdx.x; item < nitem; item += blockDim.x) {
       const int tt = item % ntile;
       const int rest = item / ntile;
       const int bl = rest % g.NB, kc = rest / g.NB;
       if (bl >= nb || k0 + kc * KK >= g.K) continue;
-      distance_item<OP, KK, TT>(g, xs + bl * g.s * g.XQ, ws + kc * KK * g.s * g.LQ,
-                                dbuf + ((size_t)bl * g.KB + kc * KK) * g.DP + tt * TT, tt * TT);
+      const int t0 = tt * TT;
+      float acc[TT][KK];
+      distance_item<OP, KK, TT>(g, xs + bl * g.s * g.XQ, ws + kc * KK * g.s * g.LQ, t0, acc);
+      float xst[TT];
+#pragma unroll
+      for (int j = 0; j < TT; ++j) xst[j] = (OP != OP_L1) ? st0[bl * g.DP + t0 + j] : 0.f;
+      const int b = b0 + bl;
+#pragma unroll
+      for (int k = 0; k < KK; ++k) {
+        const int kl = kc * KK + k, kk = k0 + kl;
+        if (kk >= g.K) break;
+        const float wst = wstat[kl];
+        float best = INFINITY; int bi = 0x7fffffff;
+        float dv[TT];
+#pragma unroll
+        for (int j = 0; j < TT; ++j) {
+          const float d = finish_distance<OP>(g.dist, acc[j][k], Lf, xst[j], wst);
+          const bool valid = t0 + j < g.Tw;
+          dv[j] = valid ? d : 0.f;
+          if (valid && d < best) { best = d; bi = t0 + j; }
+        }
+        if (a.dstore) {
+          float* dg = a.dstore + (((size_t)b * g.M + m) * g.K + kk) * g.Ts + t0;
+#pragma unroll
+          for (int j = 0; j < TT; j += 4)
+            if (t0 + j < g.Ts) *reinterpret_cast<float4*>(dg + j) = make_float4(dv[j], dv[j + 1], dv[j + 2], dv[j + 3]);
+        }
+        cand_d[(bl * g.KB + kl) * ntile + tt] = best;
+        cand_i[(bl * g.KB + kl) * ntile + tt] = bi;
+      }
     }
     __syncthreads();
-    // ---- phase 2: one warp per (sample, shapelet) row ----
-    for (int row = warp; row < g.NB * g.KB; row += kWarps) {
+    // ---- phase 2: one warp per (sample, shapelet) row reduces the tile candidates ----
+    for (int row = warp; row < g.NB * g.KB; row += nwarp) {
       const int bl = row / g.KB, kl = row - bl * g.KB;
       const int b = b0 + bl, k = k0 + kl;
       if (bl >= nb || k >= g.K) continue;
-      const float* dr = dbuf + (size_t)row * g.DP;
-      const float* xstat = st0 + bl * g.DP;
-      const float wst = wstat[kl];
-      float* dg = a.dstore ? a.dstore + (((size_t)b * g.M + m) * g.K + k) * g.Ts : nullptr;
-      const size_t o = ((size_t)b * g.K + k) * g.M + m;
-
       float dmn = INFINITY; int imn = 0x7fffffff;
-      if (g.pool == IGN_POOL_RBF_MAX) {
-        float pmx = -1.f; int imx = 0x7fffffff; float Zs = 0.f, S1s = 0.f;
-        for (int t = lane; t < g.Tw; t += 32) {
-          const float d = finish_distance(g.dist, dr[t], Lf, g.dist != IGN_DIST_L1 ? xstat[t] : 0.f, wst);
-          if (dg) dg[t] = d;
-          const float ed = eps * d;
-          const float p = expf(-(ed * ed));              // Shapelet.py:77
-          const float e = expf(p);
-          Zs += e; S1s = fmaf(e, p, S1s);
-          if (p > pmx) { pmx = p; imx = t; }
-          if (d < dmn) { dmn = d; imn = t; }
-        }
-        ArgVal mx = warp_argmax_first(pmx, imx);
-        ArgVal mn = warp_argmin_first(dmn, imn);
-        Zs = warp_sum(Zs); S1s = warp_sum(S1s);
-        if (lane == 0) {
-          a.p[o] = mx.v; a.dmin[o] = mn.v; a.arg_hard[o] = mx.i;
-          if (a.argmin) a.argmin[o] = mn.i;
-          a.Z[o] = Zs; a.S1[o] = S1s;
-        }
-      } else {
-        for (int t = lane; t < g.Tw; t += 32) {
-          const float d = finish_distance(g.dist, dr[t], Lf, g.dist != IGN_DIST_L1 ? xstat[t] : 0.f, wst);
-          if (dg) dg[t] = d;
-          if (d < dmn) { dmn = d; imn = t; }
-        }
-        ArgVal mn = warp_argmin_first(dmn, imn);
-        float Zs = 0.f, S1s = 0.f;
-        for (int t = lane; t < g.Tw; t += 32) {
-          const float d = finish_distance(g.dist, dr[t], Lf, g.dist != IGN_DIST_L1 ? xstat[t] : 0.f, wst);
-          const float e = expf(-(d - mn.v));             // softmin weights, Shapelet.py:106
-          Zs += e; S1s = fmaf(e, d, S1s);
-        }
-        Zs = warp_sum(Zs); S1s = warp_sum(S1s);
-        if (lane == 0) {
-          const float th = a.thr[(size_t)k * g.M + m];
-          a.p[o] = 1.f / (1.f + expf(-(th - mn.v)));     // Shapelet.py:109
-          a.dmin[o] = mn.v; a.arg_hard[o] = mn.i;
-          if (a.argmin) a.argmin[o] = mn.i;
-          a.Z[o] = Zs; a.S1[o] = S1s;
-        }
+      for (int tt = lane; tt < ntile; tt += 32) {
+        const float d = cand_d[row * ntile + tt];
+        if (d < dmn) { dmn = d; imn = cand_i[row * ntile + tt]; }
       }
-      if (dg && lane < g.Ts - g.Tw) dg[g.Tw + lane] = 0.f;   // pad columns
+      ArgVal mn = warp_argmin_first(dmn, imn);
+      if (lane == 0) {
+        const size_t o = ((size_t)b * g.K + k) * g.M + m;
+        float pv;
+        if (g.pool == IGN_POOL_RBF_MAX) {
+          const float ed = g.eps * mn.v;
+          pv = expf(-(ed * ed));                              // Shapelet.py:77 at the best window
+        } else {
+          pv = 1.f / (1.f + expf(-(a.thr[(size_t)k * g.M + m] - mn.v)));   // Shapelet.py:109
+        }
+        a.p[o] = pv; a.dmin[o] = mn.v;
+        if (a.argmin) a.argmin[o] = mn.i;
+      }
     }
   }
 }
@@ -387,29 +379,29 @@ __device__ __forceinline__ float bwd_op(float acc, float c, float x, float w) {
   return fmaf(c, x, acc);
 }
 
-template <int OP, int KK>
-__global__ void __launch_bounds__(kThreads, 1) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
+template <int OP>
+__global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int m = blockIdx.x;
   const int kblk = blockIdx.y / a.nlb, lblk = blockIdx.y - kblk * a.nlb;
   const int k0 = kblk * g.KB;
   const int chunk = blockIdx.z;
   const int bbeg = chunk * g.bpc, bend = min(g.B, bbeg + g.bpc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nthr = blockDim.x;
 
-  const int nkc = g.KB / KK;
   const int ntl_all = g.s * g.LQ / LT;                    // l-tiles over all residues
   const int lt_beg = lblk * a.tlb;
   const int ntl = min(a.tlb, ntl_all - lt_beg);           // l-tiles of this CTA
   const int nslot = g.NB * a.nseg;
-  const int nitem = nslot * ntl * nkc;                    // <= kThreads by construction
+  const int nitem = nslot * ntl * g.KB;                   // <= blockDim.x by construction
 
   float* xs = smem;
   float* ws = xs + g.NB * g.s * g.XQ;
-  float* cbuf = ws + g.KB * g.s * g.LQ;                   // also reused as the final reduction buffer
-  const int cred = max(g.NB * g.KB * g.DP, kThreads * LT * KK);
+  float* cbuf = ws + g.KB * g.s * g.LQ;                   // d rows -> coefficients; reused for the final reduction
+  const int cred = max(g.NB * g.KB * g.DP, kMaxThreads * LT);
   float* st0 = cbuf + cred;
-  float* st1 = st0 + (g.dist != IGN_DIST_L1 ? g.NB * g.DP : 0);
+  float* st1 = st0 + (OP != OP_L1 ? g.NB * g.DP : 0);
   float* wstat = st1 + (g.dist == IGN_DIST_PEARSON ? g.NB * g.DP : 0);
   float* rowsc = wstat + g.KB;                            // [NB][KB][2]
   float* scal = rowsc + g.NB * g.KB * 2;                  // [KB][2]
@@ -417,35 +409,28 @@ __global__ void __launch_bounds__(kThreads, 1) shapelet_bwd_kernel(const Geo g, 
   load_shapelets(g, a.W, m, k0, ws, wstat);
   if (threadIdx.x < g.KB * 2) scal[threadIdx.x] = 0.f;
 
-  // this thread's fixed tile
+  // this thread's fixed tile: 8 lags of one shapelet, one (sample slot, t-segment)
   const bool active = threadIdx.x < nitem;
-  int lt = 0, seg = 0, bl = 0, kc = 0;
+  int lt = 0, kl = 0, seg = 0, bl = 0;
   if (active) {
     int it = threadIdx.x;
     lt = it % ntl; it /= ntl;
-    seg = it % a.nseg; it /= a.nseg;
-    bl = it % g.NB; kc = it / g.NB;
+    kl = it % g.KB; it /= g.KB;
+    seg = it % a.nseg; bl = it / a.nseg;
   }
   const int ltg = lt_beg + lt;
   const int tiles_per_res = g.LQ / LT;
   const int r = ltg / tiles_per_res, q0 = (ltg - r * tiles_per_res) * LT;
-  // t-segment [ta,tb), multiples of 4
   const int seg_len = round_up(ceil_div(g.DP, a.nseg), 4);
   const int ta = min(seg * seg_len, g.DP), tb = min(ta + seg_len, g.DP);
 
-  float acc[LT][KK];
-  float wreg[LT][KK];
+  float acc[LT], wreg[LT];
 #pragma unroll
-  for (int i = 0; i < LT; ++i)
-#pragma unroll
-    for (int k = 0; k < KK; ++k) acc[i][k] = 0.f;
+  for (int i = 0; i < LT; ++i) { acc[i] = 0.f; wreg[i] = 0.f; }
   __syncthreads();
-  if (OP == OP_L1) {
+  if (OP == OP_L1 && active) {
 #pragma unroll
-    for (int i = 0; i < LT; ++i)
-#pragma unroll
-      for (int k = 0; k < KK; ++k)
-        wreg[i][k] = active ? ws[((size_t)(kc * KK + k) * g.s + r) * g.LQ + q0 + i] : 0.f;
+    for (int i = 0; i < LT; ++i) wreg[i] = ws[((size_t)kl * g.s + r) * g.LQ + q0 + i];
   }
 
   const float eps = g.eps;
@@ -455,37 +440,69 @@ __global__ void __launch_bounds__(kThreads, 1) shapelet_bwd_kernel(const Geo g, 
     const int nb = min(g.NB, bend - b0);
     __syncthreads();
     load_series(g, a.xn, a.pre1, a.pre2, m, b0, nb, xs, st0, g.dist == IGN_DIST_PEARSON ? st1 : nullptr);
+    // cooperative copy of the saved distance rows (coalesced, many loads in flight)
+    {
+      const int rowv = g.DP / 4, tot = g.NB * g.KB * rowv;
+      for (int i = threadIdx.x; i < tot; i += nthr) {
+        const int row = i / rowv, c4 = (i - row * rowv) * 4;
+        const int rbl = row / g.KB, rkl = row - rbl * g.KB;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rbl < nb && k0 + rkl < g.K && c4 < g.Ts)
+          v = *reinterpret_cast<const float4*>(a.dstore + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c4);
+        *reinterpret_cast<float4*>(cbuf + (size_t)row * g.DP + c4) = v;
+      }
+    }
     __syncthreads();
-    // ---- phase A: coefficients a_t = dLoss/dd_t * (mode factor), one warp per (sample, shapelet) row
-    for (int row = warp; row < g.NB * g.KB; row += kWarps) {
-      const int rbl = row / g.KB, kl = row - rbl * g.KB;
-      const int b = b0 + rbl, k = k0 + kl;
+    // ---- phase A: one warp per (sample, shapelet) row: statistics, then d -> coefficient in place
+    for (int row = warp; row < g.NB * g.KB; row += nwarp) {
+      const int rbl = row / g.KB, rkl = row - rbl * g.KB;
+      const int b = b0 + rbl, k = k0 + rkl;
       float* cr = cbuf + (size_t)row * g.DP;
       float sc0 = 0.f, sc1 = 0.f;
       if (rbl < nb && k < g.K) {
-        const size_t o = ((size_t)b * g.K + k) * g.M + m;
-        const float gk = a.g[o];
-        const int ih = a.arg_hard[o];
-        const float Zr = a.Z[o];
-        const float bar = a.S1[o] / Zr;
-        const float dm = a.dmin[o];
-        const float wst = wstat[kl];
-        const float* dg = a.dstore + (((size_t)b * g.M + m) * g.K + k) * g.Ts;
+        const float gk = a.g[((size_t)b * g.K + k) * g.M + m];
+        const float wst = wstat[rkl];
+        float Zs = 0.f, S1s = 0.f;
+        int ih;
+        float shift = 0.f;
+        if (g.pool == IGN_POOL_RBF_MAX) {
+          float pmx = -1.f; int imx = 0x7fffffff;
+          for (int t = lane; t < g.Tw; t += 32) {
+            const float ed = eps * cr[t];
+            const float p = __expf(-(ed * ed));
+            const float e = __expf(p);
+            Zs += e; S1s = fmaf(e, p, S1s);
+            if (p > pmx) { pmx = p; imx = t; }
+          }
+          ih = warp_argmax_first(pmx, imx).i;            // hard one-hot of Shapelet.py:79
+        } else {
+          float dmn = INFINITY; int imn = 0x7fffffff;
+          for (int t = lane; t < g.Tw; t += 32) { const float d = cr[t]; if (d < dmn) { dmn = d; imn = t; } }
+          ArgVal mn = warp_argmin_first(dmn, imn);
+          ih = mn.i; shift = mn.v;
+          for (int t = lane; t < g.Tw; t += 32) {
+            const float d = cr[t];
+            const float e = __expf(-(d - shift));
+            Zs += e; S1s = fmaf(e, d, S1s);
+          }
+        }
+        Zs = warp_sum(Zs); S1s = warp_sum(S1s);
+        const float invZ = 1.f / Zs, bar = S1s * invZ;
         for (int t = lane; t < g.DP; t += 32) {
           float coef = 0.f;
           if (t < g.Tw) {
-            const float d = dg[t];
+            const float d = cr[t];
             float c;
             if (g.pool == IGN_POOL_RBF_MAX) {
               const float ed = eps * d;
-              const float p = expf(-(ed * ed));
-              const float soft = expf(p) / Zr;
+              const float p = __expf(-(ed * ed));
+              const float soft = __expf(p) * invZ;
               c = gk * ((t == ih ? 1.f : 0.f) + soft * (p - bar)) * p * (m2e2 * d);
             } else {
-              const float soft = expf(-(d - dm)) / Zr;
+              const float soft = __expf(-(d - shift)) * invZ;
               c = gk * ((t == ih ? 1.f : 0.f) - soft * (d - bar));
             }
-            if (g.dist == IGN_DIST_L1) {
+            if (OP == OP_L1) {
               coef = c;
             } else if (g.dist == IGN_DIST_SQL2) {
               coef = c; sc0 += c;
@@ -509,16 +526,16 @@ __global__ void __launch_bounds__(kThreads, 1) shapelet_bwd_kernel(const Geo g, 
       if (lane == 0) { rowsc[row * 2] = sc0; rowsc[row * 2 + 1] = sc1; }
     }
     __syncthreads();
-    if (threadIdx.x < g.KB * 2) {   // fixed-order accumulation of the per-shapelet scalars
-      const int kl = threadIdx.x >> 1, j = threadIdx.x & 1;
+    if (OP != OP_L1 && threadIdx.x < g.KB * 2) {   // fixed-order accumulation of the per-shapelet scalars
+      const int skl = threadIdx.x >> 1, j = threadIdx.x & 1;
       float s = scal[threadIdx.x];
-      for (int rbl = 0; rbl < g.NB; ++rbl) s += rowsc[(rbl * g.KB + kl) * 2 + j];
+      for (int rbl = 0; rbl < g.NB; ++rbl) s += rowsc[(rbl * g.KB + skl) * 2 + j];
       scal[threadIdx.x] = s;
     }
     // ---- phase B: contraction over windows, sliding along t with a 12-register ring of x
     if (active && bl < nb && ta < tb) {
       const float* xr = xs + ((size_t)bl * g.s + r) * g.XQ + q0;
-      const float* cb = cbuf + ((size_t)bl * g.KB + kc * KK) * g.DP;
+      const float* cb = cbuf + ((size_t)bl * g.KB + kl) * g.DP;
       float xv[12];
       {
         float4 v0 = *reinterpret_cast<const float4*>(xr + ta);
@@ -531,16 +548,12 @@ __global__ void __launch_bounds__(kThreads, 1) shapelet_bwd_kernel(const Geo g, 
         float4 nx = *reinterpret_cast<const float4*>(xr + (TQ) + 8);                         \
         xv[((BASE) + 8) % 12] = nx.x; xv[((BASE) + 9) % 12] = nx.y;                          \
         xv[((BASE) + 10) % 12] = nx.z; xv[((BASE) + 11) % 12] = nx.w;                        \
-        float4 c4[KK];                                                                       \
-        _Pragma("unroll") for (int k = 0; k < KK; ++k)                                       \
-          c4[k] = *reinterpret_cast<const float4*>(cb + k * g.DP + (TQ));                    \
+        const float4 c4 = *reinterpret_cast<const float4*>(cb + (TQ));                       \
         _Pragma("unroll") for (int i = 0; i < LT; ++i) {                                     \
-          _Pragma("unroll") for (int k = 0; k < KK; ++k) {                                   \
-            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].x, xv[((BASE) + i + 0) % 12], wreg[i][k]); \
-            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].y, xv[((BASE) + i + 1) % 12], wreg[i][k]); \
-            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].z, xv[((BASE) + i + 2) % 12], wreg[i][k]); \
-            acc[i][k] = bwd_op<OP>(acc[i][k], c4[k].w, xv[((BASE) + i + 3) % 12], wreg[i][k]); \
-          }                                                                                  \
+          acc[i] = bwd_op<OP>(acc[i], c4.x, xv[((BASE) + i + 0) % 12], wreg[i]);             \
+          acc[i] = bwd_op<OP>(acc[i], c4.y, xv[((BASE) + i + 1) % 12], wreg[i]);             \
+          acc[i] = bwd_op<OP>(acc[i], c4.z, xv[((BASE) + i + 2) % 12], wreg[i]);             \
+          acc[i] = bwd_op<OP>(acc[i], c4.w, xv[((BASE) + i + 3) % 12], wreg[i]);             \
         }                                                                                    \
       }
       int t = ta;
@@ -557,32 +570,29 @@ __global__ void __launch_bounds__(kThreads, 1) shapelet_bwd_kernel(const Geo g, 
   float* red = cbuf;
   if (active) {
     const int slot = bl * a.nseg + seg;
-    float* dst = red + (((size_t)(kc * ntl + lt)) * nslot + slot) * (LT * KK);
+    float* dst = red + (((size_t)(kl * ntl + lt)) * nslot + slot) * LT;
 #pragma unroll
-    for (int i = 0; i < LT; ++i)
-#pragma unroll
-      for (int k = 0; k < KK; ++k) dst[i * KK + k] = acc[i][k];
+    for (int i = 0; i < LT; ++i) dst[i] = acc[i];
   }
   __syncthreads();
-  const int nout = nkc * ntl * LT * KK;
-  for (int oidx = threadIdx.x; oidx < nout; oidx += kThreads) {
-    const int ik = oidx % (LT * KK);
-    const int tile = oidx / (LT * KK);            // kc*ntl + lt
-    const int okc = tile / ntl, olt = tile - okc * ntl;
-    const int i = ik / KK, kk = ik - i * KK;
-    const float* src = red + (size_t)tile * nslot * (LT * KK) + ik;
+  const int nout = g.KB * ntl * LT;
+  for (int oidx = threadIdx.x; oidx < nout; oidx += nthr) {
+    const int i = oidx % LT;
+    const int tile = oidx / LT;                   // kl*ntl + lt
+    const int okl = tile / ntl, olt = tile - okl * ntl;
+    const float* src = red + (size_t)tile * nslot * LT + i;
     float s = 0.f;
-    for (int sl = 0; sl < nslot; ++sl) s += src[(size_t)sl * (LT * KK)];
+    for (int sl = 0; sl < nslot; ++sl) s += src[(size_t)sl * LT];
     const int oltg = lt_beg + olt;
     const int orr = oltg / tiles_per_res, oq = (oltg - orr * tiles_per_res) * LT + i;
     const int l = oq * g.s + orr;
-    const int k = k0 + okc * KK + kk;
+    const int k = k0 + okl;
     if (k < g.K && l < g.L && oq < (g.L - orr + g.s - 1) / g.s)
       a.part[(((size_t)chunk * g.K + k) * g.M + m) * g.L + l] = s;
   }
   if (lblk == 0 && threadIdx.x < g.KB * 2) {
-    const int kl = threadIdx.x >> 1, j = threadIdx.x & 1;
-    if (k0 + kl < g.K) a.scal[(((size_t)chunk * g.K + k0 + kl) * g.M + m) * 2 + j] = scal[threadIdx.x];
+    const int skl = threadIdx.x >> 1, j = threadIdx.x & 1;
+    if (k0 + skl < g.K) a.scal[(((size_t)chunk * g.K + k0 + skl) * g.M + m) * 2 + j] = scal[threadIdx.x];
   }
 }
 
@@ -646,48 +656,51 @@ bool base_geo(const ign_shapelet_desc& d, Geo& g) {
   return g.Tw > 0;
 }
 
-size_t fwd_smem_floats(const Geo& g, int NB, int KB) {
-  size_t f = (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + (size_t)NB * KB * g.DP + KB;
+int plan_bpc(const Geo& g, int ctas_per_bchunk, int NB) {
+  const int target = 24 * sm_count();
+  int nchunk = max(1, ceil_div(target, max(1, ctas_per_bchunk)));
+  nchunk = min(nchunk, ceil_div(g.B, NB));
+  return round_up(ceil_div(g.B, nchunk), NB);
+}
+
+size_t fwd_smem_floats(const Geo& g, int NB, int KB, int ntile) {
+  size_t f = (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + KB + (size_t)2 * NB * KB * ntile;
   if (g.dist != IGN_DIST_L1) f += (size_t)NB * g.DP;
   return f;
 }
 
-// fraction of issued lanes doing useful work when `nitem` items are spread over 32-lane warps
-double lane_eff(int nitem) { return (double)nitem / (double)(ceil_div(nitem, 32) * 32); }
+struct FwdPlan { int threads; size_t smem_bytes; };
 
-int plan_chunks(const Geo& g, int ctas_per_bchunk, int NB) {
-  const int target = 16 * sm_count();
-  int nchunk = max(1, ceil_div(target, max(1, ctas_per_bchunk)));
-  nchunk = min(nchunk, ceil_div(g.B, NB));
-  int bpc = round_up(ceil_div(g.B, nchunk), NB);
-  return bpc;
-}
-
-bool plan_fwd(Geo& g, int TT, size_t& smem_bytes) {
-  const size_t cap_soft = 100 * 1024, cap_hard = (size_t)max_optin_smem() - 1024;
+bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
+  const size_t cap_soft = 96 * 1024, cap_hard = (size_t)max_optin_smem() - 1024;
   const int Kpad = round_up(g.K, g.KK);
+  const int ntile = g.DP / TT;
   int KB = min(Kpad, 8 * g.KK);
-  while (KB > g.KK && fwd_smem_floats(g, 1, KB) * 4 > cap_soft) KB -= g.KK;
-  if (fwd_smem_floats(g, 1, KB) * 4 > cap_hard) return false;
-  const size_t cap = fwd_smem_floats(g, 1, KB) * 4 > cap_soft ? cap_hard : cap_soft;
-  const int ntile = g.DP / TT, nkc = KB / g.KK;
-  int best = 1; double beff = -1.0;
+  while (KB > g.KK && fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_soft) KB -= g.KK;
+  if (fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_hard) return false;
+  const size_t cap = fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_soft ? cap_hard : cap_soft;
+  const int nkc = KB / g.KK;
+  // resident rows: fill whole rounds of the thread block (idle lanes in the last round are the waste)
+  int best = 1, bthr = 32; double beff = -1.0;
   for (int NB = 1; NB <= min(g.B, 64); ++NB) {
-    if (fwd_smem_floats(g, NB, KB) * 4 > cap) break;
-    double e = lane_eff(NB * ntile * nkc);
-    if (e > beff + 0.005) { beff = e; best = NB; }
+    if (fwd_smem_floats(g, NB, KB, ntile) * 4 > cap) break;
+    const int nitem = NB * ntile * nkc;
+    const int thr = min(kMaxThreads, round_up(nitem, 32));
+    const double e = (double)nitem / (double)(ceil_div(nitem, thr) * thr);
+    if (e > beff + 0.01) { beff = e; best = NB; bthr = thr; }
   }
   g.KB = KB; g.nkb = ceil_div(Kpad, KB); g.NB = best;
-  g.bpc = plan_chunks(g, g.M * g.nkb, best);
-  smem_bytes = fwd_smem_floats(g, best, KB) * 4;
+  g.bpc = plan_bpc(g, g.M * g.nkb, best);
+  fp.threads = bthr;
+  fp.smem_bytes = fwd_smem_floats(g, best, KB, ntile) * 4;
   return true;
 }
 
-struct BwdPlan { int nseg, nlb, tlb, nchunk; size_t smem_bytes; };
+struct BwdPlan { int nseg, nlb, tlb, nchunk, threads; size_t smem_bytes; };
 
 size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
   size_t cred = (size_t)NB * KB * g.DP;
-  if (cred < (size_t)kThreads * LT * g.KK) cred = (size_t)kThreads * LT * g.KK;
+  if (cred < (size_t)kMaxThreads * LT) cred = (size_t)kMaxThreads * LT;
   size_t f = (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + cred + KB + (size_t)NB * KB * 2 + KB * 2;
   if (g.dist != IGN_DIST_L1) f += (size_t)NB * g.DP;
   if (g.dist == IGN_DIST_PEARSON) f += (size_t)NB * g.DP;
@@ -696,31 +709,30 @@ size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
 
 bool plan_bwd(Geo& g, BwdPlan& bp) {
   const size_t cap = (size_t)max_optin_smem() - 1024;
-  const size_t cap_soft = 100 * 1024;
-  const int Kpad = round_up(g.K, g.KK);
+  const size_t cap_soft = 56 * 1024;     // aim for >= 4 CTAs per SM
   const int ntl_all = g.s * g.LQ / LT;
-  // shapelet block: as many as fit the thread budget with at least one full l sweep, capped by smem
-  int KB = min(Kpad, 8 * g.KK);
-  while (KB > g.KK && ((KB / g.KK) * min(ntl_all, kThreads) > kThreads ||
-                       bwd_smem_floats(g, 1, KB) * 4 > cap_soft)) KB -= g.KK;
+  // shapelet block and lag block: KB * tlb threads cover one (sample, segment) slot
+  int KB = min(g.K, 8);
+  while (KB > 1 && bwd_smem_floats(g, 1, KB) * 4 > cap_soft) --KB;
   if (bwd_smem_floats(g, 1, KB) * 4 > cap) return false;
-  const int nkc = KB / g.KK;
-  int tlb = min(ntl_all, kThreads / nkc);
-  int nlb = ceil_div(ntl_all, tlb);
-  tlb = ceil_div(ntl_all, nlb);   // balance l-blocks
-  const int slots = max(1, kThreads / (tlb * nkc));   // (sample, t-segment) slots per CTA
-  // split slots between resident samples and t-segments: prefer more samples until smem runs out
+  int tlb = min(ntl_all, kMaxThreads / KB);
+  const int nlb = ceil_div(ntl_all, tlb);
+  tlb = ceil_div(ntl_all, nlb);          // balance the lag blocks
+  const int per_slot = tlb * KB;
+  const int slots = max(1, kMaxThreads / per_slot);
   int bestNB = 1, bestSeg = 1; double beff = -1.0;
-  for (int NB = 1; NB <= min(min(g.B, slots), 32); ++NB) {
+  for (int NB = 1; NB <= min(min(g.B, slots), 16); ++NB) {
     if (bwd_smem_floats(g, NB, KB) * 4 > (NB == 1 ? cap : cap_soft)) break;
     int nseg = max(1, slots / NB);
-    nseg = min(nseg, max(1, g.DP / 32));            // keep segments >= 32 windows
-    double e = lane_eff(NB * nseg * tlb * nkc) * ((double)(NB * nseg * tlb * nkc) / kThreads);
-    if (e > beff + 0.005) { beff = e; bestNB = NB; bestSeg = nseg; }
+    nseg = min(nseg, max(1, g.DP / 48));             // keep segments >= 48 windows
+    const int nitem = NB * nseg * per_slot;
+    const double e = (double)nitem / (double)round_up(nitem, 32) + 1e-3 * NB;   // prefer more rows per pass on ties
+    if (e > beff + 0.01) { beff = e; bestNB = NB; bestSeg = nseg; }
   }
-  g.KB = KB; g.nkb = ceil_div(Kpad, KB); g.NB = bestNB;
+  g.KB = KB; g.nkb = ceil_div(g.K, KB); g.NB = bestNB;
   bp.nseg = bestSeg; bp.nlb = nlb; bp.tlb = tlb;
-  g.bpc = plan_chunks(g, g.M * g.nkb * nlb, bestNB);
+  bp.threads = round_up(bestNB * bestSeg * per_slot, 32);
+  g.bpc = plan_bpc(g, g.M * g.nkb * nlb, bestNB);
   bp.nchunk = ceil_div(g.B, g.bpc);
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
   return true;
@@ -733,21 +745,21 @@ int set_smem(Kern kern, size_t bytes) {
 }
 
 template <int OP, int KK, int TT>
-int run_fwd(const Geo& g, const FwdArgs& a, size_t smem, cudaStream_t st) {
-  int rc = set_smem(shapelet_fwd_kernel<OP, KK, TT>, smem);
+int run_fwd(const Geo& g, const FwdArgs& a, const FwdPlan& fp, cudaStream_t st) {
+  int rc = set_smem(shapelet_fwd_kernel<OP, KK, TT>, fp.smem_bytes);
   if (rc) return rc;
   dim3 grid(g.M, g.nkb, ceil_div(g.B, g.bpc));
-  shapelet_fwd_kernel<OP, KK, TT><<<grid, kThreads, smem, st>>>(g, a);
+  shapelet_fwd_kernel<OP, KK, TT><<<grid, fp.threads, fp.smem_bytes, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }
 
-template <int OP, int KK>
+template <int OP>
 int run_bwd(const Geo& g, const BwdArgs& a, const BwdPlan& bp, cudaStream_t st) {
-  int rc = set_smem(shapelet_bwd_kernel<OP, KK>, bp.smem_bytes);
+  int rc = set_smem(shapelet_bwd_kernel<OP>, bp.smem_bytes);
   if (rc) return rc;
   dim3 grid(g.M, g.nkb * bp.nlb, bp.nchunk);
-  shapelet_bwd_kernel<OP, KK><<<grid, kThreads, bp.smem_bytes, st>>>(g, a);
+  shapelet_bwd_kernel<OP><<<grid, bp.threads, bp.smem_bytes, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }
@@ -756,17 +768,15 @@ int run_bwd(const Geo& g, const BwdArgs& a, const BwdPlan& bp, cudaStream_t st) 
 
 int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
                              const double* pre2, const float* W, const float* thr, float* p, float* dmin,
-                             int* arg_hard, int* argmin, float* Z, float* S1, float* dstore,
-                             cudaStream_t st) {
+                             int* argmin, float* dstore, cudaStream_t st) {
   Geo g;
   if (!base_geo(d, g)) { set_error("shapelet_forward: T=%d < L=%d (unfold would raise)", d.T, d.L); return IGN_ERR_INVALID; }
   const int TT = g.Tw >= 64 ? 8 : 4;
-  if (TT == 4) g.DP = round_up(g.Tw, 8);   // pitch stays a multiple of 8 (also a multiple of 4)
-  size_t smem = 0;
-  if (!plan_fwd(g, TT, smem)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
-  FwdArgs a{xn, pre1, pre2, W, thr, p, dmin, arg_hard, argmin, Z, S1, dstore};
+  FwdPlan fp;
+  if (!plan_fwd(g, TT, fp)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  FwdArgs a{xn, pre1, pre2, W, thr, p, dmin, argmin, dstore};
   const bool l1 = d.dist == IGN_DIST_L1;
-#define IGN_DISPATCH(OPV, KKV, TTV) return run_fwd<OPV, KKV, TTV>(g, a, smem, st)
+#define IGN_DISPATCH(OPV, KKV, TTV) return run_fwd<OPV, KKV, TTV>(g, a, fp, st)
   if (l1) {
     if (g.KK == 5) { if (TT == 8) IGN_DISPATCH(OP_L1, 5, 8); else IGN_DISPATCH(OP_L1, 5, 4); }
     else           { if (TT == 8) IGN_DISPATCH(OP_L1, 4, 8); else IGN_DISPATCH(OP_L1, 4, 4); }
@@ -785,8 +795,7 @@ size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
 }
 
 int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
-                             const double* pre2, const float* W, const float* gr, const int* arg_hard,
-                             const float* dmin, const float* Z, const float* S1, const float* dstore,
+                             const double* pre2, const float* W, const float* gr, const float* dstore,
                              float* dW, void* ws, size_t ws_bytes, cudaStream_t st) {
   Geo g; BwdPlan bp;
   if (!base_geo(d, g)) { set_error("shapelet_backward: T=%d < L=%d", d.T, d.L); return IGN_ERR_INVALID; }
@@ -794,12 +803,9 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   const size_t npart = (size_t)bp.nchunk * d.K * d.M * d.L;
   const size_t need = (npart + (size_t)bp.nchunk * d.K * d.M * 2) * sizeof(float);
   if (ws_bytes < need) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, need); return IGN_ERR_INVALID; }
-  BwdArgs a{xn, pre1, pre2, W, gr, arg_hard, dmin, Z, S1, dstore,
+  BwdArgs a{xn, pre1, pre2, W, gr, dstore,
             reinterpret_cast<float*>(ws), reinterpret_cast<float*>(ws) + npart, bp.nseg, bp.nlb, bp.tlb};
-  int rc;
-  const bool l1 = d.dist == IGN_DIST_L1;
-  if (l1) rc = g.KK == 5 ? run_bwd<OP_L1, 5>(g, a, bp, st) : run_bwd<OP_L1, 4>(g, a, bp, st);
-  else    rc = g.KK == 5 ? run_bwd<OP_DOT, 5>(g, a, bp, st) : run_bwd<OP_DOT, 4>(g, a, bp, st);
+  int rc = d.dist == IGN_DIST_L1 ? run_bwd<OP_L1>(g, a, bp, st) : run_bwd<OP_DOT>(g, a, bp, st);
   if (rc) return rc;
   shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, a.part, a.scal, dW, d.K, d.M, d.L,
                                                               bp.nchunk, d.dist);

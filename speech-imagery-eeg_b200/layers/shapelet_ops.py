@@ -133,18 +133,18 @@ class _ShapeletTransform(torch.autograd.Function):
         pre1 = pre2 = None
         if dist != "l1":
             pre1, pre2 = pack.prefix()
-        need_grad = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        # (grad mode is always off inside Function.forward; needs_input_grad is False under torch.no_grad())
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         dev = xn.device
-        out = torch.empty((4, B, K, M), dtype=torch.float32, device=dev)     # p, dmin, Z, S1
-        idx = torch.empty((2, B, K, M), dtype=torch.int32, device=dev)      # arg_hard, argmin
+        out = torch.empty((2, B, K, M), dtype=torch.float32, device=dev)     # p, dmin
+        idx = torch.empty((B, K, M), dtype=torch.int32, device=dev)         # argmin_t d
         dstore = None
         if need_grad:
             Tw = C.padded_windows(T, L, int(stride))
             dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             C.check(C.lib.ign_shapelet_forward(byref(desc), _ptr(xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(thr),
-                                               _ptr(out[0]), _ptr(out[1]), _ptr(idx[0]), _ptr(idx[1]),
-                                               _ptr(out[2]), _ptr(out[3]), _ptr(dstore), _stream()),
+                                               _ptr(out[0]), _ptr(out[1]), _ptr(idx), _ptr(dstore), _stream()),
                     "ign_shapelet_forward")
         ctx.set_materialize_grads(False)
         ctx.desc = desc
@@ -152,13 +152,13 @@ class _ShapeletTransform(torch.autograd.Function):
         ctx.pack = pack
         ctx.thr_shape = None if threshold is None else threshold.shape
         if need_grad:
-            ctx.save_for_backward(Wc, out, idx, dstore)
+            ctx.save_for_backward(Wc, out, dstore)
         ctx.mark_non_differentiable(idx)
         return out[0], out[1], idx
 
     @staticmethod
     def backward(ctx, g_p, g_dmin, _g_idx):
-        Wc, out, idx, dstore = ctx.saved_tensors
+        Wc, out, dstore = ctx.saved_tensors
         desc, pack = ctx.desc, ctx.pack
         # d.min() (Shapelet.py:84) feeds reporting only; a gradient arriving there follows the hard argmin
         # and is not produced by any loss of the reference (experiment_classification.py:325-329).
@@ -185,15 +185,14 @@ class _ShapeletTransform(torch.autograd.Function):
             dW = torch.empty_like(Wc)
             with torch.cuda.device(g.device):
                 C.check(C.lib.ign_shapelet_backward(byref(desc), _ptr(pack.xn), _ptr(pre1), _ptr(pre2), _ptr(Wc),
-                                                    _ptr(g), _ptr(idx[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
-                                                    _ptr(dstore), _ptr(dW), _ptr(ws), int(nbytes), _stream()),
+                                                    _ptr(g), _ptr(dstore), _ptr(dW), _ptr(ws), int(nbytes), _stream()),
                         "ign_shapelet_backward")
         return dW, dthr, None, None, None, None, None, None
 
 
 def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: float = 1.0, dist: str = "l1",
                        pool: str = "rbf_max", threshold: Optional[torch.Tensor] = None, precision: str = "fp32"):
-    """Returns (p [B,K,M], dmin [B,K,M], idx [2,B,K,M] int32 = (hard index, argmin_t d))."""
+    """Returns (p [B,K,M], dmin [B,K,M], argmin_t d [B,K,M] int32)."""
     _require_cuda(W, "shapelet weights")
     _check_device(W.device)
     if pool == "lts_min" and threshold is None:

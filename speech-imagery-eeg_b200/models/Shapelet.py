@@ -40,7 +40,7 @@ class Shapelet(nn.Module):
         return None
 
     def transform(self, pack: SeriesPack):
-        """Fused distance + pooling on a packed, normalised batch -> ([B,K*M], [B,K*M], idx[2,B,K,M])."""
+        """Fused distance + pooling on a packed, normalised batch -> ([B,K*M], [B,K*M], argmin_t d [B,K,M])."""
         if pack.T < self.length:   # what x.unfold raises in Shapelet.py:61
             raise RuntimeError(f"maximum size for tensor at dimension 2 is {pack.T} but size is {self.length}")
         p, dmin, idx = shapelet_transform(pack, self.weights, self.stride, self.eps, self._dist(), self.pool,
@@ -120,7 +120,7 @@ class ShapeBottleneckModel(nn.Module):
         self.dropout = nn.Dropout(p=configs.dropout)
         self.lambda_reg = configs.lambda_reg      # L1 on classifier weights
         self.lambda_div = configs.lambda_div      # shapelet diversity
-        self.last_indices = None                  # (hard idx, argmin_t d) per group of the latest forward
+        self.last_indices = None                  # argmin_t d [B,K,M] per group of the latest forward
 
     def _build_layers(self, configs, num_shapelet, shapelet_len):
         precision = getattr(configs, "shapelet_precision", "fp32")
