@@ -1,0 +1,379 @@
+"""Contract benchmark: InterpGN training throughput on synthetic CHISCO-shaped EEG (BASELINE.json config 2:
+125 channels, T=1000, 3 classes, default shapelet set K=5 x L in {100,200,300,500}, FCN deep expert).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step is one full training step (forward, backward, gradient all-reduce when N>1, Adam) on a per-GPU batch
+of --batch samples (weak scaling).  Rank 0 prints ONE JSON line:
+  value        samples/s, whole job, inputs already resident in HBM, CUDA events, max over ranks
+  e2e          the same step through the public Experiment API with the batch copied from pinned host
+               memory every step and the loss read back every step (host clock, max over ranks)
+  roofline     the dominant kernel of the step, timed live with CUDA events on the launching stream
+  rooflines    the same for every kernel family of the hot path
+  cpu_baseline the CPU restatement of the reference path (oracle/, "port") timed on this box's host cores on a
+               bounded sample (N=1 only)
+`--impl reference` times that CPU path alone under the same contract (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "speech-imagery-eeg_b200"))
+
+import torch  # noqa: E402
+
+CONFIG2 = dict(enc_in=125, seq_len=1000, num_class=3)          # BASELINE.json configs[1]
+LENGTH_FRACS = [0.1, 0.2, 0.3, 0.5]
+K_PER_LEN = 5
+FP32_LANES_PER_SM = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
+    ap.add_argument("--dnn_type", default="FCN")
+    ap.add_argument("--distance_func", default="euclidean")
+    ap.add_argument("--memory_efficient", action="store_true")
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--num_class", type=int, default=3)
+    ap.add_argument("--cpu_batch", type=int, default=2)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--amp", action="store_true", help="bf16 autocast for the deep expert (reference default is fp32 in its scripts)")
+    return ap.parse_args()
+
+
+def model_args(a):
+    from types import SimpleNamespace
+    return SimpleNamespace(
+        model="InterpGN", dnn_type=a.dnn_type, dataset="CHISCO-synthetic", data="synthetic",
+        enc_in=CONFIG2["enc_in"], seq_len=CONFIG2["seq_len"], num_class=a.num_class, c_out=a.num_class,
+        epsilon=1.0, distance_func=a.distance_func, memory_efficient=a.memory_efficient, sbm_cls="linear",
+        dropout=0.0, lambda_reg=0.1, lambda_div=0.1, num_shapelet=10, shapelet_precision=a.precision,
+        lr=5e-3, train_epochs=500, gradient_accumulation_steps=1, gradient_clip=0, pos_weight=False,
+        beta_schedule="constant", amp=a.amp, gating_value=None, batch_size=a.batch, patience=50, seed=0,
+        num_workers=0, log_interval=20, min_epochs=0, lr_decay=False,
+        # Transformer expert (run.py defaults)
+        task_name="classification", pred_len=0, label_len=0, output_attention=False, d_model=512, embed="timeF",
+        freq="h", factor=1, n_heads=8, d_ff=2048, activation="gelu", e_layers=2)
+
+
+def algorithmic_elements(B, M, T, K, fracs):
+    """E = B*M*sum_g K*T'_g*L_g window-shapelet-lag elements."""
+    import math
+    out = {}
+    for f in fracs:
+        L = max(3, math.ceil(f * T))
+        out[L] = B * M * K * (T - L + 1) * L
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full summary, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU restatement of the reference step (oracle) — the cpu_baseline leg and the --impl reference arm
+# ----------------------------------------------------------------------------------------------------
+class CpuReferenceStep:
+    """One InterpGN(FCN) training step exactly as the reference computes it on CPU: eager unfold/broadcast
+    distance (Shapelet.py:61-84) through oracle/ign_oracle.py, FCN expert, Gini gate, CE + regulariser +
+    beta*CE(shapelet_preds), Adam lr 5e-3 (experiment_classification.py:313-343), fp32, AMP off."""
+
+    def __init__(self, a):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ign_oracle as O
+        from models.FullyConvNet import FullyConvNetwork
+        self.O = O
+        cfg = model_args(a)
+        torch.manual_seed(0)
+        T, M, C = cfg.seq_len, cfg.enc_in, cfg.num_class
+        self.lens = O.shapelet_lengths(T, LENGTH_FRACS)
+        self.strides = [O.shapelet_stride(T, L) for L in self.lens]
+        self.Ws = [torch.normal(0, 1, (K_PER_LEN, M, L)).requires_grad_(True) for L in self.lens]
+        self.Wc = (torch.randn(C, K_PER_LEN * M * len(self.lens)) * 0.02).requires_grad_(True)
+        self.fcn = FullyConvNetwork(cfg)
+        self.mode = O.resolve_mode(a.distance_func, a.memory_efficient)
+        self.opt = torch.optim.Adam(self.Ws + [self.Wc] + list(self.fcn.parameters()), lr=5e-3)
+        self.cfg = cfg
+
+    def step(self, x, y):
+        O = self.O
+        sbm_out, probs, dists = O.sbm_forward(x, self.Ws, self.strides, self.Wc, 1.0, self.mode)
+        deep_out = self.fcn(x)
+        out, eta = O.gate_forward(sbm_out, deep_out)
+        loss = torch.nn.functional.cross_entropy(out, y) + O.sbm_loss(self.Wc, self.Ws, 0.1, 0.1) \
+            + torch.nn.functional.cross_entropy(sbm_out, y)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return float(loss)
+
+
+def time_cpu_reference(a, steps, warmup, batch, budget_s=None):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = CpuReferenceStep(a)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, ref.cfg.seq_len, ref.cfg.enc_in, generator=g)
+    y = torch.randint(0, ref.cfg.num_class, (batch,), generator=g)
+    for _ in range(warmup):
+        ref.step(x, y)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        ref.step(x, y)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return batch * done / dt, dt / done * 1e3, done, cores
+
+
+def run_reference_arm(a):
+    """The reference's own CPU implementation of the path (oracle port: the reference is pure Python and its
+    modules cannot travel to the GPU box; oracle/ign_oracle.py restates them line by line and is pinned to
+    their outputs by tests/golden).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    # bounded sample: one CHISCO-shaped sample per step (the reference needs ~4 GB per sample), capped in time
+    sps, ms, done, cores = time_cpu_reference(a, a.steps, min(a.warmup, 1), 1, budget_s=240.0)
+    line = {
+        "impl": "reference", "metric": "train samples/sec", "value": sps, "unit": "samples/s", "n_gpus": a.gpus,
+        "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, 1, 1),
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "InterpGN(%s) full train step, batch 1 of the config-2 workload, %d steps" % (a.dnn_type, done)},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(a, per_gpu_batch, world):
+    return {"workload": "InterpGN(%s) train step on synthetic CHISCO-shaped EEG: 125 ch x T=1000, %d classes, "
+                        "shapelets K=5 x L={100,200,300,500}, distance_func=%s%s" % (
+                            a.dnn_type, a.num_class, a.distance_func, "+memory_efficient" if a.memory_efficient else ""),
+            "baseline_config": "configs[1]", "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world,
+            "parallelism": "dp%d" % world, "precision": a.precision, "amp": bool(a.amp),
+            "l2": "inputs larger than L2 (x 128 MB + saved distances 1.9 GB per step)"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    import torch.distributed as dist
+    from exp.experiment_classification import Experiment
+    from layers.shapelet_ops import STATS
+
+    cfg = model_args(a)
+    torch.manual_seed(0)
+    exp = Experiment(cfg, load_data=False)          # also initialises torch.distributed from torchrun's env
+    rank, world, dev = exp.rank, exp.world, exp.device
+    exp.model.train()
+    torch.set_float32_matmul_precision("medium")    # experiment_classification.py:297
+    B, T, M, C = a.batch, cfg.seq_len, cfg.enc_in, cfg.num_class
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, T, M, device=dev, generator=gen)
+    y = torch.randint(0, C, (B,), device=dev, generator=gen)
+    mask = torch.ones(B, T, device=dev)
+    exp.grads.zero_grad()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    step_no = 0
+    for _ in range(max(a.warmup, 3)):
+        step_no += 1
+        exp.train_step(x, y, mask, 0, step_no)
+    # ---------------- device-resident timed region ----------------
+    sampler = ClockSampler(exp.local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    STATS.reset(timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_no += 1
+        exp.train_step(x, y, mask, 0, step_no)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = STATS.launches
+    kern = STATS.summary()
+    STATS.reset(timing=False)
+    value = world * B * a.steps / (ms_total * 1e-3)
+
+    # ---------------- end-to-end region: pinned host batch in, loss out, every step ----------------
+    xh = torch.randn(B, T, M).pin_memory()
+    yh = torch.randint(0, C, (B, 1)).pin_memory()
+    mh = torch.ones(B, T, dtype=torch.bool).pin_memory()
+    for _ in range(2):
+        step_no += 1
+        float(exp.train_step(*exp._to_device(xh, yh, mh), 0, step_no))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_no += 1
+        loss = exp.train_step(*exp._to_device(xh, yh, mh), 0, step_no)
+        loss_host = float(loss)                    # D2H read of the step's result
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * B * a.steps / e2e_s, "unit": "samples/s",
+           "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8 + mh.numel(), "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_s / a.steps * 1e3, "last_loss": loss_host}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- rooflines from the live per-kernel CUDA-event times ----------------
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    alu_peak = sms * FP32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12        # T FP32 instr/s (FADD/FSETP: 1 op each)
+    E = algorithmic_elements(B, M, T, K_PER_LEN, LENGTH_FRACS)
+    l1 = (a.distance_func not in ("cosine", "pearson")) and not a.memory_efficient
+    fams = {}
+    for tag, (n, ms) in kern.items():
+        fam = tag.split("/")[0]
+        L = int(tag.rsplit("L", 1)[1]) if "/L" in tag else None
+        f = fams.setdefault(fam, {"launches": 0, "ms": 0.0, "ops": 0.0, "bytes": 0.0})
+        f["launches"] += n; f["ms"] += ms
+        if fam == "shapelet_fwd":
+            f["ops"] += n * 2.0 * E[L]                      # 2 flop per element
+        elif fam == "shapelet_bwd":
+            f["ops"] += n * 4.0 * E[L]
+        elif fam == "instnorm":
+            f["bytes"] += n * (2.0 * B * T * M * 4)
+        elif fam == "window_prefix":
+            f["bytes"] += n * (B * M * T * 4 + 2.0 * B * M * (T + 1) * 8)
+    rooflines = []
+    for fam, f in sorted(fams.items(), key=lambda kv: -kv[1]["ms"]):
+        avg_ms = f["ms"] / max(1, f["launches"])
+        r = {"kernel": fam, "launches": f["launches"], "avg_ms": avg_ms, "share_of_step": f["ms"] / ms_total}
+        if f["ops"]:
+            # L1 executes 1 FP32 op per algorithmic flop (no FMA): peak = lanes*clock; dot modes are FFMA (2 flop/op)
+            peak = alu_peak if l1 else 2.0 * alu_peak
+            ach = f["ops"] / (f["ms"] * 1e-3) / 1e12
+            r.update(bound="fp32_alu", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                     peak_source="%d SMs x %d FP32 lanes x %.0f MHz (%s)" % (sms, FP32_LANES_PER_SM, sm_max_mhz, peak_src),
+                     traffic=traffic_from_profiles(fam))
+        elif f["bytes"]:
+            ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+            r.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
+                     peak_source=peak_src, traffic=traffic_from_profiles(fam))
+        rooflines.append(r)
+    dominant = next((r for r in rooflines if "bound" in r), None)
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        sps, ms, done, cores = time_cpu_reference(a, 1, 0, a.cpu_batch)
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "1 full InterpGN(%s) train step on %d CHISCO-shaped samples (oracle/ign_oracle.py restatement "
+                         "of the reference's eager path, fp32, %d threads)" % (a.dnn_type, a.cpu_batch, cores),
+               "ms_per_step": ms}
+
+    line = {
+        "metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, B, world),
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": dominant, "rooflines": rooflines, "cpu_baseline": cpu,
+        "shapelet_layer": {"fwd_tflops": fams.get("shapelet_fwd", {}).get("ops", 0) / max(1e-9, fams.get("shapelet_fwd", {}).get("ms", 0) * 1e-3) / 1e12,
+                           "bwd_tflops": fams.get("shapelet_bwd", {}).get("ops", 0) / max(1e-9, fams.get("shapelet_bwd", {}).get("ms", 0) * 1e-3) / 1e12,
+                           "share_of_step": sum(f["ms"] for k, f in fams.items() if k.startswith("shapelet")) / ms_total},
+        "allreduce_bytes_per_step": exp.grads.nbytes() if world > 1 else 0,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

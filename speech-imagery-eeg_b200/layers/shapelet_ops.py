@@ -44,6 +44,41 @@ def _require_cuda(t: torch.Tensor, name: str):
 _checked_devices = set()
 
 
+class KernelStats:
+    """Launch counter + optional CUDA-event timing of every C-ABI call, on the stream the kernels run on.
+    bench.py enables it around the timed region to obtain per-kernel durations for the roofline."""
+
+    def __init__(self):
+        self.launches = 0          # kernels launched through the C ABI since the last reset
+        self.timing = False
+        self.records = []          # (tag, start_event, end_event)
+
+    def reset(self, timing=False):
+        self.launches, self.timing, self.records = 0, timing, []
+
+    def call(self, tag, nkernels, fn):
+        self.launches += nkernels
+        if not self.timing:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.records.append((tag, e0, e1))
+        return out
+
+    def summary(self):
+        """{tag: (calls, total_ms)}; call after torch.cuda.synchronize()."""
+        agg = {}
+        for tag, e0, e1 in self.records:
+            n, t = agg.get(tag, (0, 0.0))
+            agg[tag] = (n + 1, t + e0.elapsed_time(e1))
+        return agg
+
+
+STATS = KernelStats()
+
+
 def _check_device(dev: torch.device):
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     if idx not in _checked_devices:
@@ -77,8 +112,8 @@ class SeriesPack:
             B, M, T = self.B, self.M, self.T
             pre = torch.empty((2, B, M, T + 1), dtype=torch.float64, device=self.xn.device)
             with torch.cuda.device(self.xn.device):
-                C.check(C.lib.ign_window_prefix(_ptr(self.xn), _ptr(pre[0]), _ptr(pre[1]), B, M, T, _stream()),
-                        "ign_window_prefix")
+                C.check(STATS.call("window_prefix", 1, lambda: C.lib.ign_window_prefix(
+                    _ptr(self.xn), _ptr(pre[0]), _ptr(pre[1]), B, M, T, _stream())), "ign_window_prefix")
             self._pre = (pre[0], pre[1])
         return self._pre
 
@@ -109,8 +144,8 @@ def instance_norm(x: torch.Tensor) -> SeriesPack:
     B, T, M = x.shape
     xn = torch.empty((B, M, C.padded_len(T)), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        C.check(C.lib.ign_instnorm_forward(_ptr(x), _ptr(xn), None, None, B, T, M, _stream()),
-                "ign_instnorm_forward")
+        C.check(STATS.call("instnorm", 1, lambda: C.lib.ign_instnorm_forward(
+            _ptr(x), _ptr(xn), None, None, B, T, M, _stream())), "ign_instnorm_forward")
     return SeriesPack(xn, T)
 
 
@@ -143,11 +178,12 @@ class _ShapeletTransform(torch.autograd.Function):
             Tw = C.padded_windows(T, L, int(stride))
             dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            C.check(C.lib.ign_shapelet_forward(byref(desc), _ptr(xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(thr),
-                                               _ptr(out[0]), _ptr(out[1]), _ptr(idx), _ptr(dstore), _stream()),
-                    "ign_shapelet_forward")
+            C.check(STATS.call("shapelet_fwd/%s/L%d" % (dist, L), 1, lambda: C.lib.ign_shapelet_forward(
+                byref(desc), _ptr(xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(thr), _ptr(out[0]), _ptr(out[1]),
+                _ptr(idx), _ptr(dstore), _stream())), "ign_shapelet_forward")
         ctx.set_materialize_grads(False)
         ctx.desc = desc
+        ctx.dist = dist
         ctx.pool = pool
         ctx.pack = pack
         ctx.thr_shape = None if threshold is None else threshold.shape
@@ -184,9 +220,9 @@ class _ShapeletTransform(torch.autograd.Function):
             ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=g.device)
             dW = torch.empty_like(Wc)
             with torch.cuda.device(g.device):
-                C.check(C.lib.ign_shapelet_backward(byref(desc), _ptr(pack.xn), _ptr(pre1), _ptr(pre2), _ptr(Wc),
-                                                    _ptr(g), _ptr(dstore), _ptr(dW), _ptr(ws), int(nbytes), _stream()),
-                        "ign_shapelet_backward")
+                C.check(STATS.call("shapelet_bwd/%s/L%d" % (ctx.dist, desc.L), 2, lambda: C.lib.ign_shapelet_backward(
+                    byref(desc), _ptr(pack.xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(g), _ptr(dstore), _ptr(dW),
+                    _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
         return dW, dthr, None, None, None, None, None, None
 
 
@@ -214,8 +250,8 @@ class _GiniGate(torch.autograd.Function):
         use_gate = gating_value is not None
         gv = float(gating_value) if use_gate else 0.0
         with torch.cuda.device(s.device):
-            C.check(C.lib.ign_gate_forward(_ptr(s), _ptr(z), _ptr(out), _ptr(eta), B, Cn, int(use_gate), gv, _stream()),
-                    "ign_gate_forward")
+            C.check(STATS.call("gate_fwd", 1, lambda: C.lib.ign_gate_forward(
+                _ptr(s), _ptr(z), _ptr(out), _ptr(eta), B, Cn, int(use_gate), gv, _stream())), "ign_gate_forward")
         ctx.save_for_backward(s, z)
         ctx.gate = (use_gate, gv)
         ctx.in_dtypes = (sbm_out.dtype, deep_out.dtype)
@@ -231,8 +267,9 @@ class _GiniGate(torch.autograd.Function):
         gz = torch.empty_like(z)
         use_gate, gv = ctx.gate
         with torch.cuda.device(s.device):
-            C.check(C.lib.ign_gate_backward(_ptr(s), _ptr(z), _ptr(go), _ptr(ge), _ptr(gs), _ptr(gz), B, Cn,
-                                            int(use_gate), gv, _stream()), "ign_gate_backward")
+            C.check(STATS.call("gate_bwd", 1, lambda: C.lib.ign_gate_backward(
+                _ptr(s), _ptr(z), _ptr(go), _ptr(ge), _ptr(gs), _ptr(gz), B, Cn, int(use_gate), gv, _stream())),
+                "ign_gate_backward")
         return gs.to(ctx.in_dtypes[0]), gz.to(ctx.in_dtypes[1]), None
 
 

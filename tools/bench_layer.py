@@ -75,10 +75,10 @@ def main():
                 p.backward(g, retain_graph=True)
             tb = timeit(bwd, a.iters, flush)
             tot_f += tft; tot_b += tb
-            print(f"{dist:8s} L={L:4d} fwd(infer) {tf:8.3f} ms {2 * E / tf / 1e9:8.1f} GFLOP/s | fwd(train) {tft:8.3f} ms | "
-                  f"bwd {tb:8.3f} ms {4 * E / tb / 1e9:8.1f} GFLOP/s")
+            print(f"{dist:8s} L={L:4d} fwd(infer) {tf:8.3f} ms {2 * E / tf / 1e9:8.1f} TFLOP/s | fwd(train) {tft:8.3f} ms | "
+                  f"bwd {tb:8.3f} ms {4 * E / tb / 1e9:8.1f} TFLOP/s")
             rows.append(dict(kernel="shapelet", dist=dist, L=L, fwd_infer_ms=tf, fwd_train_ms=tft, bwd_ms=tb,
-                             fwd_gflops=2 * E / tf / 1e9, bwd_gflops=4 * E / tb / 1e9, E=E))
+                             fwd_tflops=2 * E / tf / 1e9, bwd_tflops=4 * E / tb / 1e9, E=E))
         print(f"{dist:8s} total fwd(train) {tot_f:8.3f} ms  bwd {tot_b:8.3f} ms  -> {a.B / (tot_f + tot_b) * 1e3:9.1f} samples/s (layer only)")
     if a.json:
         json.dump(rows, open(a.json, "w"), indent=1)
