@@ -86,10 +86,14 @@ int32_t ign_padded_windows(int32_t T, int32_t L, int32_t stride);
 int32_t ign_instnorm_forward(const float* x_dev, float* xn_dev, float* mean_dev, float* rstd_dev,
                              int32_t B, int32_t T, int32_t M, void* stream);
 
-/* Sliding-window statistics for the norm terms of cosine / pearson / sql2:
- *   pre1_dev[b,m,j] = sum_{i<j} xn[b,m,i], pre2_dev[b,m,j] = sum_{i<j} xn[b,m,i]^2, j in [0,T], fp64,
- *   row pitch T+1.  ||x_w||^2 of window t = pre2[t*stride+L]-pre2[t*stride] (stride 1) — for stride>1
- *   the same identity holds on the contiguous window. */
+/* pitch (doubles) of one prefix-sum row: T+4 rounded up to a multiple of 4 (32-byte rows) */
+int32_t ign_prefix_pitch(int32_t T);
+
+/* Sliding-window statistics for the norm terms of cosine / pearson / sql2 (fp64 exclusive prefix sums):
+ *   P1[b,m,j] = sum_{i<j} xn[b,m,i], P2[b,m,j] = sum_{i<j} xn[b,m,i]^2, j in [0,T].
+ *   Storage: row pitch ign_prefix_pitch(T); P[j] is at slot 3+j of its row (slots 0..2 are zero padding, so
+ *   the kernel's 4-sample runs are 32-byte aligned).  ||x_w||^2 of the window starting at sample j0 is
+ *   P2[j0+L]-P2[j0]; its sum is P1[j0+L]-P1[j0]. */
 int32_t ign_window_prefix(const float* xn_dev, double* pre1_dev, double* pre2_dev,
                           int32_t B, int32_t M, int32_t T, void* stream);
 
@@ -117,11 +121,13 @@ size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* desc);
  *   g_dev [B,K,M] = dLoss/d(max_p)  (rbf_max)   or   dLoss/d(min_d)  (lts_min; the caller folds the
  *   sigmoid: g_min = -g_p * p * (1-p), dthreshold = sum_b g_p * p * (1-p))
  *   dstore_dev [B,M,K,Tw] as written by ign_shapelet_forward on the same inputs.
+ *   dmin_dev / argmin_dev [B,K,M]: the forward's outputs; required for lts_min (its hard index and soft-min
+ *   shift), ignored (may be NULL) for rbf_max, whose arg-max-of-p one-hot is re-derived from dstore.
  *   dW_dev [K,M,L] is overwritten (not accumulated).  Deterministic (no float atomics). */
 int32_t ign_shapelet_backward(const ign_shapelet_desc* desc, const float* xn_dev, const double* pre1_dev,
                               const double* pre2_dev, const float* W_dev, const float* g_dev,
-                              const float* dstore_dev, float* dW_dev, void* workspace_dev,
-                              size_t workspace_bytes, void* stream);
+                              const float* dstore_dev, const float* dmin_dev, const int32_t* argmin_dev,
+                              float* dW_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* InterpGN gate + mixture (InterpGN.py:44-52): q=softmax(s), eta=(C*sum q^2-1)/(C-1),
  * if use_gate: eta=1 where eta>gating_value; out=eta*s+(1-eta)*z.  s,z,out [B,C]; eta [B]. */

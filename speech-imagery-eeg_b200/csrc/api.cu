@@ -74,6 +74,7 @@ int32_t ign_device_check(int32_t device) {
 int32_t ign_padded_len(int32_t T) { return padded_len(T); }
 int32_t ign_num_windows(int32_t T, int32_t L, int32_t stride) { return (L <= 0 || stride <= 0) ? 0 : num_windows(T, L, stride); }
 int32_t ign_padded_windows(int32_t T, int32_t L, int32_t stride) { return (L <= 0 || stride <= 0) ? 0 : padded_windows(T, L, stride); }
+int32_t ign_prefix_pitch(int32_t T) { return prefix_pitch(T); }
 
 int32_t ign_instnorm_forward(const float* x, float* xn, float* mean, float* rstd, int32_t B, int32_t T,
                              int32_t M, void* stream) {
@@ -111,14 +112,15 @@ size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
 }
 
 int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const double* pre1, const double* pre2,
-                              const float* W, const float* g, const float* dstore, float* dW, void* ws,
-                              size_t ws_bytes, void* stream) {
+                              const float* W, const float* g, const float* dstore, const float* dmin,
+                              const int32_t* argmin, float* dW, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_desc(d, "shapelet_backward");
   if (rc) return rc;
   IGN_REQUIRE(xn && W && g && dW && ws, "shapelet_backward: null pointer");
   IGN_REQUIRE(dstore, "shapelet_backward: dstore (window distances saved by forward) is required");
+  IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || (dmin && argmin), "shapelet_backward: lts_min needs the forward's dmin and argmin");
   IGN_REQUIRE(d->dist == IGN_DIST_L1 || (pre1 && pre2), "shapelet_backward: dist %d needs the window prefix sums", d->dist);
-  return launch_shapelet_bwd_simt(*d, xn, pre1, pre2, W, g, dstore, dW, ws, ws_bytes, (cudaStream_t)stream);
+  return launch_shapelet_bwd_simt(*d, xn, pre1, pre2, W, g, dstore, dmin, argmin, dW, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int32_t ign_gate_forward(const float* s, const float* z, float* out, float* eta, int32_t B, int32_t C,
@@ -165,10 +167,10 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
   IGN_TRY(cudaMalloc(&xn, nxn * 4));
   IGN_TRY(cudaMalloc(&W, wmax * 4));
   IGN_TRY(cudaMalloc(&out, nf * 2 * 4));
-  if (dist != IGN_DIST_L1) IGN_TRY(cudaMalloc(&pre, (size_t)B * M * (T + 1) * 2 * sizeof(double)));
+  if (dist != IGN_DIST_L1) IGN_TRY(cudaMalloc(&pre, (size_t)B * M * prefix_pitch(T) * 2 * sizeof(double)));
   IGN_TRY(cudaMemcpyAsync(x, x_host, nx * 4, cudaMemcpyHostToDevice, st));
   rc = launch_instnorm(x, xn, nullptr, nullptr, B, T, M, st);
-  double* pre2 = pre ? pre + (size_t)B * M * (T + 1) : nullptr;
+  double* pre2 = pre ? pre + (size_t)B * M * prefix_pitch(T) : nullptr;
   if (!rc && pre) rc = launch_prefix(xn, pre, pre2, B, M, T, st);
   std::vector<float> hp, hd;
   int col = 0;

@@ -35,6 +35,9 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 inline int padded_len(int T) { return round_up(T, 4); }
 inline int num_windows(int T, int L, int s) { return T < L ? 0 : (T - L) / s + 1; }
 inline int padded_windows(int T, int L, int s) { return round_up(num_windows(T, L, s), 4); }
+// fp64 prefix rows: pitch (doubles) and the slot of P[0]; P[j] lives at row*pitch + kPrefixOrigin + j
+constexpr int kPrefixOrigin = 3;
+__host__ __device__ inline int prefix_pitch(int T) { return round_up(T + 4, 4); }
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) ----
 int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, int T, int M,
@@ -46,7 +49,8 @@ int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const 
 size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d);
 int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
                              const double* pre2, const float* W, const float* g, const float* dstore,
-                             float* dW, void* ws, size_t ws_bytes, cudaStream_t st);
+                             const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
+                             cudaStream_t st);
 int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int B, int C, int use_gate,
                     float gv, cudaStream_t st);
 int launch_gate_bwd(const float* s, const float* z, const float* go, const float* ge, float* gs,

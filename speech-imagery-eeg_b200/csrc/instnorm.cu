@@ -14,8 +14,74 @@ namespace {
 constexpr int kNormThreads = 256;
 constexpr int kNormWarps = kNormThreads / 32;
 
-// One CTA per (32-channel tile, sample).  x is read three times (mean, variance, normalise); the tile is
-// T*128 bytes, so passes 2 and 3 hit L2/L1 and DRAM sees one read + one write.
+// ---- single-read instance norm: the whole (T x CT-channel) tile of one sample is staged in shared memory,
+// so DRAM sees exactly one read of x and one write of xn.  CT = 16 keeps the tile at ~68 KB for T = 1000
+// (3 CTAs per SM: one CTA's loads overlap another's stores).  The tile is stored [t][CT+1] so both the
+// channel-major fill (lanes = channels) and the time-major drain (lanes = time) are bank-conflict free.
+template <int CT>
+__global__ void __launch_bounds__(kNormThreads) instnorm_tile_kernel(const float* __restrict__ x,
+                                                                     float* __restrict__ xn,
+                                                                     float* __restrict__ mean_out,
+                                                                     float* __restrict__ rstd_out, int T,
+                                                                     int M, int Tp) {
+  extern __shared__ __align__(16) float tile[];            // [T][CT+1]
+  __shared__ float s_mean[CT], s_den[CT];
+  constexpr int P = CT + 1;
+  constexpr int TPW = 32 / CT;                             // time rows covered by one warp load
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * CT, b = blockIdx.y;
+  const int c = lane % CT, dt = lane / CT;
+  const bool mv = m0 + c < M;
+  const float* xb = x + (size_t)b * T * M + m0 + c;
+
+  // fill: each warp instruction reads TPW rows x CT channels (CT*4 contiguous bytes per row)
+  const int rows_per_iter = kNormWarps * TPW;
+  for (int t0 = warp * TPW + dt; t0 < T; t0 += rows_per_iter * 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * rows_per_iter;
+      v[u] = (mv && t < T) ? __ldg(xb + (size_t)t * M) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * rows_per_iter;
+      if (t < T) tile[t * P + c] = v[u];
+    }
+  }
+  __syncthreads();
+  // statistics: 256/CT threads per channel, two passes over shared memory (mean, then squared deviations)
+  constexpr int TPC = kNormThreads / CT;
+  const int sc = threadIdx.x / TPC, si = threadIdx.x % TPC;
+  float acc = 0.f;
+  for (int t = si; t < T; t += TPC) acc += tile[t * P + sc];
+#pragma unroll
+  for (int o = TPC / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const float mu = acc / (float)T;
+  acc = 0.f;
+  for (int t = si; t < T; t += TPC) { const float d = tile[t * P + sc] - mu; acc = fmaf(d, d, acc); }
+#pragma unroll
+  for (int o = TPC / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (si == 0) {
+    const float sd = sqrtf(acc / (float)(T - 1));          // unbiased, as torch.std; T==1 -> NaN
+    s_mean[sc] = mu; s_den[sc] = sd + 1e-8f;
+    if (m0 + sc < M) {
+      if (mean_out) mean_out[(size_t)b * M + m0 + sc] = mu;
+      if (rstd_out) rstd_out[(size_t)b * M + m0 + sc] = 1.f / (sd + 1e-8f);
+    }
+  }
+  __syncthreads();
+  // drain: one warp per channel row, 128 B per store instruction
+  for (int ch = warp; ch < CT; ch += kNormWarps) {
+    if (m0 + ch >= M) continue;
+    const float mu_c = s_mean[ch], den = s_den[ch];
+    float* dst = xn + ((size_t)b * M + m0 + ch) * Tp;
+    for (int t = lane; t < Tp; t += 32) dst[t] = t < T ? (tile[t * P + ch] - mu_c) / den : 0.f;
+  }
+}
+
+// Fallback for very long series (tile does not fit shared memory): three passes over x, passes 2 and 3
+// mostly from L2.
 __global__ void __launch_bounds__(kNormThreads) instnorm_kernel(const float* __restrict__ x,
                                                                 float* __restrict__ xn,
                                                                 float* __restrict__ mean_out,
@@ -31,7 +97,6 @@ __global__ void __launch_bounds__(kNormThreads) instnorm_kernel(const float* __r
   const bool mv = m < M;
   const float* xb = x + (size_t)b * T * M;
 
-  // pass 1: mean
   float acc = 0.f;
   for (int t = warp; t < T; t += kNormWarps) acc += mv ? __ldg(xb + (size_t)t * M + m) : 0.f;
   part[warp][lane] = acc;
@@ -44,7 +109,6 @@ __global__ void __launch_bounds__(kNormThreads) instnorm_kernel(const float* __r
   }
   __syncthreads();
   const float mu = s_mean[lane];
-  // pass 2: unbiased variance about the mean (two-pass, like torch.std)
   acc = 0.f;
   for (int t = warp; t < T; t += kNormWarps) {
     float v = mv ? __ldg(xb + (size_t)t * M + m) - mu : 0.f;
@@ -57,7 +121,7 @@ __global__ void __launch_bounds__(kNormThreads) instnorm_kernel(const float* __r
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kNormWarps; ++w) s += part[w][lane];
-    float sd = sqrtf(s / (float)(T - 1));   // T==1 -> NaN, as torch.std
+    float sd = sqrtf(s / (float)(T - 1));
     s_den[lane] = sd + 1e-8f;
     if (mv) {
       if (mean_out) mean_out[(size_t)b * M + m] = mu;
@@ -65,7 +129,6 @@ __global__ void __launch_bounds__(kNormThreads) instnorm_kernel(const float* __r
     }
   }
   __syncthreads();
-  // pass 3: normalise + transpose through a padded smem tile; rows of xn are written 128 B at a time
   const int ntile = (Tp + 31) / 32;
   for (int tt = warp; tt < ntile; tt += kNormWarps) {
     const int t0 = tt * 32;
@@ -99,33 +162,46 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
   return v;
 }
 
-// One warp per series row; each lane owns 4 consecutive samples per 128-sample chunk.
+// One warp per series row; each lane owns 4 consecutive samples per 128-sample chunk.  Row layout (pitch PP
+// doubles, 32-byte aligned): [3] = P[0] = 0, [4+j] = P[j+1], so each lane's four results form one aligned
+// 32-byte run and are written with two 16-byte stores.
 __global__ void __launch_bounds__(256) prefix_kernel(const float* __restrict__ xn,
                                                      double* __restrict__ pre1,
-                                                     double* __restrict__ pre2, int rows, int T, int Tp) {
+                                                     double* __restrict__ pre2, int rows, int T, int Tp,
+                                                     int PP) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = xn + (size_t)row * Tp;
-  double* o1 = pre1 + (size_t)row * (T + 1);
-  double* o2 = pre2 + (size_t)row * (T + 1);
+  double* o1 = pre1 + (size_t)row * PP;
+  double* o2 = pre2 + (size_t)row * PP;
   double c1 = 0.0, c2 = 0.0;
-  if (lane == 0) { o1[0] = 0.0; o2[0] = 0.0; }
-  for (int base = 0; base < T; base += 128) {
-    const int j = base + lane * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < Tp) v = *reinterpret_cast<const float4*>(xr + j);   // Tp % 4 == 0, pad columns are zero
+  if (lane < 4) { o1[lane] = 0.0; o2[lane] = 0.0; }
+  const int nchunk = (T + 127) / 128;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane * 4 < Tp) v = *reinterpret_cast<const float4*>(xr + lane * 4);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int j = ch * 128 + lane * 4;
+    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);           // prefetch the next chunk before the scan
+    if (ch + 1 < nchunk && j + 128 < Tp) nv = *reinterpret_cast<const float4*>(xr + j + 128);
     double a0 = v.x, a1 = a0 + (double)v.y, a2 = a1 + (double)v.z, a3 = a2 + (double)v.w;
     double q0 = (double)v.x * v.x, q1 = q0 + (double)v.y * v.y, q2 = q1 + (double)v.z * v.z,
            q3 = q2 + (double)v.w * v.w;
-    double s1 = warp_incl_scan(a3, lane), s2 = warp_incl_scan(q3, lane);
-    double e1 = c1 + s1 - a3, e2 = c2 + s2 - q3;   // exclusive offset of this lane
-    if (j + 0 < T) { o1[j + 1] = e1 + a0; o2[j + 1] = e2 + q0; }
-    if (j + 1 < T) { o1[j + 2] = e1 + a1; o2[j + 2] = e2 + q1; }
-    if (j + 2 < T) { o1[j + 3] = e1 + a2; o2[j + 3] = e2 + q2; }
-    if (j + 3 < T) { o1[j + 4] = e1 + a3; o2[j + 4] = e2 + q3; }
+    const double s1 = warp_incl_scan(a3, lane), s2 = warp_incl_scan(q3, lane);
+    const double e1 = c1 + s1 - a3, e2 = c2 + s2 - q3;     // exclusive offset of this lane
+    if (j + 3 < T) {                                        // whole 32-byte run in range (pad slots absorb the tail)
+      *reinterpret_cast<double2*>(o1 + 4 + j) = make_double2(e1 + a0, e1 + a1);
+      *reinterpret_cast<double2*>(o1 + 6 + j) = make_double2(e1 + a2, e1 + a3);
+      *reinterpret_cast<double2*>(o2 + 4 + j) = make_double2(e2 + q0, e2 + q1);
+      *reinterpret_cast<double2*>(o2 + 6 + j) = make_double2(e2 + q2, e2 + q3);
+    } else {
+      if (j + 0 < T) { o1[4 + j] = e1 + a0; o2[4 + j] = e2 + q0; }
+      if (j + 1 < T) { o1[5 + j] = e1 + a1; o2[5 + j] = e2 + q1; }
+      if (j + 2 < T) { o1[6 + j] = e1 + a2; o2[6 + j] = e2 + q2; }
+    }
     c1 += __shfl_sync(0xffffffffu, s1, 31);
     c2 += __shfl_sync(0xffffffffu, s2, 31);
+    v = nv;
   }
 }
 
@@ -133,15 +209,28 @@ __global__ void __launch_bounds__(256) prefix_kernel(const float* __restrict__ x
 
 int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, int T, int M,
                     cudaStream_t st) {
-  dim3 grid(ceil_div(M, 32), B);
-  instnorm_kernel<<<grid, kNormThreads, 0, st>>>(x, xn, mean, rstd, T, M, padded_len(T));
+  const int Tp = padded_len(T);
+  const size_t tile16 = (size_t)T * 17 * sizeof(float);
+  if (tile16 + 2048 <= (size_t)max_optin_smem()) {
+    static bool configured = false;
+    if (!configured) {
+      IGN_CUDA(cudaFuncSetAttribute(instnorm_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    max_optin_smem() - 2048));
+      configured = true;
+    }
+    dim3 grid(ceil_div(M, 16), B);
+    instnorm_tile_kernel<16><<<grid, kNormThreads, tile16, st>>>(x, xn, mean, rstd, T, M, Tp);
+  } else {
+    dim3 grid(ceil_div(M, 32), B);
+    instnorm_kernel<<<grid, kNormThreads, 0, st>>>(x, xn, mean, rstd, T, M, Tp);
+  }
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }
 
 int launch_prefix(const float* xn, double* pre1, double* pre2, int B, int M, int T, cudaStream_t st) {
   const int rows = B * M;
-  prefix_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(xn, pre1, pre2, rows, T, padded_len(T));
+  prefix_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(xn, pre1, pre2, rows, T, padded_len(T), prefix_pitch(T));
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }

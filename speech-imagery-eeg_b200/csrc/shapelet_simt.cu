@@ -67,12 +67,20 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  const float* xn; const double* pre1; const double* pre2; const float* W; const float* g;
-  const float* dstore;
-  float* part;   // [nchunk][K][M][L]
-  float* scal;   // [nchunk][K][M][2]
+  const float* xn; const float* W;
+  const float* coef;    // [B][M][K][Ts] per-window coefficients a_t written by pool_bwd_kernel
+  float* part;          // [nchunk][K][M][L]
   int nseg, nlb, tlb;   // t-segments per row, l-blocks, l-tiles per l-block
+  int hcap;             // L1 only: capacity (power of two) of the shapelet-value hash set; 0 = always exact
 };
+
+struct PoolArgs {
+  const float* g; const float* dstore; const float* dmin; const int* argmin;
+  const double* pre1; const double* pre2; const float* wstat;   // wstat [K][M]: sum (w-mean)^2 (pearson)
+  float* coef;          // [B][M][K][Ts]
+  float* rowsc;         // [B][M][K][2] per-row scalars for the finalize kernel
+};
+
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory staging helpers
@@ -142,12 +150,12 @@ __device__ void load_series(const Geo& g, const float* __restrict__ xn, const do
       xs[i] = v;
     }
   }
-  if (g.dist != IGN_DIST_L1) {
+  if (g.dist != IGN_DIST_L1 && st0) {
     for (int i = threadIdx.x; i < g.NB * g.DP; i += nthr) {
       const int bl = i / g.DP, t = i - bl * g.DP;
       float a = 0.f, c = 0.f;
       if (bl < nb && t < g.Tw) {
-        const size_t row = ((size_t)(b0 + bl) * g.M + m) * (g.T + 1);
+        const size_t row = ((size_t)(b0 + bl) * g.M + m) * prefix_pitch(g.T) + kPrefixOrigin;
         const int j0 = t * g.s;
         const double sxx = pre2[row + j0 + g.L] - pre2[row + j0];
         if (g.dist == IGN_DIST_SQL2) {
@@ -368,17 +376,133 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
 // ------------------------------------------------------------------------------------------------
 // backward kernel
 // ------------------------------------------------------------------------------------------------
-template <int OP>
-__device__ __forceinline__ float bwd_op(float acc, float c, float x, float w) {
+// L1 backward accumulates A[l] = sum_t c_t ([x>w] + 0.5 [x==w]); the finalize kernel forms
+// sum_t c_t sign(x-w) = 2 A[l] - sum_t c_t  (sign(0) = 0 exactly, as torch's abs backward).
+// Exact ties x == w are impossible for a series row that shares no value with the CTA's shapelets; that is
+// checked per row against a hash set of the shapelet values, and such rows take the 2-instruction path.
+template <int OP, bool EXACT>
+__device__ __forceinline__ float bwd_op(float acc, float c, float hc, float x, float w) {
   if (OP == OP_L1) {
-    // acc += c * sign(x - w), sign(0) = 0 (torch abs backward)
     if (x > w) acc += c;
-    if (x < w) acc -= c;
+    if (EXACT) { if (x == w) acc += hc; }
     return acc;
   }
   return fmaf(c, x, acc);
 }
 
+constexpr unsigned kHashEmpty = 0x7fc00001u;   // a NaN payload: never equal to a series value
+__device__ __forceinline__ unsigned hash_key(float v) {
+  unsigned b = __float_as_uint(v);
+  return b == 0x80000000u ? 0u : b;            // -0 == +0
+}
+__device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) {
+  return ((key * 0x9E3779B1u) >> 7) & mask;
+}
+
+// ---- pooling backward: elementwise over all (sample, channel, shapelet, window), HBM-bound ----
+// One warp per saved distance row d[b,m,k,:]: soft-max statistics of the row (Z, S1 and the reference's
+// hard one-hot = first arg-max of p, Shapelet.py:79 | for lts_min the forward's argmin, :105), then the
+// coefficient a_t = dLoss/dd_t times the distance mode's norm factor, written to `coef`; two per-row
+// scalars go to `rowsc` for the finalize kernel.
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolArgs a, int rows) {
+  extern __shared__ __align__(16) float prow[];          // [warps][DP]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int row = blockIdx.x * nwarp + warp;
+  if (row >= rows) return;
+  float* dr = prow + (size_t)warp * g.DP;
+  const int k = row % g.K, bm = row / g.K;
+  const int m = bm % g.M, b = bm / g.M;
+  const float* src = a.dstore + (size_t)row * g.Ts;
+  for (int t = lane * 4; t < g.Ts; t += 128)
+    *reinterpret_cast<float4*>(dr + t) = *reinterpret_cast<const float4*>(src + t);
+  __syncwarp();
+  const size_t o = ((size_t)b * g.K + k) * g.M + m;
+  const float gk = a.g[o];
+  const float eps = g.eps, m2e2 = -2.f * eps * eps;
+  float Zs = 0.f, S1s = 0.f, shift = 0.f;
+  int ih;
+  if (g.pool == IGN_POOL_RBF_MAX) {
+    float pmx = -1.f; int imx = 0x7fffffff;
+#pragma unroll 4
+    for (int t = lane; t < g.Tw; t += 32) {
+      const float ed = eps * dr[t];
+      const float p = __expf(-(ed * ed));
+      const float e = __expf(p);
+      Zs += e; S1s = fmaf(e, p, S1s);
+      if (p > pmx) { pmx = p; imx = t; }
+    }
+    ih = warp_argmax_first(pmx, imx).i;
+  } else {
+    shift = a.dmin[o]; ih = a.argmin[o];
+#pragma unroll 4
+    for (int t = lane; t < g.Tw; t += 32) {
+      const float d = dr[t];
+      const float e = __expf(-(d - shift));
+      Zs += e; S1s = fmaf(e, d, S1s);
+    }
+  }
+  Zs = warp_sum(Zs); S1s = warp_sum(S1s);
+  const float invZ = 1.f / Zs, bar = S1s * invZ;
+  const float wst = (g.dist == IGN_DIST_PEARSON) ? a.wstat[(size_t)k * g.M + m] : 0.f;
+  const size_t prow0 = (size_t)bm * prefix_pitch(g.T) + kPrefixOrigin;
+  float* dst = a.coef + (size_t)row * g.Ts;
+  float sc0 = 0.f, sc1 = 0.f;
+#pragma unroll 2
+  for (int t = lane; t < g.Ts; t += 32) {
+    float coef = 0.f;
+    if (t < g.Tw) {
+      const float d = dr[t];
+      float c;
+      if (g.pool == IGN_POOL_RBF_MAX) {
+        const float ed = eps * d;
+        const float p = __expf(-(ed * ed));
+        const float soft = __expf(p) * invZ;
+        c = gk * ((t == ih ? 1.f : 0.f) + soft * (p - bar)) * p * (m2e2 * d);
+      } else {
+        const float soft = __expf(-(d - shift)) * invZ;
+        c = gk * ((t == ih ? 1.f : 0.f) - soft * (d - bar));
+      }
+      if (g.dist == IGN_DIST_L1 || g.dist == IGN_DIST_SQL2) {
+        coef = c; sc0 += c;
+      } else {
+        const int j0 = t * g.s;
+        const double sxx = a.pre2[prow0 + j0 + g.L] - a.pre2[prow0 + j0];
+        if (g.dist == IGN_DIST_COSINE) {
+          coef = c / fmaxf(sqrtf((float)sxx), 1e-8f);
+          sc0 = fmaf(c, 1.f - d, sc0);
+        } else {
+          const double sx = a.pre1[prow0 + j0 + g.L] - a.pre1[prow0 + j0];
+          const float sxc = (float)fmax(sxx - sx * sx / (double)g.L, 0.0), mu = (float)(sx / (double)g.L);
+          const float root = sqrtf(sxc * wst), D = root + 1e-8f;
+          coef = c / D;
+          sc0 = fmaf(coef, mu, sc0);
+          sc1 += c * (1.f - d) * sxc / (root * D);
+        }
+      }
+    }
+    dst[t] = coef;
+  }
+  sc0 = warp_sum(sc0); sc1 = warp_sum(sc1);
+  if (lane == 0) { a.rowsc[(size_t)row * 2] = sc0; a.rowsc[(size_t)row * 2 + 1] = sc1; }
+}
+
+// sum (w - mean)^2 per (k, m) shapelet row (pearson backward).  One warp per row.
+__global__ void __launch_bounds__(256) shapelet_centred_norm_kernel(const float* __restrict__ W,
+                                                                   float* __restrict__ wstat, int rows, int L) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* w = W + (size_t)row * L;
+  float s = 0.f;
+  for (int l = lane; l < L; l += 32) s += w[l];
+  const float mean = warp_sum(s) / (float)L;
+  float c2 = 0.f;
+  for (int l = lane; l < L; l += 32) { const float v = w[l] - mean; c2 = fmaf(v, v, c2); }
+  c2 = warp_sum(c2);
+  if (lane == 0) wstat[row] = c2;
+}
+
+// ---- contraction kernel: dW partials from the coefficients and the series (pure FP32-pipe work) ----
 template <int OP>
 __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -387,7 +511,6 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   const int k0 = kblk * g.KB;
   const int chunk = blockIdx.z;
   const int bbeg = chunk * g.bpc, bend = min(g.B, bbeg + g.bpc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int nthr = blockDim.x;
 
   const int ntl_all = g.s * g.LQ / LT;                    // l-tiles over all residues
@@ -398,16 +521,31 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
 
   float* xs = smem;
   float* ws = xs + g.NB * g.s * g.XQ;
-  float* cbuf = ws + g.KB * g.s * g.LQ;                   // d rows -> coefficients; reused for the final reduction
+  float* cbuf = ws + g.KB * g.s * g.LQ;                   // coefficient rows; reused for the final reduction
   const int cred = max(g.NB * g.KB * g.DP, kMaxThreads * LT);
-  float* st0 = cbuf + cred;
-  float* st1 = st0 + (OP != OP_L1 ? g.NB * g.DP : 0);
-  float* wstat = st1 + (g.dist == IGN_DIST_PEARSON ? g.NB * g.DP : 0);
-  float* rowsc = wstat + g.KB;                            // [NB][KB][2]
-  float* scal = rowsc + g.NB * g.KB * 2;                  // [KB][2]
+  float* wstat = cbuf + cred;
+  int* tieflag = reinterpret_cast<int*>(wstat + g.KB);    // [NB] row may contain x == w
+  unsigned* hset = reinterpret_cast<unsigned*>(tieflag + g.NB);
 
-  load_shapelets(g, a.W, m, k0, ws, wstat);
-  if (threadIdx.x < g.KB * 2) scal[threadIdx.x] = 0.f;
+  if (OP == OP_L1) {
+    load_shapelets(g, a.W, m, k0, ws, wstat);
+    if (a.hcap) {
+      for (int i = threadIdx.x; i < a.hcap; i += nthr) hset[i] = kHashEmpty;
+      __syncthreads();
+      const unsigned mask = a.hcap - 1;
+      for (int i = threadIdx.x; i < g.KB * g.L; i += nthr) {
+        const int hk = i / g.L, l = i - hk * g.L;
+        if (k0 + hk >= g.K) continue;
+        const unsigned key = hash_key(ws[((size_t)hk * g.s + l % g.s) * g.LQ + l / g.s]);
+        unsigned h = hash_slot(key, mask);
+        while (true) {
+          const unsigned old = atomicCAS(&hset[h], kHashEmpty, key);
+          if (old == kHashEmpty || old == key) break;
+          h = (h + 1) & mask;
+        }
+      }
+    }
+  }
 
   // this thread's fixed tile: 8 lags of one shapelet, one (sample slot, t-segment)
   const bool active = threadIdx.x < nitem;
@@ -433,106 +571,41 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     for (int i = 0; i < LT; ++i) wreg[i] = ws[((size_t)kl * g.s + r) * g.LQ + q0 + i];
   }
 
-  const float eps = g.eps;
-  const float m2e2 = -2.f * eps * eps;
-
   for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
     __syncthreads();
-    load_series(g, a.xn, a.pre1, a.pre2, m, b0, nb, xs, st0, g.dist == IGN_DIST_PEARSON ? st1 : nullptr);
-    // cooperative copy of the saved distance rows (coalesced, many loads in flight)
-    {
+    load_series(g, a.xn, nullptr, nullptr, m, b0, nb, xs, nullptr, nullptr);
+    if (OP == OP_L1) {
+      if (threadIdx.x < g.NB) tieflag[threadIdx.x] = a.hcap ? 0 : 1;
+    }
+    {  // coefficient rows -> shared memory (coalesced 16-byte loads, many in flight)
       const int rowv = g.DP / 4, tot = g.NB * g.KB * rowv;
       for (int i = threadIdx.x; i < tot; i += nthr) {
         const int row = i / rowv, c4 = (i - row * rowv) * 4;
         const int rbl = row / g.KB, rkl = row - rbl * g.KB;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rbl < nb && k0 + rkl < g.K && c4 < g.Ts)
-          v = *reinterpret_cast<const float4*>(a.dstore + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c4);
+          v = *reinterpret_cast<const float4*>(a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c4);
         *reinterpret_cast<float4*>(cbuf + (size_t)row * g.DP + c4) = v;
       }
     }
     __syncthreads();
-    // ---- phase A: one warp per (sample, shapelet) row: statistics, then d -> coefficient in place
-    for (int row = warp; row < g.NB * g.KB; row += nwarp) {
-      const int rbl = row / g.KB, rkl = row - rbl * g.KB;
-      const int b = b0 + rbl, k = k0 + rkl;
-      float* cr = cbuf + (size_t)row * g.DP;
-      float sc0 = 0.f, sc1 = 0.f;
-      if (rbl < nb && k < g.K) {
-        const float gk = a.g[((size_t)b * g.K + k) * g.M + m];
-        const float wst = wstat[rkl];
-        float Zs = 0.f, S1s = 0.f;
-        int ih;
-        float shift = 0.f;
-        if (g.pool == IGN_POOL_RBF_MAX) {
-          float pmx = -1.f; int imx = 0x7fffffff;
-          for (int t = lane; t < g.Tw; t += 32) {
-            const float ed = eps * cr[t];
-            const float p = __expf(-(ed * ed));
-            const float e = __expf(p);
-            Zs += e; S1s = fmaf(e, p, S1s);
-            if (p > pmx) { pmx = p; imx = t; }
-          }
-          ih = warp_argmax_first(pmx, imx).i;            // hard one-hot of Shapelet.py:79
-        } else {
-          float dmn = INFINITY; int imn = 0x7fffffff;
-          for (int t = lane; t < g.Tw; t += 32) { const float d = cr[t]; if (d < dmn) { dmn = d; imn = t; } }
-          ArgVal mn = warp_argmin_first(dmn, imn);
-          ih = mn.i; shift = mn.v;
-          for (int t = lane; t < g.Tw; t += 32) {
-            const float d = cr[t];
-            const float e = __expf(-(d - shift));
-            Zs += e; S1s = fmaf(e, d, S1s);
-          }
+    if (OP == OP_L1 && a.hcap) {   // does any sample of this row equal any shapelet value?
+      const unsigned mask = a.hcap - 1;
+      for (int i = threadIdx.x; i < nb * g.T; i += nthr) {
+        const int rbl = i / g.T, t = i - rbl * g.T;
+        const unsigned key = hash_key(xs[((size_t)rbl * g.s + t % g.s) * g.XQ + t / g.s]);
+        unsigned h = hash_slot(key, mask);
+        while (true) {
+          const unsigned v = hset[h];
+          if (v == key) { tieflag[rbl] = 1; break; }
+          if (v == kHashEmpty) break;
+          h = (h + 1) & mask;
         }
-        Zs = warp_sum(Zs); S1s = warp_sum(S1s);
-        const float invZ = 1.f / Zs, bar = S1s * invZ;
-        for (int t = lane; t < g.DP; t += 32) {
-          float coef = 0.f;
-          if (t < g.Tw) {
-            const float d = cr[t];
-            float c;
-            if (g.pool == IGN_POOL_RBF_MAX) {
-              const float ed = eps * d;
-              const float p = __expf(-(ed * ed));
-              const float soft = __expf(p) * invZ;
-              c = gk * ((t == ih ? 1.f : 0.f) + soft * (p - bar)) * p * (m2e2 * d);
-            } else {
-              const float soft = __expf(-(d - shift)) * invZ;
-              c = gk * ((t == ih ? 1.f : 0.f) - soft * (d - bar));
-            }
-            if (OP == OP_L1) {
-              coef = c;
-            } else if (g.dist == IGN_DIST_SQL2) {
-              coef = c; sc0 += c;
-            } else if (g.dist == IGN_DIST_COSINE) {
-              coef = c * st0[rbl * g.DP + t];
-              sc0 = fmaf(c, 1.f - d, sc0);
-            } else {
-              const float sxc = st0[rbl * g.DP + t], mu = st1[rbl * g.DP + t];
-              const float root = sqrtf(sxc * wst), D = root + 1e-8f;
-              coef = c / D;
-              sc0 = fmaf(coef, mu, sc0);
-              sc1 += c * (1.f - d) * sxc / (root * D);
-            }
-          }
-          cr[t] = coef;
-        }
-      } else {
-        for (int t = lane; t < g.DP; t += 32) cr[t] = 0.f;
       }
-      sc0 = warp_sum(sc0); sc1 = warp_sum(sc1);
-      if (lane == 0) { rowsc[row * 2] = sc0; rowsc[row * 2 + 1] = sc1; }
+      __syncthreads();
     }
-    __syncthreads();
-    if (OP != OP_L1 && threadIdx.x < g.KB * 2) {   // fixed-order accumulation of the per-shapelet scalars
-      const int skl = threadIdx.x >> 1, j = threadIdx.x & 1;
-      float s = scal[threadIdx.x];
-      for (int rbl = 0; rbl < g.NB; ++rbl) s += rowsc[(rbl * g.KB + skl) * 2 + j];
-      scal[threadIdx.x] = s;
-    }
-    // ---- phase B: contraction over windows, sliding along t with a 12-register ring of x
+    // ---- contraction over windows, sliding along t with a 12-register ring of x
     if (active && bl < nb && ta < tb) {
       const float* xr = xs + ((size_t)bl * g.s + r) * g.XQ + q0;
       const float* cb = cbuf + ((size_t)bl * g.KB + kl) * g.DP;
@@ -543,24 +616,33 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
         xv[0] = v0.x; xv[1] = v0.y; xv[2] = v0.z; xv[3] = v0.w;
         xv[4] = v1.x; xv[5] = v1.y; xv[6] = v1.z; xv[7] = v1.w;
       }
-#define IGN_BWD_STEP(BASE, TQ)                                                               \
+#define IGN_BWD_STEP(EX, BASE, TQ)                                                           \
       {                                                                                      \
         float4 nx = *reinterpret_cast<const float4*>(xr + (TQ) + 8);                         \
         xv[((BASE) + 8) % 12] = nx.x; xv[((BASE) + 9) % 12] = nx.y;                          \
         xv[((BASE) + 10) % 12] = nx.z; xv[((BASE) + 11) % 12] = nx.w;                        \
         const float4 c4 = *reinterpret_cast<const float4*>(cb + (TQ));                       \
+        const float4 h4 = make_float4(0.5f * c4.x, 0.5f * c4.y, 0.5f * c4.z, 0.5f * c4.w);   \
         _Pragma("unroll") for (int i = 0; i < LT; ++i) {                                     \
-          acc[i] = bwd_op<OP>(acc[i], c4.x, xv[((BASE) + i + 0) % 12], wreg[i]);             \
-          acc[i] = bwd_op<OP>(acc[i], c4.y, xv[((BASE) + i + 1) % 12], wreg[i]);             \
-          acc[i] = bwd_op<OP>(acc[i], c4.z, xv[((BASE) + i + 2) % 12], wreg[i]);             \
-          acc[i] = bwd_op<OP>(acc[i], c4.w, xv[((BASE) + i + 3) % 12], wreg[i]);             \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.x, h4.x, xv[((BASE) + i + 0) % 12], wreg[i]);   \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.y, h4.y, xv[((BASE) + i + 1) % 12], wreg[i]);   \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.z, h4.z, xv[((BASE) + i + 2) % 12], wreg[i]);   \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.w, h4.w, xv[((BASE) + i + 3) % 12], wreg[i]);   \
         }                                                                                    \
       }
-      int t = ta;
-      for (; t + 12 <= tb; t += 12) {
-        IGN_BWD_STEP(0, t) IGN_BWD_STEP(4, t + 4) IGN_BWD_STEP(8, t + 8)
+#define IGN_BWD_SWEEP(EX)                                                                    \
+      {                                                                                      \
+        int t = ta;                                                                          \
+        for (; t + 12 <= tb; t += 12) {                                                      \
+          IGN_BWD_STEP(EX, 0, t) IGN_BWD_STEP(EX, 4, t + 4) IGN_BWD_STEP(EX, 8, t + 8)       \
+        }                                                                                    \
+        if (t + 4 <= tb) {                                                                   \
+          IGN_BWD_STEP(EX, 0, t) t += 4;                                                     \
+          if (t + 4 <= tb) { IGN_BWD_STEP(EX, 4, t) t += 4; }                                \
+        }                                                                                    \
       }
-      if (t + 4 <= tb) { IGN_BWD_STEP(0, t) t += 4; if (t + 4 <= tb) { IGN_BWD_STEP(4, t) t += 4; } }
+      if (OP == OP_L1 && tieflag[bl]) IGN_BWD_SWEEP(true) else IGN_BWD_SWEEP(false)
+#undef IGN_BWD_SWEEP
 #undef IGN_BWD_STEP
     }
   }
@@ -590,29 +672,25 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     if (k < g.K && l < g.L && oq < (g.L - orr + g.s - 1) / g.s)
       a.part[(((size_t)chunk * g.K + k) * g.M + m) * g.L + l] = s;
   }
-  if (lblk == 0 && threadIdx.x < g.KB * 2) {
-    const int skl = threadIdx.x >> 1, j = threadIdx.x & 1;
-    if (k0 + skl < g.K) a.scal[(((size_t)chunk * g.K + k0 + skl) * g.M + m) * 2 + j] = scal[threadIdx.x];
-  }
 }
 
-// dW[k,m,:] from the per-chunk partial contractions and scalars.  One warp per (k,m) row.
+// dW[k,m,:] from the per-chunk partial contractions and the per-row scalars.  One warp per (k,m) row.
 __global__ void __launch_bounds__(256) shapelet_bwd_finalize(const float* __restrict__ W,
                                                             const float* __restrict__ part,
-                                                            const float* __restrict__ scal,
-                                                            float* __restrict__ dW, int K, int M, int L,
+                                                            const float* __restrict__ rowsc,
+                                                            float* __restrict__ dW, int B, int K, int M, int L,
                                                             int nchunk, int dist) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= K * M) return;
+  const int k = row / M, m = row - k * M;
   const float* w = W + (size_t)row * L;
   float s0 = 0.f, s1 = 0.f;
-  if (dist != IGN_DIST_L1) {
-    for (int c = 0; c < nchunk; ++c) {
-      s0 += scal[((size_t)c * K * M + row) * 2];
-      s1 += scal[((size_t)c * K * M + row) * 2 + 1];
-    }
+  for (int b = lane; b < B; b += 32) {            // fixed order: bit-reproducible
+    const size_t r = (((size_t)b * M + m) * K + k) * 2;
+    s0 += rowsc[r]; s1 += rowsc[r + 1];
   }
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
   float mean = 0.f, inv_nw = 0.f;
   if (dist == IGN_DIST_COSINE || dist == IGN_DIST_PEARSON) {
     float a = 0.f, b2 = 0.f;
@@ -626,7 +704,7 @@ __global__ void __launch_bounds__(256) shapelet_bwd_finalize(const float* __rest
     float G = 0.f;
     for (int c = 0; c < nchunk; ++c) G += part[((size_t)c * K * M + row) * L + l];
     float o;
-    if (dist == IGN_DIST_L1) o = -G / Lf;
+    if (dist == IGN_DIST_L1) o = -(2.f * G - s0) / Lf;
     else if (dist == IGN_DIST_SQL2) o = (2.f / Lf) * (w[l] * s0 - G);
     else if (dist == IGN_DIST_COSINE) o = -G * inv_nw + w[l] * s0 * inv_nw * inv_nw;
     else o = -(G - s0) + (w[l] - mean) * s1;
@@ -696,15 +774,19 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
   return true;
 }
 
-struct BwdPlan { int nseg, nlb, tlb, nchunk, threads; size_t smem_bytes; };
+struct BwdPlan { int nseg, nlb, tlb, nchunk, threads, hcap; size_t smem_bytes; };
+
+int bwd_hash_cap(const Geo& g, int KB) {
+  if (g.dist != IGN_DIST_L1) return 0;
+  size_t need = 2 * (size_t)KB * g.L, cap = 256;
+  while (cap < need) cap <<= 1;
+  return cap <= 16384 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path
+}
 
 size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
   size_t cred = (size_t)NB * KB * g.DP;
   if (cred < (size_t)kMaxThreads * LT) cred = (size_t)kMaxThreads * LT;
-  size_t f = (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + cred + KB + (size_t)NB * KB * 2 + KB * 2;
-  if (g.dist != IGN_DIST_L1) f += (size_t)NB * g.DP;
-  if (g.dist == IGN_DIST_PEARSON) f += (size_t)NB * g.DP;
-  return f;
+  return (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + cred + KB + NB + bwd_hash_cap(g, KB);
 }
 
 bool plan_bwd(Geo& g, BwdPlan& bp) {
@@ -734,6 +816,7 @@ bool plan_bwd(Geo& g, BwdPlan& bp) {
   bp.threads = round_up(bestNB * bestSeg * per_slot, 32);
   g.bpc = plan_bpc(g, g.M * g.nkb * nlb, bestNB);
   bp.nchunk = ceil_div(g.B, g.bpc);
+  bp.hcap = bwd_hash_cap(g, KB);
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
   return true;
 }
@@ -788,27 +871,60 @@ int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   return IGN_OK;
 }
 
+struct BwdWorkspace { size_t part, coef, rowsc, wstat, total; };   // offsets/size in floats
+
+BwdWorkspace bwd_workspace(const ign_shapelet_desc& d, const Geo& g, const BwdPlan& bp) {
+  BwdWorkspace w;
+  w.part = 0;
+  w.coef = (size_t)bp.nchunk * d.K * d.M * d.L;
+  w.coef = (w.coef + 3) / 4 * 4;                         // 16-byte aligned rows
+  w.rowsc = w.coef + (size_t)d.B * d.M * d.K * g.Ts;
+  w.wstat = w.rowsc + (size_t)d.B * d.M * d.K * 2;
+  w.total = w.wstat + (size_t)d.K * d.M;
+  return w;
+}
+
 size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
   Geo g; BwdPlan bp;
   if (!base_geo(d, g) || !plan_bwd(g, bp)) return 0;
-  return ((size_t)bp.nchunk * d.K * d.M * d.L + (size_t)bp.nchunk * d.K * d.M * 2) * sizeof(float);
+  return bwd_workspace(d, g, bp).total * sizeof(float);
 }
 
 int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
                              const double* pre2, const float* W, const float* gr, const float* dstore,
-                             float* dW, void* ws, size_t ws_bytes, cudaStream_t st) {
+                             const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
+                             cudaStream_t st) {
   Geo g; BwdPlan bp;
   if (!base_geo(d, g)) { set_error("shapelet_backward: T=%d < L=%d", d.T, d.L); return IGN_ERR_INVALID; }
   if (!plan_bwd(g, bp)) { set_error("shapelet_backward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
-  const size_t npart = (size_t)bp.nchunk * d.K * d.M * d.L;
-  const size_t need = (npart + (size_t)bp.nchunk * d.K * d.M * 2) * sizeof(float);
-  if (ws_bytes < need) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, need); return IGN_ERR_INVALID; }
-  BwdArgs a{xn, pre1, pre2, W, gr, dstore,
-            reinterpret_cast<float*>(ws), reinterpret_cast<float*>(ws) + npart, bp.nseg, bp.nlb, bp.tlb};
+  const BwdWorkspace wo = bwd_workspace(d, g, bp);
+  if (ws_bytes < wo.total * sizeof(float)) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, wo.total * sizeof(float)); return IGN_ERR_INVALID; }
+  if (((uintptr_t)ws & 15) != 0) { set_error("shapelet_backward: workspace must be 16-byte aligned"); return IGN_ERR_INVALID; }
+  float* base = reinterpret_cast<float*>(ws);
+  // 1. pooling backward (elementwise, HBM-bound): d -> per-window coefficients + per-row scalars
+  if (d.dist == IGN_DIST_PEARSON) {
+    shapelet_centred_norm_kernel<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.wstat, d.K * d.M, d.L);
+    IGN_CUDA(cudaGetLastError());
+  }
+  {
+    const int rows = d.B * d.M * d.K;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * g.DP * sizeof(float) > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * g.DP * sizeof(float);
+    if (smem > (size_t)max_optin_smem() - 1024) { set_error("shapelet_backward: %d windows per series do not fit shared memory", g.Tw); return IGN_ERR_UNSUPPORTED; }
+    int rc = set_smem(pool_bwd_kernel, smem);
+    if (rc) return rc;
+    PoolArgs pa{gr, dstore, dmin, argmin, pre1, pre2, base + wo.wstat, base + wo.coef, base + wo.rowsc};
+    pool_bwd_kernel<<<ceil_div(rows, warps), warps * 32, smem, st>>>(g, pa, rows);
+    IGN_CUDA(cudaGetLastError());
+  }
+  // 2. contraction with the series (FP32 pipe) into per-chunk partials
+  BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, bp.hcap};
   int rc = d.dist == IGN_DIST_L1 ? run_bwd<OP_L1>(g, a, bp, st) : run_bwd<OP_DOT>(g, a, bp, st);
   if (rc) return rc;
-  shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, a.part, a.scal, dW, d.K, d.M, d.L,
-                                                              bp.nchunk, d.dist);
+  // 3. combine
+  shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
+                                                              d.M, d.L, bp.nchunk, d.dist);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }

@@ -37,11 +37,12 @@ _SIGNATURES = {
     "ign_padded_len": (c_int32, [c_int32]),
     "ign_num_windows": (c_int32, [c_int32, c_int32, c_int32]),
     "ign_padded_windows": (c_int32, [c_int32, c_int32, c_int32]),
+    "ign_prefix_pitch": (c_int32, [c_int32]),
     "ign_instnorm_forward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),
     "ign_window_prefix": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
     "ign_shapelet_forward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 10),
     "ign_shapelet_backward_workspace": (c_size_t, [POINTER(ShapeletDesc)]),
-    "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 8 + [c_size_t, _P]),
+    "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 10 + [c_size_t, _P]),
     "ign_gate_forward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P]),
     "ign_gate_backward": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P]),
     "ign_sbm_transform_host": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, POINTER(_P),

@@ -110,7 +110,7 @@ class SeriesPack:
     def prefix(self) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._pre is None:
             B, M, T = self.B, self.M, self.T
-            pre = torch.empty((2, B, M, T + 1), dtype=torch.float64, device=self.xn.device)
+            pre = torch.empty((2, B, M, C.lib.ign_prefix_pitch(T)), dtype=torch.float64, device=self.xn.device)
             with torch.cuda.device(self.xn.device):
                 C.check(STATS.call("window_prefix", 1, lambda: C.lib.ign_window_prefix(
                     _ptr(self.xn), _ptr(pre[0]), _ptr(pre[1]), B, M, T, _stream())), "ign_window_prefix")
@@ -188,13 +188,13 @@ class _ShapeletTransform(torch.autograd.Function):
         ctx.pack = pack
         ctx.thr_shape = None if threshold is None else threshold.shape
         if need_grad:
-            ctx.save_for_backward(Wc, out, dstore)
+            ctx.save_for_backward(Wc, out, idx, dstore)
         ctx.mark_non_differentiable(idx)
         return out[0], out[1], idx
 
     @staticmethod
     def backward(ctx, g_p, g_dmin, _g_idx):
-        Wc, out, dstore = ctx.saved_tensors
+        Wc, out, idx, dstore = ctx.saved_tensors
         desc, pack = ctx.desc, ctx.pack
         # d.min() (Shapelet.py:84) feeds reporting only; a gradient arriving there follows the hard argmin
         # and is not produced by any loss of the reference (experiment_classification.py:325-329).
@@ -221,8 +221,8 @@ class _ShapeletTransform(torch.autograd.Function):
             dW = torch.empty_like(Wc)
             with torch.cuda.device(g.device):
                 C.check(STATS.call("shapelet_bwd/%s/L%d" % (ctx.dist, desc.L), 2, lambda: C.lib.ign_shapelet_backward(
-                    byref(desc), _ptr(pack.xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(g), _ptr(dstore), _ptr(dW),
-                    _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
+                    byref(desc), _ptr(pack.xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(g), _ptr(dstore), _ptr(out[1]),
+                    _ptr(idx), _ptr(dW), _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
         return dW, dthr, None, None, None, None, None, None
 
 

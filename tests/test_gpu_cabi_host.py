@@ -40,7 +40,7 @@ def test_sbm_transform_host(flag, dist):
 def test_instnorm_and_prefix_kernels():
     from layers.shapelet_ops import instance_norm
     torch.manual_seed(3)
-    for (B, T, M) in [(3, 29, 12), (2, 1000, 125), (4, 130, 33)]:
+    for (B, T, M) in [(3, 29, 12), (2, 1000, 125), (4, 130, 33), (2, 4100, 5), (1, 257, 16)]:
         x = torch.randn(B, T, M) * 3 + 1.5
         pack = instance_norm(x.cuda())
         ref = O.instance_norm(x)
@@ -50,9 +50,10 @@ def test_instnorm_and_prefix_kernels():
         own = pack.xn[:, :, :T].double().cpu()       # prefix sums are defined on the kernel's own xn
         r1 = torch.cumsum(own, -1)
         r2 = torch.cumsum(own ** 2, -1)
-        torch.testing.assert_close(p1[:, :, 1:].cpu(), r1, rtol=1e-9, atol=1e-9)
-        torch.testing.assert_close(p2[:, :, 1:].cpu(), r2, rtol=1e-9, atol=1e-9)
-        assert float(p1[:, :, 0].abs().sum()) == 0.0
+        # row layout: slot 3 holds P[0] = 0, slot 4+j holds P[j+1] (include/ign_b200.h)
+        torch.testing.assert_close(p1[:, :, 4:4 + T].cpu(), r1, rtol=1e-9, atol=1e-9)
+        torch.testing.assert_close(p2[:, :, 4:4 + T].cpu(), r2, rtol=1e-9, atol=1e-9)
+        assert float(p1[:, :, :4].abs().sum()) == 0.0 and float(p2[:, :, :4].abs().sum()) == 0.0
 
 
 def test_bad_arguments_return_status_not_crash():

@@ -55,7 +55,7 @@ def main():
         pack._pre = None
         pack.prefix()
     t_pre = timeit(pref, a.iters, flush)
-    pb = x.numel() * 4 + 2 * a.B * a.M * (a.T + 1) * 8
+    pb = x.numel() * 4 + 2 * a.B * a.M * (a.T + 4) * 8
     print(f"prefix    {t_pre:8.3f} ms  {pb / t_pre / 1e6:8.1f} GB/s")
     rows.append(dict(kernel="prefix", ms=t_pre, gbs=pb / t_pre / 1e6))
     for dist in a.dists.split(","):
