@@ -214,7 +214,7 @@ def run_reference_arm(a):
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(a, per_gpu_batch, world):
@@ -227,7 +227,24 @@ def workload_config(a, per_gpu_batch, world):
 
 
 # ----------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The contract is ONE JSON line on stdout; libraries (NCCL, cuDNN) may print to fd 1, so main() points
+    fd 1 at stderr for the whole run and the result line goes to the saved descriptor."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         return run_reference_arm(a)
@@ -369,7 +386,7 @@ def main():
                            "share_of_step": sum(f["ms"] for k, f in fams.items() if k.startswith("shapelet")) / ms_total},
         "allreduce_bytes_per_step": exp.grads.nbytes() if world > 1 else 0,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

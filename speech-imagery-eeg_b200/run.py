@@ -91,6 +91,8 @@ def main(argv=None):
         if exp.is_main and res is not None:
             with open(os.path.join(exp.checkpoint_dir, "test_results.pkl"), "wb") as f:
                 pickle.dump({"test_loss": loss, "test_metrics": res, "test_df": df, "args": vars(args)}, f)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
     return results
 
 
