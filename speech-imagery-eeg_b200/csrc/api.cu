@@ -99,10 +99,14 @@ int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const 
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || thr, "shapelet_forward: LTS pooling needs threshold");
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || d->dist <= IGN_DIST_SQL2,
               "shapelet_forward: DistThresholdShapelet ignores distance_func (Shapelet.py:100-103); use L1 or SQL2");
-  if (d->precision != IGN_PREC_FP32 && d->dist != IGN_DIST_L1) {
-    set_error("shapelet_forward: tcgen05 precision modes are not built into this library yet");
+  if (d->precision == IGN_PREC_BF16 && d->dist != IGN_DIST_L1) {
+    set_error("shapelet_forward: the bf16 operand mode is not built yet (use fp32, 3xtf32 or tf32)");
     return IGN_ERR_UNSUPPORTED;
   }
+  // tcgen05 engine for the cross-term distances; geometries it does not cover (stride > 1, more than 2048
+  // windows per series) run on the exact-fp32 CUDA-core engine instead
+  if (d->precision != IGN_PREC_FP32 && shapelet_fwd_tc_supported(*d))
+    return launch_shapelet_fwd_tc(*d, xn, pre1, pre2, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
   return launch_shapelet_fwd_simt(*d, xn, pre1, pre2, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
 }
 

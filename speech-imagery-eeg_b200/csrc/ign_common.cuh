@@ -51,6 +51,10 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
                              const double* pre2, const float* W, const float* g, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
                              cudaStream_t st);
+bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d);
+int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const double* pre1, const double* pre2,
+                           const float* W, const float* thr, float* p, float* dmin, int* argmin, float* dstore,
+                           cudaStream_t st);
 int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int B, int C, int use_gate,
                     float gv, cudaStream_t st);
 int launch_gate_bwd(const float* s, const float* z, const float* go, const float* ge, float* gs,

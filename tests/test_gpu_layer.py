@@ -14,12 +14,12 @@ DEV = "cuda"
 RTOL, ATOL = 2e-5, 2e-6          # forward values (fp32 path)
 
 
-def run_layer(xn, W, stride, eps, dist, pool="rbf_max", thr=None, g=None):
+def run_layer(xn, W, stride, eps, dist, pool="rbf_max", thr=None, g=None, precision="fp32"):
     from layers.shapelet_ops import SeriesPack, shapelet_transform
     Wd = W.detach().clone().to(DEV).requires_grad_(g is not None)      # fresh leaf: .grad never accumulates across calls
     thd = None if thr is None else thr.detach().clone().to(DEV).requires_grad_(g is not None)
     pack = SeriesPack.from_channel_major(xn.to(DEV))
-    p, dmin, idx = shapelet_transform(pack, Wd, stride, eps, dist, pool, thd)
+    p, dmin, idx = shapelet_transform(pack, Wd, stride, eps, dist, pool, thd, precision)
     dW = dthr = None
     if g is not None:
         (p * g.to(DEV)).sum().backward()
@@ -212,3 +212,64 @@ def test_gate_kernel_vs_oracle():
             gs, gz = O.gate_backward_formula(s.double(), z.double(), go.double(), ge.double(), gv)
             assert_close(sd.grad, gs, 1e-4, 1e-5, "gate d/ds")
             assert_close(zd.grad, gz, 1e-4, 1e-5, "gate d/dz")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 engine (cross-term distances).  3xTF32 is the fp32-equivalent mode and is held to the same bound as
+# the CUDA-core engine; single-pass TF32 is a separate mode with its own tolerance (2e-4
+# relative on d for unit-variance data, argmin flips ~0.1 %).
+# ---------------------------------------------------------------------------------------------------------
+TC_SHAPES = [
+    (3, 4, 64, 5, 9),          # one k-block of 32, N = 80
+    (2, 3, 200, 10, 37),       # K = 10 -> two shapelet blocks
+    (2, 5, 130, 7, 16),        # N = 112
+    (2, 2, 96, 3, 96),         # T == L: one window
+    (1, 1, 17, 1, 3),          # minimum sizes
+    (2, 2, 300, 45, 20),       # six shapelet blocks, last one ragged
+    (5, 3, 120, 5, 30),        # odd batch vs samples per tile
+    (3, 2, 1000, 5, 100),      # CHISCO geometry: 57 window groups, 2 samples per tile
+    (5, 2, 1000, 5, 500),      # 32 window groups, 4 samples per tile, 17 k-blocks, ragged last tile
+    (2, 1, 2100, 4, 100),      # 126 window groups: one sample per tile
+]
+
+
+@pytest.mark.parametrize("precision,rtol,atol", [("3xtf32", 2e-5, 2e-6), ("tf32", 3e-3, 3e-3)])
+@pytest.mark.parametrize("flag", ["sql2", "cosine", "pearson"])
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tcgen05_forward_vs_oracle(precision, rtol, atol, flag, shape):
+    B, M, T, K, L = shape
+    mode, dist = MODES[flag]
+    torch.manual_seed(4321 + B + M + T + K)
+    xn, W = torch.randn(B, M, T), torch.randn(K, M, L)
+    ref = O.shapelet_forward(xn, W, 1, 0.8, mode)
+    p, dmin, idx, _, _ = run_layer(xn, W, 1, 0.8, dist, precision=precision)
+    assert_close(dmin.reshape(B, -1), ref.dmin, rtol, atol, f"{precision} {flag} dmin")
+    assert_close(p.reshape(B, -1), ref.p, rtol, atol, f"{precision} {flag} p")
+    if precision == "3xtf32":
+        index_parity(idx, ref.argmin_d, ref.d, False, L, f"{precision} {flag} argmin")
+
+
+@pytest.mark.parametrize("flag", ["cosine", "pearson", "sql2"])
+def test_tcgen05_training_path(flag):
+    """tcgen05 forward feeds the saved distances to the backward kernels: gradients still match the oracle."""
+    mode, dist = MODES[flag]
+    torch.manual_seed(77)
+    B, M, T, K, L = 4, 6, 1000, 5, 200
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    p, dmin, idx, dW, _ = run_layer(xn, W, 1, 1.0, dist, g=g, precision="3xtf32")
+    ref = O.shapelet_forward(xn, W, 1, 1.0, mode)
+    assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, flag + " p")
+    dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 1.0, mode)
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), flag + " dW")
+    # the two engines agree with each other far inside the tolerance
+    p32, d32, _, _, _ = run_layer(xn, W, 1, 1.0, dist)
+    assert_close(dmin, d32, 2e-6, 2e-6, flag + " 3xtf32 vs fp32 engine")
+
+
+def test_tcgen05_falls_back_for_strided_windows():
+    """stride > 1 is outside the tensor-core path: the exact-fp32 engine answers instead (same results)."""
+    torch.manual_seed(3)
+    xn, W = torch.randn(2, 2, 400), torch.randn(4, 2, 50)
+    a = run_layer(xn, W, 3, 1.0, "cosine", precision="3xtf32")
+    b = run_layer(xn, W, 3, 1.0, "cosine")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
