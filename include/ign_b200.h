@@ -93,13 +93,28 @@ int32_t ign_prefix_pitch(int32_t T);
  *   P1[b,m,j] = sum_{i<j} xn[b,m,i], P2[b,m,j] = sum_{i<j} xn[b,m,i]^2, j in [0,T].
  *   Storage: row pitch ign_prefix_pitch(T); P[j] is at slot 3+j of its row (slots 0..2 are zero padding, so
  *   the kernel's 4-sample runs are 32-byte aligned).  ||x_w||^2 of the window starting at sample j0 is
- *   P2[j0+L]-P2[j0]; its sum is P1[j0+L]-P1[j0]. */
+ *   P2[j0+L]-P2[j0]; its sum is P1[j0+L]-P1[j0].  (Stand-alone form of the pass; the distance kernels consume
+ *   the fused per-group output of ign_window_stats below.) */
 int32_t ign_window_prefix(const float* xn_dev, double* pre1_dev, double* pre2_dev,
                           int32_t B, int32_t M, int32_t T, void* stream);
 
+/* pitch (floats) of one window-statistics row: T' rounded up to a multiple of 16 (zero padded) */
+int32_t ign_stats_pitch(int32_t T, int32_t L, int32_t stride);
+
+/* The sliding-window prefix-sum pass in the form the distance kernels consume: for G (<= 8) length groups at
+ * once, per series row an fp64 prefix scan of xn and xn^2 in shared memory, then per window the fp32 norm term
+ *   SQL2: st0 = ||x_w||^2      COSINE: st0 = 1/max(||x_w||,1e-8)      PEARSON: st0 = sum (x_w-mu)^2, st1 = mu
+ * L / stride are HOST arrays of G ints; st0_dev / st1_dev are HOST arrays of G device pointers, each
+ * [B,M,ign_stats_pitch(T,L[g],stride[g])] (st1_dev may be NULL unless dist == PEARSON).
+ * Reference: the norm / mean terms inside cosine_similarity, pearson_corrcoef and ShapeletDistanceFunc
+ * (Shapelet.py:11-19, :28, :64-69). */
+int32_t ign_window_stats(const float* xn_dev, int32_t B, int32_t M, int32_t T, int32_t G, const int32_t* L,
+                         const int32_t* stride, int32_t dist, float* const* st0_dev, float* const* st1_dev,
+                         void* stream);
+
 /* Shapelet.forward / DistThresholdShapelet.forward for one length group.
- *   xn_dev [B,M,Tp]; pre1/pre2 [B,M,T+1] (required unless dist==L1); W_dev [K,M,L];
- *   threshold_dev [K,M] (required for LTS_MIN).
+ *   xn_dev [B,M,Tp]; st0_dev [B,M,SP] window statistics of this group from ign_window_stats (required unless
+ *   dist==L1); W_dev [K,M,L]; threshold_dev [K,M] (required for LTS_MIN).
  * Outputs, all [B,K,M]:
  *   p_dev       pooled predicate: max_t exp(-(eps d_t)^2) = exp(-(eps min_t d_t)^2)   Shapelet.py:77-82
  *               | sigmoid(thr - min_t d_t)                                            Shapelet.py:105-109
@@ -107,11 +122,12 @@ int32_t ign_window_prefix(const float* xn_dev, double* pre1_dev, double* pre2_de
  *   argmin_dev  argmin_t d_t, first index on ties (may be NULL).  It is also the arg-max of p barring
  *               ties of p in fp32; backward re-derives the reference's arg-max-of-p one-hot itself.
  *   dstore_dev  optional [B,M,K,Tw] (Tw = ign_padded_windows) all window distances, kept for backward
- *               (the soft-max statistics are recomputed from it); NULL in inference. */
-int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev, const double* pre1_dev,
-                             const double* pre2_dev, const float* W_dev, const float* threshold_dev,
-                             float* p_dev, float* dmin_dev, int32_t* argmin_dev, float* dstore_dev,
-                             void* stream);
+ *               (the soft-max statistics are recomputed from it); NULL in inference.
+ * Engine: precision FP32 -> CUDA-core kernels; 3XTF32 / TF32 -> tcgen05 kernel (stride 1, T' <= 2048;
+ * other geometries run on the FP32 engine). */
+int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,
+                             const float* W_dev, const float* threshold_dev, float* p_dev, float* dmin_dev,
+                             int32_t* argmin_dev, float* dstore_dev, void* stream);
 
 /* bytes of scratch ign_shapelet_backward needs for this problem */
 size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* desc);
@@ -120,12 +136,13 @@ size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* desc);
  * (Shapelet.py:79-82 | :105-108): every window receives soft_t*(p_t - pbar) (+1 at the hard index).
  *   g_dev [B,K,M] = dLoss/d(max_p)  (rbf_max)   or   dLoss/d(min_d)  (lts_min; the caller folds the
  *   sigmoid: g_min = -g_p * p * (1-p), dthreshold = sum_b g_p * p * (1-p))
+ *   st0_dev / st1_dev: window statistics as for forward (st1 only for PEARSON; both NULL for L1).
  *   dstore_dev [B,M,K,Tw] as written by ign_shapelet_forward on the same inputs.
  *   dmin_dev / argmin_dev [B,K,M]: the forward's outputs; required for lts_min (its hard index and soft-min
  *   shift), ignored (may be NULL) for rbf_max, whose arg-max-of-p one-hot is re-derived from dstore.
  *   dW_dev [K,M,L] is overwritten (not accumulated).  Deterministic (no float atomics). */
-int32_t ign_shapelet_backward(const ign_shapelet_desc* desc, const float* xn_dev, const double* pre1_dev,
-                              const double* pre2_dev, const float* W_dev, const float* g_dev,
+int32_t ign_shapelet_backward(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,
+                              const float* st1_dev, const float* W_dev, const float* g_dev,
                               const float* dstore_dev, const float* dmin_dev, const int32_t* argmin_dev,
                               float* dW_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 

@@ -89,13 +89,32 @@ int32_t ign_window_prefix(const float* xn, double* pre1, double* pre2, int32_t B
   return launch_prefix(xn, pre1, pre2, B, M, T, (cudaStream_t)stream);
 }
 
-int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const double* pre1, const double* pre2,
-                             const float* W, const float* thr, float* p, float* dmin, int32_t* argmin,
-                             float* dstore, void* stream) {
+int32_t ign_stats_pitch(int32_t T, int32_t L, int32_t stride) { return (L <= 0 || stride <= 0) ? 0 : stats_pitch(T, L, stride); }
+
+int32_t ign_window_stats(const float* xn, int32_t B, int32_t M, int32_t T, int32_t G, const int32_t* L,
+                         const int32_t* stride, int32_t dist, float* const* st0, float* const* st1, void* stream) {
+  IGN_REQUIRE(xn && L && stride && st0, "window_stats: null pointer");
+  IGN_REQUIRE(B > 0 && M > 0 && T > 0, "window_stats: bad shape B=%d T=%d M=%d", B, T, M);
+  IGN_REQUIRE(G > 0 && G <= kMaxStatGroups, "window_stats: 1..%d groups per call (got %d)", kMaxStatGroups, G);
+  IGN_REQUIRE(dist >= IGN_DIST_SQL2 && dist <= IGN_DIST_PEARSON, "window_stats: dist %d has no norm term", dist);
+  IGN_REQUIRE(dist != IGN_DIST_PEARSON || st1, "window_stats: PEARSON needs st1");
+  StatGroups sg;
+  sg.n = G;
+  for (int g = 0; g < G; ++g) {
+    IGN_REQUIRE(L[g] > 0 && stride[g] > 0 && T >= L[g] && st0[g], "window_stats: bad group %d (L=%d stride=%d)", g, L[g], stride[g]);
+    IGN_REQUIRE(dist != IGN_DIST_PEARSON || st1[g], "window_stats: PEARSON needs st1[%d]", g);
+    sg.L[g] = L[g]; sg.s[g] = stride[g]; sg.Tw[g] = num_windows(T, L[g], stride[g]);
+    sg.SP[g] = stats_pitch(T, L[g], stride[g]); sg.st0[g] = st0[g]; sg.st1[g] = st1 ? st1[g] : nullptr;
+  }
+  return launch_window_stats(xn, sg, B, M, T, dist, (cudaStream_t)stream);
+}
+
+int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const float* st0, const float* W,
+                             const float* thr, float* p, float* dmin, int32_t* argmin, float* dstore, void* stream) {
   int rc = check_desc(d, "shapelet_forward");
   if (rc) return rc;
   IGN_REQUIRE(xn && W && p && dmin, "shapelet_forward: null pointer");
-  IGN_REQUIRE(d->dist == IGN_DIST_L1 || (pre1 && pre2), "shapelet_forward: dist %d needs the window prefix sums", d->dist);
+  IGN_REQUIRE(d->dist == IGN_DIST_L1 || st0, "shapelet_forward: dist %d needs the window statistics (ign_window_stats)", d->dist);
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || thr, "shapelet_forward: LTS pooling needs threshold");
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || d->dist <= IGN_DIST_SQL2,
               "shapelet_forward: DistThresholdShapelet ignores distance_func (Shapelet.py:100-103); use L1 or SQL2");
@@ -106,8 +125,8 @@ int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const 
   // tcgen05 engine for the cross-term distances; geometries it does not cover (stride > 1, more than 2048
   // windows per series) run on the exact-fp32 CUDA-core engine instead
   if (d->precision != IGN_PREC_FP32 && shapelet_fwd_tc_supported(*d))
-    return launch_shapelet_fwd_tc(*d, xn, pre1, pre2, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
-  return launch_shapelet_fwd_simt(*d, xn, pre1, pre2, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
+    return launch_shapelet_fwd_tc(*d, xn, st0, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
+  return launch_shapelet_fwd_simt(*d, xn, st0, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
 }
 
 size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
@@ -115,7 +134,7 @@ size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
   return shapelet_bwd_workspace_simt(*d);
 }
 
-int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const double* pre1, const double* pre2,
+int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const float* st0, const float* st1,
                               const float* W, const float* g, const float* dstore, const float* dmin,
                               const int32_t* argmin, float* dW, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_desc(d, "shapelet_backward");
@@ -123,8 +142,9 @@ int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const
   IGN_REQUIRE(xn && W && g && dW && ws, "shapelet_backward: null pointer");
   IGN_REQUIRE(dstore, "shapelet_backward: dstore (window distances saved by forward) is required");
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || (dmin && argmin), "shapelet_backward: lts_min needs the forward's dmin and argmin");
-  IGN_REQUIRE(d->dist == IGN_DIST_L1 || (pre1 && pre2), "shapelet_backward: dist %d needs the window prefix sums", d->dist);
-  return launch_shapelet_bwd_simt(*d, xn, pre1, pre2, W, g, dstore, dmin, argmin, dW, ws, ws_bytes, (cudaStream_t)stream);
+  IGN_REQUIRE(d->dist < IGN_DIST_COSINE || st0, "shapelet_backward: dist %d needs the window statistics", d->dist);
+  IGN_REQUIRE(d->dist != IGN_DIST_PEARSON || st1, "shapelet_backward: PEARSON needs st1 (window means)");
+  return launch_shapelet_bwd_simt(*d, xn, st0, st1, W, g, dstore, dmin, argmin, dW, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int32_t ign_gate_forward(const float* s, const float* z, float* out, float* eta, int32_t B, int32_t C,
@@ -146,6 +166,7 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
                                float eps, int32_t dist, int32_t precision, float* probs_host, float* dists_host) {
   IGN_REQUIRE(x_host && W_host && K && L && stride && probs_host && dists_host, "sbm_transform_host: null pointer");
   IGN_REQUIRE(B > 0 && T > 0 && M > 0 && G > 0, "sbm_transform_host: bad shape");
+  IGN_REQUIRE(G <= kMaxStatGroups, "sbm_transform_host: at most %d groups", kMaxStatGroups);
   int rc = ign_device_check(-1);
   if (rc) return rc;
   const int Tp = padded_len(T);
@@ -160,7 +181,7 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
   cudaStream_t st;
   IGN_CUDA(cudaStreamCreate(&st));
   float *x = nullptr, *xn = nullptr, *W = nullptr, *out = nullptr;
-  double* pre = nullptr;
+  void* pre = nullptr;
   const size_t nx = (size_t)B * T * M, nxn = (size_t)B * M * Tp, nf = (size_t)B * Kmax * M;
   auto cleanup = [&]() {
     cudaFree(x); cudaFree(xn); cudaFree(W); cudaFree(out); cudaFree(pre);
@@ -171,18 +192,26 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
   IGN_TRY(cudaMalloc(&xn, nxn * 4));
   IGN_TRY(cudaMalloc(&W, wmax * 4));
   IGN_TRY(cudaMalloc(&out, nf * 2 * 4));
-  if (dist != IGN_DIST_L1) IGN_TRY(cudaMalloc(&pre, (size_t)B * M * prefix_pitch(T) * 2 * sizeof(double)));
+  size_t soff[kMaxStatGroups + 1] = {0};
+  if (dist != IGN_DIST_L1) {
+    for (int g = 0; g < G; ++g) soff[g + 1] = soff[g] + (size_t)B * M * stats_pitch(T, L[g], stride[g]);
+    IGN_TRY(cudaMalloc(&pre, soff[G] * 2 * sizeof(float)));
+  }
   IGN_TRY(cudaMemcpyAsync(x, x_host, nx * 4, cudaMemcpyHostToDevice, st));
   rc = launch_instnorm(x, xn, nullptr, nullptr, B, T, M, st);
-  double* pre2 = pre ? pre + (size_t)B * M * prefix_pitch(T) : nullptr;
-  if (!rc && pre) rc = launch_prefix(xn, pre, pre2, B, M, T, st);
+  float* sbase = reinterpret_cast<float*>(pre);
+  if (!rc && pre) {
+    float* p0[kMaxStatGroups]; float* p1[kMaxStatGroups];
+    for (int g = 0; g < G; ++g) { p0[g] = sbase + soff[g]; p1[g] = sbase + soff[G] + soff[g]; }
+    rc = ign_window_stats(xn, B, M, T, G, L, stride, dist, p0, p1, st);
+  }
   std::vector<float> hp, hd;
   int col = 0;
   for (int g = 0; g < G && !rc; ++g) {
     ign_shapelet_desc d{B, M, T, Tp, K[g], L[g], stride[g], eps, dist, IGN_POOL_RBF_MAX, precision};
     const size_t n = (size_t)B * K[g] * M;
     IGN_TRY(cudaMemcpyAsync(W, W_host[g], (size_t)K[g] * M * L[g] * 4, cudaMemcpyHostToDevice, st));
-    rc = ign_shapelet_forward(&d, xn, pre, pre2, W, nullptr, out, out + nf, nullptr, nullptr, st);
+    rc = ign_shapelet_forward(&d, xn, pre ? sbase + soff[g] : nullptr, W, nullptr, out, out + nf, nullptr, nullptr, st);
     if (rc) break;
     hp.resize(n); hd.resize(n);
     IGN_TRY(cudaMemcpyAsync(hp.data(), out, n * 4, cudaMemcpyDeviceToHost, st));

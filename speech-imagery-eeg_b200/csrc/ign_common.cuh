@@ -38,21 +38,26 @@ inline int padded_windows(int T, int L, int s) { return round_up(num_windows(T, 
 // fp64 prefix rows: pitch (doubles) and the slot of P[0]; P[j] lives at row*pitch + kPrefixOrigin + j
 constexpr int kPrefixOrigin = 3;
 __host__ __device__ inline int prefix_pitch(int T) { return round_up(T + 4, 4); }
+// per-group fp32 window statistics: row pitch = windows rounded up to 16 (zero padded)
+inline int stats_pitch(int T, int L, int s) { return round_up(num_windows(T, L, s), 16); }
+constexpr int kMaxStatGroups = 8;
+struct StatGroups { int n; int L[kMaxStatGroups], s[kMaxStatGroups], Tw[kMaxStatGroups], SP[kMaxStatGroups]; float* st0[kMaxStatGroups]; float* st1[kMaxStatGroups]; };
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) ----
 int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, int T, int M,
                     cudaStream_t st);
 int launch_prefix(const float* xn, double* pre1, double* pre2, int B, int M, int T, cudaStream_t st);
-int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
-                             const double* pre2, const float* W, const float* thr, float* p, float* dmin,
+int launch_window_stats(const float* xn, const StatGroups& G, int B, int M, int T, int dist, cudaStream_t st);
+int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
+                             const float* W, const float* thr, float* p, float* dmin,
                              int* argmin, float* dstore, cudaStream_t st);
 size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d);
-int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
-                             const double* pre2, const float* W, const float* g, const float* dstore,
+int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
+                             const float* st1, const float* W, const float* g, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
                              cudaStream_t st);
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d);
-int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const double* pre1, const double* pre2,
+int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const float* st0,
                            const float* W, const float* thr, float* p, float* dmin, int* argmin, float* dstore,
                            cudaStream_t st);
 int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int B, int C, int use_gate,

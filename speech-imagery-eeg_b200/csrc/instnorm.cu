@@ -205,6 +205,77 @@ __global__ void __launch_bounds__(256) prefix_kernel(const float* __restrict__ x
   }
 }
 
+
+// Sliding-window statistics for all length groups in one pass: per series row an fp64 prefix scan of x and
+// x^2 in shared memory, then for every group g and window t the norm term its distance needs, as fp32:
+//   sql2    st0 = ||x_w||^2            cosine  st0 = 1/max(||x_w||,1e-8)
+//   pearson st0 = sum (x_w-mu)^2, st1 = mu
+// Rows are written coalesced with pitch SP_g (windows rounded up to 16, pad = 0).  One warp per row.
+__global__ void __launch_bounds__(256) window_stats_kernel(const float* __restrict__ xn, const StatGroups G,
+                                                           int rows, int T, int Tp, int dist) {
+  extern __shared__ __align__(16) double pbuf[];          // [warps][nseq][T+1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const bool need1 = dist == IGN_DIST_PEARSON;
+  const int nseq = need1 ? 2 : 1;
+  double* P2 = pbuf + (size_t)warp * nseq * (T + 1);
+  double* P1 = P2 + (T + 1);
+  const float* xr = xn + (size_t)row * Tp;
+  if (lane == 0) { P2[0] = 0.0; if (need1) P1[0] = 0.0; }
+  double c1 = 0.0, c2 = 0.0;
+  const int nchunk = (T + 127) / 128;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane * 4 < Tp) v = *reinterpret_cast<const float4*>(xr + lane * 4);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int j = ch * 128 + lane * 4;
+    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch + 1 < nchunk && j + 128 < Tp) nv = *reinterpret_cast<const float4*>(xr + j + 128);
+    const double q0 = (double)v.x * v.x, q1 = q0 + (double)v.y * v.y, q2 = q1 + (double)v.z * v.z,
+                 q3 = q2 + (double)v.w * v.w;
+    const double s2 = warp_incl_scan(q3, lane);
+    const double e2 = c2 + s2 - q3;
+    if (j + 0 < T) P2[j + 1] = e2 + q0;
+    if (j + 1 < T) P2[j + 2] = e2 + q1;
+    if (j + 2 < T) P2[j + 3] = e2 + q2;
+    if (j + 3 < T) P2[j + 4] = e2 + q3;
+    c2 += __shfl_sync(0xffffffffu, s2, 31);
+    if (need1) {
+      const double a0 = v.x, a1 = a0 + (double)v.y, a2 = a1 + (double)v.z, a3 = a2 + (double)v.w;
+      const double s1 = warp_incl_scan(a3, lane);
+      const double e1 = c1 + s1 - a3;
+      if (j + 0 < T) P1[j + 1] = e1 + a0;
+      if (j + 1 < T) P1[j + 2] = e1 + a1;
+      if (j + 2 < T) P1[j + 3] = e1 + a2;
+      if (j + 3 < T) P1[j + 4] = e1 + a3;
+      c1 += __shfl_sync(0xffffffffu, s1, 31);
+    }
+    v = nv;
+  }
+  __syncwarp();
+  for (int gi = 0; gi < G.n; ++gi) {
+    const int L = G.L[gi], st = G.s[gi], Tw = G.Tw[gi], SP = G.SP[gi];
+    float* o0 = G.st0[gi] + (size_t)row * SP;
+    float* o1 = need1 ? G.st1[gi] + (size_t)row * SP : nullptr;
+    for (int t = lane; t < SP; t += 32) {
+      float a = 0.f, b = 0.f;
+      if (t < Tw) {
+        const int j0 = t * st;
+        const double sxx = P2[j0 + L] - P2[j0];
+        if (dist == IGN_DIST_SQL2) a = (float)sxx;
+        else if (dist == IGN_DIST_COSINE) a = 1.f / fmaxf(sqrtf((float)sxx), 1e-8f);
+        else {
+          const double sx = P1[j0 + L] - P1[j0];
+          a = (float)fmax(sxx - sx * sx / (double)L, 0.0);
+          b = (float)(sx / (double)L);
+        }
+      }
+      o0[t] = a;
+      if (o1) o1[t] = b;
+    }
+  }
+}
+
 }  // namespace
 
 int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, int T, int M,
@@ -231,6 +302,19 @@ int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, 
 int launch_prefix(const float* xn, double* pre1, double* pre2, int B, int M, int T, cudaStream_t st) {
   const int rows = B * M;
   prefix_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(xn, pre1, pre2, rows, T, padded_len(T), prefix_pitch(T));
+  IGN_CUDA(cudaGetLastError());
+  return IGN_OK;
+}
+
+int launch_window_stats(const float* xn, const StatGroups& G, int B, int M, int T, int dist, cudaStream_t st) {
+  const int rows = B * M;
+  const size_t per_warp = (size_t)(dist == IGN_DIST_PEARSON ? 2 : 1) * (T + 1) * sizeof(double);
+  int warps = 8;
+  while (warps > 1 && warps * per_warp > 64 * 1024) warps >>= 1;
+  const size_t smem = warps * per_warp;
+  if (smem > (size_t)max_optin_smem() - 1024) { set_error("window_stats: series of %d samples do not fit shared memory", T); return IGN_ERR_UNSUPPORTED; }
+  IGN_CUDA(cudaFuncSetAttribute(window_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  window_stats_kernel<<<ceil_div(rows, warps), warps * 32, smem, st>>>(xn, G, rows, T, padded_len(T), dist);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }

@@ -62,8 +62,9 @@ struct Geo {  // geometry shared by forward and backward
 };
 
 struct FwdArgs {
-  const float* xn; const double* pre1; const double* pre2; const float* W; const float* thr;
+  const float* xn; const float* st0; const float* W; const float* thr;   // st0: window statistics [B,M,SP]
   float* p; float* dmin; int* argmin; float* dstore;
+  int SP;
 };
 
 struct BwdArgs {
@@ -76,7 +77,7 @@ struct BwdArgs {
 
 struct PoolArgs {
   const float* g; const float* dstore; const float* dmin; const int* argmin;
-  const double* pre1; const double* pre2; const float* wstat;   // wstat [K][M]: sum (w-mean)^2 (pearson)
+  const float* st0; const float* st1; int SP; const float* wstat;   // window stats [B,M,SP]; wstat [K][M]: sum (w-mean)^2 (pearson)
   float* coef;          // [B][M][K][Ts]
   float* rowsc;         // [B][M][K][2] per-row scalars for the finalize kernel
 };
@@ -126,10 +127,9 @@ __device__ void load_shapelets(const Geo& g, const float* __restrict__ W, int m,
   }
 }
 
-// Series rows for samples [b0,b0+nb) of channel m, de-interleaved by residue; window statistics.
-__device__ void load_series(const Geo& g, const float* __restrict__ xn, const double* __restrict__ pre1,
-                            const double* __restrict__ pre2, int m, int b0, int nb, float* xs, float* st0,
-                            float* st1) {
+// Series rows for samples [b0,b0+nb) of channel m, de-interleaved by residue; window statistics rows.
+__device__ void load_series(const Geo& g, const float* __restrict__ xn, const float* __restrict__ stat, int SP,
+                            int m, int b0, int nb, float* xs, float* st0) {
   const int rowlen = g.s * g.XQ;
   const int total = g.NB * rowlen;
   const int nthr = blockDim.x;
@@ -150,26 +150,13 @@ __device__ void load_series(const Geo& g, const float* __restrict__ xn, const do
       xs[i] = v;
     }
   }
-  if (g.dist != IGN_DIST_L1 && st0) {
-    for (int i = threadIdx.x; i < g.NB * g.DP; i += nthr) {
-      const int bl = i / g.DP, t = i - bl * g.DP;
-      float a = 0.f, c = 0.f;
-      if (bl < nb && t < g.Tw) {
-        const size_t row = ((size_t)(b0 + bl) * g.M + m) * prefix_pitch(g.T) + kPrefixOrigin;
-        const int j0 = t * g.s;
-        const double sxx = pre2[row + j0 + g.L] - pre2[row + j0];
-        if (g.dist == IGN_DIST_SQL2) {
-          a = (float)sxx;
-        } else if (g.dist == IGN_DIST_COSINE) {
-          a = 1.f / fmaxf(sqrtf((float)sxx), 1e-8f);
-        } else {
-          const double sx = pre1[row + j0 + g.L] - pre1[row + j0];
-          a = (float)fmax(sxx - sx * sx / (double)g.L, 0.0);   // sum (x-mu)^2
-          c = (float)(sx / (double)g.L);                       // mu
-        }
-      }
-      st0[i] = a;
-      if (st1) st1[i] = c;
+  if (st0) {   // cross-term distances: per-window norm terms from the window-statistics pass (SP % 16 == 0)
+    const int rowv = g.DP / 4;
+    for (int i = threadIdx.x; i < g.NB * rowv; i += nthr) {
+      const int bl = i / rowv, t = (i - bl * rowv) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bl < nb && t < SP) v = *reinterpret_cast<const float4*>(stat + ((size_t)(b0 + bl) * g.M + m) * SP + t);
+      *reinterpret_cast<float4*>(st0 + bl * g.DP + t) = v;
     }
   }
 }
@@ -306,7 +293,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
   for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
     __syncthreads();   // previous pass finished with xs/cand (and ws is written on the first pass)
-    load_series(g, a.xn, a.pre1, a.pre2, m, b0, nb, xs, st0, nullptr);
+    load_series(g, a.xn, a.st0, a.SP, m, b0, nb, xs, OP != OP_L1 ? st0 : nullptr);
     __syncthreads();
     // ---- phase 1: distances + register epilogue ----
     for (int item = threadIdx.x; item < nitem; item += blockDim.x) {
@@ -444,7 +431,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   Zs = warp_sum(Zs); S1s = warp_sum(S1s);
   const float invZ = 1.f / Zs, bar = S1s * invZ;
   const float wst = (g.dist == IGN_DIST_PEARSON) ? a.wstat[(size_t)k * g.M + m] : 0.f;
-  const size_t prow0 = (size_t)bm * prefix_pitch(g.T) + kPrefixOrigin;
+  const size_t srow = (size_t)bm * a.SP;
   float* dst = a.coef + (size_t)row * g.Ts;
   float sc0 = 0.f, sc1 = 0.f;
 #pragma unroll 2
@@ -465,14 +452,11 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
       if (g.dist == IGN_DIST_L1 || g.dist == IGN_DIST_SQL2) {
         coef = c; sc0 += c;
       } else {
-        const int j0 = t * g.s;
-        const double sxx = a.pre2[prow0 + j0 + g.L] - a.pre2[prow0 + j0];
         if (g.dist == IGN_DIST_COSINE) {
-          coef = c / fmaxf(sqrtf((float)sxx), 1e-8f);
+          coef = c * a.st0[srow + t];
           sc0 = fmaf(c, 1.f - d, sc0);
         } else {
-          const double sx = a.pre1[prow0 + j0 + g.L] - a.pre1[prow0 + j0];
-          const float sxc = (float)fmax(sxx - sx * sx / (double)g.L, 0.0), mu = (float)(sx / (double)g.L);
+          const float sxc = a.st0[srow + t], mu = a.st1[srow + t];
           const float root = sqrtf(sxc * wst), D = root + 1e-8f;
           coef = c / D;
           sc0 = fmaf(coef, mu, sc0);
@@ -574,7 +558,7 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
     __syncthreads();
-    load_series(g, a.xn, nullptr, nullptr, m, b0, nb, xs, nullptr, nullptr);
+    load_series(g, a.xn, nullptr, 0, m, b0, nb, xs, nullptr);
     if (OP == OP_L1) {
       if (threadIdx.x < g.NB) tieflag[threadIdx.x] = a.hcap ? 0 : 1;
     }
@@ -849,15 +833,15 @@ int run_bwd(const Geo& g, const BwdArgs& a, const BwdPlan& bp, cudaStream_t st) 
 
 }  // namespace
 
-int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
-                             const double* pre2, const float* W, const float* thr, float* p, float* dmin,
+int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
+                             const float* W, const float* thr, float* p, float* dmin,
                              int* argmin, float* dstore, cudaStream_t st) {
   Geo g;
   if (!base_geo(d, g)) { set_error("shapelet_forward: T=%d < L=%d (unfold would raise)", d.T, d.L); return IGN_ERR_INVALID; }
   const int TT = g.Tw >= 64 ? 8 : 4;
   FwdPlan fp;
   if (!plan_fwd(g, TT, fp)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
-  FwdArgs a{xn, pre1, pre2, W, thr, p, dmin, argmin, dstore};
+  FwdArgs a{xn, st0, W, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, d.stride)};
   const bool l1 = d.dist == IGN_DIST_L1;
 #define IGN_DISPATCH(OPV, KKV, TTV) return run_fwd<OPV, KKV, TTV>(g, a, fp, st)
   if (l1) {
@@ -890,8 +874,8 @@ size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
   return bwd_workspace(d, g, bp).total * sizeof(float);
 }
 
-int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const double* pre1,
-                             const double* pre2, const float* W, const float* gr, const float* dstore,
+int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
+                             const float* st1, const float* W, const float* gr, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
                              cudaStream_t st) {
   Geo g; BwdPlan bp;
@@ -914,7 +898,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     if (smem > (size_t)max_optin_smem() - 1024) { set_error("shapelet_backward: %d windows per series do not fit shared memory", g.Tw); return IGN_ERR_UNSUPPORTED; }
     int rc = set_smem(pool_bwd_kernel, smem);
     if (rc) return rc;
-    PoolArgs pa{gr, dstore, dmin, argmin, pre1, pre2, base + wo.wstat, base + wo.coef, base + wo.rowsc};
+    PoolArgs pa{gr, dstore, dmin, argmin, st0, st1, stats_pitch(d.T, d.L, d.stride), base + wo.wstat, base + wo.coef, base + wo.rowsc};
     pool_bwd_kernel<<<ceil_div(rows, warps), warps * 32, smem, st>>>(g, pa, rows);
     IGN_CUDA(cudaGetLastError());
   }

@@ -56,8 +56,9 @@ struct TcGeo {
 };
 
 struct TcArgs {
-  const float* xn; const double* pre1; const double* pre2; const float* W; const float* thr;
+  const float* xn; const float* st0; const float* W; const float* thr;   // st0: window statistics [B,M,SP]
   float* p; float* dmin; int* argmin; float* dstore;
+  int SP;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -179,8 +180,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
   const uint32_t tmem_cols = 2 * acc_cols;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpilogueThreads); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpilogueThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
@@ -228,6 +229,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       cp_async_commit();
     };
     if (ntile > 0) prefetch_rows(0, 0);
+    // Per-thread constants: A task q covers row r = 16 q + (p >> 3), chunk c = p & 7; B task u covers shapelet
+    // u, shift j = p >> 3, chunk c.  Swizzled destinations differ only by q * 2048 / u * 2048 bytes.
+    const int pr = p >> 3, pc = p & 7;
+    const uint32_t dst0 = (uint32_t)(pr * 128 + ((pc ^ (pr & 7)) << 4));
+    const int b_src0 = (pr & 3) * g.KG * g.WR + kWshPad + 4 * (pc - (pr >> 2));
+    int a_src[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int r = q * 16 + pr;
+      const int bl = r / g.RI, i = r - bl * g.RI;
+      a_src[q] = bl < g.RB ? bl * g.XR + i * kShifts + pc * 4 : -1;
+    }
     uint32_t it = 0;                                                 // global stage counter
     for (int tile = 0; tile < ntile; ++tile) {
       const int buf = tile & 1;
@@ -236,38 +249,31 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       bar_sync(1, kProducerThreads);      // rows of this tile landed; everyone is done with the other buffer
       if (tile + 1 < ntile) prefetch_rows(tile + 1, buf ^ 1);
       const float* xb = xbuf + (size_t)buf * g.RB * g.XR;
+      const int live_lim = nb * g.XR;                                // a_src below this offset belongs to a live sample
       for (int kb = 0; kb < g.NKB; ++kb, ++it) {
         const int s = it % g.nstage;
         const uint32_t ph = (it / g.nstage) & 1;
         mbar_wait(&empty[s], ph ^ 1);                                // passes immediately on the first lap
-        uint8_t* sa_hi = stage0 + (size_t)s * stage_bytes;
+        uint8_t* sa_hi = stage0 + (size_t)s * stage_bytes + dst0;
         uint8_t* sb_hi = sa_hi + a_bytes;
-        uint8_t* sa_lo = sb_hi + b_bytes;
-        uint8_t* sb_lo = sa_lo + a_bytes;
+        const int lo_off = a_bytes + b_bytes;
         // A tile: row r = bl*RI + i holds x[bl][16 i + 32 kb + (0..31)]
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int task = q * kProducerThreads + p;
-          const int r = task >> 3, c = task & 7;
-          const int bl = r / g.RI, i = r - bl * g.RI;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bl < nb) v = *reinterpret_cast<const float4*>(xb + (size_t)bl * g.XR + i * kShifts + kb * kKBlock + c * 4);
-          const uint32_t off = sw128_off(r, c);
-          *reinterpret_cast<float4*>(sa_hi + off) = v;
-          if (g.split) *reinterpret_cast<float4*>(sa_lo + off) = tf32_lo(v);
+          if (a_src[q] >= 0 && a_src[q] < live_lim) v = *reinterpret_cast<const float4*>(xb + a_src[q] + kb * kKBlock);
+          *reinterpret_cast<float4*>(sa_hi + q * 2048) = v;
+          if (g.split) *reinterpret_cast<float4*>(sa_hi + q * 2048 + lo_off) = tf32_lo(v);
         }
-        // B tile: row n = 16 kl + j holds w'[kl][32 kb + (0..31) - j]
-        for (int task = p; task < g.N * 8; task += kProducerThreads) {
-          const int n = task >> 3, c = task & 7;
-          const int kl = n >> 4, j = n & 15;
-          const float4 v = *reinterpret_cast<const float4*>(
-              wsh + ((size_t)(j & 3) * g.KG + kl) * g.WR + kWshPad + kb * kKBlock + 4 * (c - (j >> 2)));
-          const uint32_t off = sw128_off(n, c);
-          *reinterpret_cast<float4*>(sb_hi + off) = v;
-          if (g.split) *reinterpret_cast<float4*>(sb_lo + off) = tf32_lo(v);
+        // B tile: row n = 16 u + j holds w'[u][32 kb + (0..31) - j]
+        for (int u = 0; u < g.KG; ++u) {
+          const float4 v = *reinterpret_cast<const float4*>(wsh + b_src0 + u * g.WR + kb * kKBlock);
+          *reinterpret_cast<float4*>(sb_hi + u * 2048) = v;
+          if (g.split) *reinterpret_cast<float4*>(sb_hi + u * 2048 + lo_off) = tf32_lo(v);
         }
         fence_proxy_async();                                         // generic-proxy writes -> async proxy (UMMA)
-        mbar_arrive(&full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
       }
     }
   } else if (warp < 8) {
@@ -308,28 +314,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       const bool row_live = bl < g.RB && bl < nb;
       const int b = b0 + bl;
       const int t0 = i * kShifts;
-      // window statistics of this row's 16 windows from the fp64 prefix sums (issued before the wait)
-      float xst[16];
+      // this row's 16 window norm terms (fp32, from the window-statistics pass): four 16-byte loads issued
+      // before the accumulator wait so their latency hides under the MMAs of this tile
+      float4 xs4[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) xst[j] = 0.f;
-      if (row_live) {
-        const size_t prow = ((size_t)b * g.M + m) * prefix_pitch(g.T) + kPrefixOrigin;
+      for (int j = 0; j < 4; ++j) xs4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_live && t0 < a.SP) {
+        const float4* sp = reinterpret_cast<const float4*>(a.st0 + ((size_t)b * g.M + m) * a.SP + t0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int t = t0 + j;
-          if (t < g.Tw) {
-            const double sxx = a.pre2[prow + t + g.L] - a.pre2[prow + t];
-            if (g.dist == IGN_DIST_SQL2) xst[j] = (float)sxx;
-            else if (g.dist == IGN_DIST_COSINE) xst[j] = 1.f / fmaxf(sqrtf((float)sxx), 1e-8f);
-            else {
-              const double sx = a.pre1[prow + t + g.L] - a.pre1[prow + t];
-              xst[j] = (float)fmax(sxx - sx * sx / (double)g.L, 0.0);
-            }
-          }
-        }
+        for (int j = 0; j < 4; ++j) xs4[j] = __ldg(sp + j);
       }
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
       tc_fence_after();
+      const float xst[16] = {xs4[0].x, xs4[0].y, xs4[0].z, xs4[0].w, xs4[1].x, xs4[1].y, xs4[1].z, xs4[1].w,
+                             xs4[2].x, xs4[2].y, xs4[2].z, xs4[2].w, xs4[3].x, xs4[3].y, xs4[3].z, xs4[3].w};
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int kl = 0; kl < g.KG; ++kl) {
         uint32_t v[16];
@@ -360,18 +358,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
         cand_i[e * g.KG + kl] = bi;
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);                                     // accumulator drained
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);                      // this warp's quarter of the accumulator is drained
       bar_sync(2, kEpilogueThreads);
-      // per (sample, shapelet) arg-min over the RI rows of that sample, first index on ties
-      if (e < g.RB * g.KG) {
-        const int rbl = e / g.KG, kl = e - rbl * g.KG;
+      // per (sample, shapelet) arg-min over the RI rows of that sample, first index on ties: one warp per pair
+      for (int pair = ew; pair < g.RB * g.KG; pair += 4) {
+        const int rbl = pair / g.KG, kl = pair - rbl * g.KG;
         const int k = k0 + kl;
-        if (rbl < nb && k < g.K) {
-          float dmn = INFINITY; int imn = 0x7fffffff;
-          for (int ii = 0; ii < g.RI; ++ii) {
-            const float d = cand_d[(rbl * g.RI + ii) * g.KG + kl];
-            if (d < dmn) { dmn = d; imn = cand_i[(rbl * g.RI + ii) * g.KG + kl]; }
-          }
+        if (rbl >= nb || k >= g.K) continue;
+        float dmn = INFINITY; int imn = 0x7fffffff;
+        for (int ii = lane; ii < g.RI; ii += 32) {
+          const float d = cand_d[(rbl * g.RI + ii) * g.KG + kl];
+          if (d < dmn) { dmn = d; imn = cand_i[(rbl * g.RI + ii) * g.KG + kl]; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, dmn, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, imn, o);
+          if (od < dmn || (od == dmn && oi < imn)) { dmn = od; imn = oi; }
+        }
+        if (lane == 0) {
           const size_t o = ((size_t)(b0 + rbl) * g.K + k) * g.M + m;
           float pv;
           if (g.pool == IGN_POOL_RBF_MAX) { const float ed = g.eps * dmn; pv = expf(-(ed * ed)); }
@@ -440,7 +446,7 @@ bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d) {
   return true;
 }
 
-int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const double* pre1, const double* pre2,
+int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const float* st0,
                            const float* W, const float* thr, float* p, float* dmin, int* argmin, float* dstore,
                            cudaStream_t st) {
   TcGeo g;
@@ -464,7 +470,7 @@ int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const do
   g.bpc = round_up(ceil_div(d.B, nchunk), g.RB);
   const size_t smem = tc_smem_bytes(g, g.nstage);
   IGN_CUDA(cudaFuncSetAttribute(shapelet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TcArgs a{xn, pre1, pre2, W, thr, p, dmin, argmin, dstore};
+  TcArgs a{xn, st0, W, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, 1)};
   dim3 grid(d.M, g.nkb, ceil_div(d.B, g.bpc));
   shapelet_fwd_tc_kernel<<<grid, kThreadsTC, smem, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());

@@ -8,7 +8,7 @@ Replaces the eager op chains of the reference:
 """
 from __future__ import annotations
 
-from ctypes import byref
+from ctypes import byref, c_int32, c_void_p
 from typing import Optional, Tuple
 
 import torch
@@ -94,6 +94,7 @@ class SeriesPack:
         self.xn = xn
         self.T = T
         self._pre = None
+        self._stats = {}
 
     @property
     def B(self):
@@ -108,6 +109,7 @@ class SeriesPack:
         return self.xn.shape[2]
 
     def prefix(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Stand-alone fp64 prefix sums (ign_window_prefix); the distance kernels use window_stats() instead."""
         if self._pre is None:
             B, M, T = self.B, self.M, self.T
             pre = torch.empty((2, B, M, C.lib.ign_prefix_pitch(T)), dtype=torch.float64, device=self.xn.device)
@@ -116,6 +118,42 @@ class SeriesPack:
                     _ptr(self.xn), _ptr(pre[0]), _ptr(pre[1]), B, M, T, _stream())), "ign_window_prefix")
             self._pre = (pre[0], pre[1])
         return self._pre
+
+    def prepare_stats(self, dist: str, groups):
+        """One fused prefix + window-difference pass for several (L, stride) groups (ign_window_stats).
+        ShapeBottleneckModel calls this once per batch so the series is scanned once for all its layers."""
+        if dist == "l1":
+            return
+        todo = [(int(L), int(s)) for (L, s) in groups if (dist, int(L), int(s)) not in self._stats]
+        todo = list(dict.fromkeys(todo))
+        B, M, T = self.B, self.M, self.T
+        for i in range(0, len(todo), 8):
+            part = todo[i:i + 8]
+            G = len(part)
+            st0, st1 = [], []
+            for (L, s) in part:
+                sp = C.lib.ign_stats_pitch(T, L, s)
+                buf = torch.empty((2 if dist == "pearson" else 1, B, M, sp), dtype=torch.float32, device=self.xn.device)
+                st0.append(buf[0]); st1.append(buf[1] if dist == "pearson" else None)
+            Ls = (c_int32 * G)(*[L for L, _ in part])
+            Ss = (c_int32 * G)(*[s for _, s in part])
+            p0 = (c_void_p * G)(*[t.data_ptr() for t in st0])
+            p1 = (c_void_p * G)(*[(t.data_ptr() if t is not None else None) for t in st1])
+            with torch.cuda.device(self.xn.device):
+                C.check(STATS.call("window_stats", 1, lambda: C.lib.ign_window_stats(
+                    _ptr(self.xn), B, M, T, G, Ls, Ss, C.DIST[dist], p0, p1 if dist == "pearson" else None,
+                    _stream())), "ign_window_stats")
+            for (L, s), a0, a1 in zip(part, st0, st1):
+                self._stats[(dist, L, s)] = (a0, a1)
+
+    def window_stats(self, dist: str, L: int, stride: int):
+        """(st0, st1) fp32 [B,M,SP] for one group; computed on demand if prepare_stats was not called."""
+        if dist == "l1":
+            return None, None
+        key = (dist, int(L), int(stride))
+        if key not in self._stats:
+            self.prepare_stats(dist, [(L, stride)])
+        return self._stats[key]
 
     @staticmethod
     def from_channel_major(x: torch.Tensor) -> "SeriesPack":
@@ -165,9 +203,7 @@ class _ShapeletTransform(torch.autograd.Function):
             thr = threshold.detach().to(torch.float32).reshape(K, M).contiguous()
         desc = C.ShapeletDesc(B, M, T, Tp, K, L, int(stride), float(eps), C.DIST[dist], C.POOL[pool],
                               C.PRECISION[precision])
-        pre1 = pre2 = None
-        if dist != "l1":
-            pre1, pre2 = pack.prefix()
+        st0, _ = pack.window_stats(dist, L, stride)
         # (grad mode is always off inside Function.forward; needs_input_grad is False under torch.no_grad())
         need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         dev = xn.device
@@ -179,7 +215,7 @@ class _ShapeletTransform(torch.autograd.Function):
             dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             C.check(STATS.call("shapelet_fwd/%s/L%d" % (dist, L), 1, lambda: C.lib.ign_shapelet_forward(
-                byref(desc), _ptr(xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(thr), _ptr(out[0]), _ptr(out[1]),
+                byref(desc), _ptr(xn), _ptr(st0), _ptr(Wc), _ptr(thr), _ptr(out[0]), _ptr(out[1]),
                 _ptr(idx), _ptr(dstore), _stream())), "ign_shapelet_forward")
         ctx.set_materialize_grads(False)
         ctx.desc = desc
@@ -213,15 +249,13 @@ class _ShapeletTransform(torch.autograd.Function):
             g = (-g * sig).contiguous()                 # dLoss/d(min_d)
         dW = None
         if ctx.needs_input_grad[0]:
-            pre1 = pre2 = None
-            if desc.dist != C.DIST["l1"]:
-                pre1, pre2 = pack.prefix()
+            st0, st1 = pack.window_stats(ctx.dist, desc.L, desc.stride)
             nbytes = C.lib.ign_shapelet_backward_workspace(byref(desc))
             ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=g.device)
             dW = torch.empty_like(Wc)
             with torch.cuda.device(g.device):
                 C.check(STATS.call("shapelet_bwd/%s/L%d" % (ctx.dist, desc.L), 2, lambda: C.lib.ign_shapelet_backward(
-                    byref(desc), _ptr(pack.xn), _ptr(pre1), _ptr(pre2), _ptr(Wc), _ptr(g), _ptr(dstore), _ptr(out[1]),
+                    byref(desc), _ptr(pack.xn), _ptr(st0), _ptr(st1), _ptr(Wc), _ptr(g), _ptr(dstore), _ptr(out[1]),
                     _ptr(idx), _ptr(dW), _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
         return dW, dthr, None, None, None, None, None, None
 

@@ -134,6 +134,8 @@ class ShapeBottleneckModel(nn.Module):
 
     def forward(self, x, *args, **kwargs):
         pack = instance_norm(x)                             # Shapelet.py:186-187 (one fused kernel)
+        first = self.shapelets[0]                           # norm terms of all length groups in one pass
+        pack.prepare_stats(first._dist(), [(s.length, s.stride) for s in self.shapelets])
         probs, dists, idxs = [], [], []
         for layer in self.shapelets:                        # Shapelet.py:191-194
             p, d, idx = layer.transform(pack)

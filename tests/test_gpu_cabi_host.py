@@ -54,16 +54,32 @@ def test_instnorm_and_prefix_kernels():
         torch.testing.assert_close(p1[:, :, 4:4 + T].cpu(), r1, rtol=1e-9, atol=1e-9)
         torch.testing.assert_close(p2[:, :, 4:4 + T].cpu(), r2, rtol=1e-9, atol=1e-9)
         assert float(p1[:, :, :4].abs().sum()) == 0.0 and float(p2[:, :, :4].abs().sum()) == 0.0
+        # fused per-group window statistics against the same prefix sums
+        L, s = max(3, T // 5), 1 if T < 3000 else 7
+        Tw = (T - L) // s + 1
+        j0 = torch.arange(Tw) * s
+        sxx = (torch.cat([torch.zeros(B, M, 1, dtype=torch.double), r2], -1)[:, :, j0 + L] -
+               torch.cat([torch.zeros(B, M, 1, dtype=torch.double), r2], -1)[:, :, j0])
+        sx = (torch.cat([torch.zeros(B, M, 1, dtype=torch.double), r1], -1)[:, :, j0 + L] -
+              torch.cat([torch.zeros(B, M, 1, dtype=torch.double), r1], -1)[:, :, j0])
+        a0, _ = pack.window_stats("sql2", L, s)
+        torch.testing.assert_close(a0[:, :, :Tw].double().cpu(), sxx, rtol=2e-7, atol=1e-6)
+        assert float(a0[:, :, Tw:].abs().sum()) == 0.0 and a0.shape[-1] % 16 == 0
+        c0, _ = pack.window_stats("cosine", L, s)
+        torch.testing.assert_close(c0[:, :, :Tw].double().cpu(), 1.0 / sxx.sqrt().clamp_min(1e-8), rtol=1e-6, atol=1e-7)
+        q0, q1 = pack.window_stats("pearson", L, s)
+        torch.testing.assert_close(q1[:, :, :Tw].double().cpu(), sx / L, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(q0[:, :, :Tw].double().cpu(), (sxx - sx * sx / L).clamp_min(0), rtol=1e-5, atol=1e-4)
 
 
 def test_bad_arguments_return_status_not_crash():
     from ctypes import byref
     from layers import ign_cabi as C
     d = C.ShapeletDesc(2, 3, 10, 12, 4, 11, 1, 1.0, 0, 0, 0)
-    rc = C.lib.ign_shapelet_forward(byref(d), *([None] * 10))
+    rc = C.lib.ign_shapelet_forward(byref(d), *([None] * 9))
     assert rc == 1 and "T < L" in C.last_error()
     d = C.ShapeletDesc(2, 3, 16, 16, 4, 5, 1, 1.0, 2, 0, 0)
     x = torch.zeros(2, 3, 16, device="cuda")
-    rc = C.lib.ign_shapelet_forward(byref(d), x.data_ptr(), None, None, x.data_ptr(), None, x.data_ptr(),
+    rc = C.lib.ign_shapelet_forward(byref(d), x.data_ptr(), None, x.data_ptr(), None, x.data_ptr(),
                                     x.data_ptr(), None, None, None)
-    assert rc == 1 and "prefix" in C.last_error()
+    assert rc == 1 and "window statistics" in C.last_error()

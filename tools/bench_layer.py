@@ -51,13 +51,15 @@ def main():
     print(f"instnorm  {t_norm:8.3f} ms  {nbytes / t_norm / 1e6:8.1f} GB/s (algorithmic read+write)")
     rows.append(dict(kernel="instnorm", ms=t_norm, gbs=nbytes / t_norm / 1e6))
 
-    def pref():
-        pack._pre = None
-        pack.prefix()
-    t_pre = timeit(pref, a.iters, flush)
-    pb = x.numel() * 4 + 2 * a.B * a.M * (a.T + 4) * 8
-    print(f"prefix    {t_pre:8.3f} ms  {pb / t_pre / 1e6:8.1f} GB/s")
-    rows.append(dict(kernel="prefix", ms=t_pre, gbs=pb / t_pre / 1e6))
+    Ls = [int(v) for v in a.Ls.split(",")]
+
+    def wstats():
+        pack._stats = {}
+        pack.prepare_stats("cosine", [(L, 1) for L in Ls])
+    t_pre = timeit(wstats, a.iters, flush)
+    pb = x.numel() * 4 + sum(a.B * a.M * ((a.T - L + 1 + 15) // 16 * 16) * 4 for L in Ls)
+    print(f"winstats  {t_pre:8.3f} ms  {pb / t_pre / 1e6:8.1f} GB/s (all {len(Ls)} groups, cosine)")
+    rows.append(dict(kernel="window_stats", ms=t_pre, gbs=pb / t_pre / 1e6))
     for dist in a.dists.split(","):
         tot_f = tot_b = 0.0
         for L in [int(v) for v in a.Ls.split(",")]:
