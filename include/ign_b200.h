@@ -74,6 +74,9 @@ const char* ign_last_error(void);
 /* IGN_OK iff `device` (or the current device when < 0) is compute capability 10.x */
 int32_t ign_device_check(int32_t device);
 
+/* debug: role-level cycle counters of the tcgen05 kernel (only in builds with -DIGN_TC_PROFILE) */
+int32_t ign_debug_tc_profile(uint64_t* host16, int32_t reset);
+
 /* pitch (floats) of one normalised series row: T rounded up to a multiple of 4 (16-byte rows) */
 int32_t ign_padded_len(int32_t T);
 /* number of windows T' (0 when T < L: the reference's unfold raises there) and its padded pitch */

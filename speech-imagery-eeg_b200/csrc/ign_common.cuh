@@ -56,6 +56,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
                              const float* st1, const float* W, const float* g, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
                              cudaStream_t st);
+int tc_profile_read(unsigned long long* host16, int reset);
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d);
 int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const float* st0,
                            const float* W, const float* thr, float* p, float* dmin, int* argmin, float* dstore,

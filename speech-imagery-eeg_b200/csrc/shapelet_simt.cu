@@ -234,11 +234,13 @@ __device__ __forceinline__ void distance_item(const Geo& g, const float* __restr
 
 // raw accumulator -> distance
 template <int OP>
-__device__ __forceinline__ float finish_distance(int dist, float raw, float L, float xstat, float wstat) {
-  if (OP == OP_L1) return raw / L;
-  if (dist == IGN_DIST_SQL2) return fmaxf((xstat + wstat - 2.f * raw) / L, 0.f);
+__device__ __forceinline__ float finish_distance(int dist, float raw, float invL, float xstat, float wstat) {
+  // (multiplication by 1/L and __fdividef differ from the reference's true divisions by <= 2 ulp and avoid the
+  //  IEEE-division slow path, which zero numerators on padded windows would otherwise take warp-wide)
+  if (OP == OP_L1) return raw * invL;
+  if (dist == IGN_DIST_SQL2) return fmaxf((xstat + wstat - 2.f * raw) * invL, 0.f);
   if (dist == IGN_DIST_COSINE) return 1.f - raw * xstat * wstat;
-  return 1.f - raw / (sqrtf(xstat * wstat) + 1e-8f);
+  return 1.f - __fdividef(raw, sqrtf(xstat * wstat) + 1e-8f);
 }
 
 struct ArgVal { float v; int i; };
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
   load_shapelets(g, a.W, m, k0, ws, wstat);
 
   const int nitem = g.NB * ntile * nkc;
-  const float Lf = (float)g.L;
+  const float Lf = 1.f / (float)g.L;   // 1/L
 
   for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
@@ -458,9 +460,9 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
         } else {
           const float sxc = a.st0[srow + t], mu = a.st1[srow + t];
           const float root = sqrtf(sxc * wst), D = root + 1e-8f;
-          coef = c / D;
+          coef = __fdividef(c, D);
           sc0 = fmaf(coef, mu, sc0);
-          sc1 += c * (1.f - d) * sxc / (root * D);
+          sc1 += __fdividef(c * (1.f - d) * sxc, root * D);
         }
       }
     }

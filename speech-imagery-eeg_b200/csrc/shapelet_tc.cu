@@ -148,6 +148,16 @@ __device__ __forceinline__ float4 tf32_lo(float4 v) {   // v - trunc_tf32(v), ex
   return o;
 }
 
+// Optional role-level cycle accounting (debug builds only: -DIGN_TC_PROFILE).
+#ifdef IGN_TC_PROFILE
+__device__ unsigned long long g_tc_prof[16];
+#define TC_CLK() clock64()
+#define TC_ADD(slot, t0) atomicAdd(&g_tc_prof[slot], (unsigned long long)(clock64() - (t0)))
+#else
+#define TC_CLK() 0ll
+#define TC_ADD(slot, t0) ((void)(t0))
+#endif
+
 // ---------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const TcGeo g, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -245,15 +255,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     for (int tile = 0; tile < ntile; ++tile) {
       const int buf = tile & 1;
       const int nb = min(g.RB, bend - (bbeg + tile * g.RB));
+      long long tr0 = TC_CLK();
       cp_async_wait_all();
       bar_sync(1, kProducerThreads);      // rows of this tile landed; everyone is done with the other buffer
+      if (p == 0) TC_ADD(3, tr0);
       if (tile + 1 < ntile) prefetch_rows(tile + 1, buf ^ 1);
       const float* xb = xbuf + (size_t)buf * g.RB * g.XR;
       const int live_lim = nb * g.XR;                                // a_src below this offset belongs to a live sample
       for (int kb = 0; kb < g.NKB; ++kb, ++it) {
         const int s = it % g.nstage;
         const uint32_t ph = (it / g.nstage) & 1;
+        long long tp0 = TC_CLK();
         mbar_wait(&empty[s], ph ^ 1);                                // passes immediately on the first lap
+        if (p == 0) TC_ADD(0, tp0);
+        tp0 = TC_CLK();
         uint8_t* sa_hi = stage0 + (size_t)s * stage_bytes + dst0;
         uint8_t* sb_hi = sa_hi + a_bytes;
         const int lo_off = a_bytes + b_bytes;
@@ -271,9 +286,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
           *reinterpret_cast<float4*>(sb_hi + u * 2048) = v;
           if (g.split) *reinterpret_cast<float4*>(sb_hi + u * 2048 + lo_off) = tf32_lo(v);
         }
+        if (p == 0) TC_ADD(1, tp0);
+        tp0 = TC_CLK();
         fence_proxy_async();                                         // generic-proxy writes -> async proxy (UMMA)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
+        if (p == 0) TC_ADD(2, tp0);
       }
     }
   } else if (warp < 8) {
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     const int e = threadIdx.x - kProducerThreads;                   // 0..127 = accumulator row
     const int ew = warp - 4;                                        // TMEM lane quarter
     const int bl = e / g.RI, i = e - bl * g.RI;
-    const float Lf = (float)g.L;
+    const float invL = 1.f / (float)g.L;
     for (int kl = ew; kl < g.KG; kl += 4) {       // shapelet statistics (same arithmetic as the FP32 engine)
       const int k = k0 + kl;
       float stat = 0.f;
@@ -324,7 +342,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
 #pragma unroll
         for (int j = 0; j < 4; ++j) xs4[j] = __ldg(sp + j);
       }
+      long long te0 = TC_CLK();
       mbar_wait(&tfull[acc], (tile >> 1) & 1);
+      if (e == 0) TC_ADD(7, te0);
+      te0 = TC_CLK();
       tc_fence_after();
       const float xst[16] = {xs4[0].x, xs4[0].y, xs4[0].z, xs4[0].w, xs4[1].x, xs4[1].y, xs4[1].z, xs4[1].w,
                              xs4[2].x, xs4[2].y, xs4[2].z, xs4[2].w, xs4[3].x, xs4[3].y, xs4[3].z, xs4[3].w};
@@ -341,9 +362,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
         for (int j = 0; j < 16; ++j) {
           const float raw = __uint_as_float(v[j]);
           float d;
-          if (g.dist == IGN_DIST_SQL2) d = fmaxf((xst[j] + wst - 2.f * raw) / Lf, 0.f);
+          if (g.dist == IGN_DIST_SQL2) d = fmaxf((xst[j] + wst - 2.f * raw) * invL, 0.f);
           else if (g.dist == IGN_DIST_COSINE) d = 1.f - raw * xst[j] * wst;
-          else d = 1.f - raw / (sqrtf(xst[j] * wst) + 1e-8f);
+          else d = 1.f - __fdividef(raw, sqrtf(xst[j] * wst) + 1e-8f);   // no IEEE slow path on zero numerators
           const bool valid = row_live && k < g.K && (t0 + j) < g.Tw;
           dv[j] = valid ? d : 0.f;
           if (valid && d < best) { best = d; bi = t0 + j; }
@@ -360,6 +381,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);                      // this warp's quarter of the accumulator is drained
+      if (e == 0) TC_ADD(8, te0);
+      te0 = TC_CLK();
       bar_sync(2, kEpilogueThreads);
       // per (sample, shapelet) arg-min over the RI rows of that sample, first index on ties: one warp per pair
       for (int pair = ew; pair < g.RB * g.KG; pair += 4) {
@@ -387,6 +410,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
         }
       }
       bar_sync(2, kEpilogueThreads);                                 // cand arrays free for the next tile
+      if (e == 0) TC_ADD(9, te0);
     }
   } else {
     // =================================================================== MMA ISSUER (one thread)
@@ -395,12 +419,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       uint32_t it = 0;
       for (int tile = 0; tile < ntile; ++tile) {
         const int acc = tile & 1;
+        long long tm0 = TC_CLK();
         mbar_wait(&tempty[acc], ((tile >> 1) & 1) ^ 1);              // passes immediately for the first two tiles
+        TC_ADD(4, tm0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
         for (int kb = 0; kb < g.NKB; ++kb, ++it) {
           const int s = it % g.nstage;
+          tm0 = TC_CLK();
           mbar_wait(&full[s], (it / g.nstage) & 1);
+          TC_ADD(5, tm0);
+          tm0 = TC_CLK();
           tc_fence_after();
           const uint32_t sa_hi = smem_u32(stage0 + (size_t)s * stage_bytes);
           const uint32_t sb_hi = sa_hi + a_bytes;
@@ -418,6 +447,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
             }
           }
           umma_commit(&empty[s]);                                    // stage reusable once these MMAs retire
+          TC_ADD(6, tm0);
         }
         umma_commit(&tfull[acc]);                                    // accumulator complete
       }
@@ -437,6 +467,18 @@ size_t tc_smem_bytes(const TcGeo& g, int nstage) {
 }
 
 }  // namespace
+
+int tc_profile_read(unsigned long long* host16, int reset) {
+#ifdef IGN_TC_PROFILE
+  IGN_CUDA(cudaMemcpyFromSymbol(host16, g_tc_prof, sizeof(unsigned long long) * 16));
+  if (reset) { unsigned long long z[16] = {0}; IGN_CUDA(cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z))); }
+  return IGN_OK;
+#else
+  (void)host16; (void)reset;
+  set_error("library built without -DIGN_TC_PROFILE");
+  return IGN_ERR_UNSUPPORTED;
+#endif
+}
 
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d) {
   if (d.dist == IGN_DIST_L1 || d.stride != 1) return false;
