@@ -150,6 +150,7 @@ class CpuReferenceStep:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import ign_oracle as O
         from models.FullyConvNet import FullyConvNetwork
+        from models.Transformer import Model as TransformerExpert
         self.O = O
         cfg = model_args(a)
         torch.manual_seed(0)
@@ -158,7 +159,7 @@ class CpuReferenceStep:
         self.strides = [O.shapelet_stride(T, L) for L in self.lens]
         self.Ws = [torch.normal(0, 1, (K_PER_LEN, M, L)).requires_grad_(True) for L in self.lens]
         self.Wc = (torch.randn(C, K_PER_LEN * M * len(self.lens)) * 0.02).requires_grad_(True)
-        self.fcn = FullyConvNetwork(cfg)
+        self.fcn = TransformerExpert(cfg) if a.dnn_type == "Transformer" else FullyConvNetwork(cfg)
         self.mode = O.resolve_mode(a.distance_func, a.memory_efficient)
         self.opt = torch.optim.Adam(self.Ws + [self.Wc] + list(self.fcn.parameters()), lr=5e-3)
         self.cfg = cfg
@@ -166,7 +167,7 @@ class CpuReferenceStep:
     def step(self, x, y):
         O = self.O
         sbm_out, probs, dists = O.sbm_forward(x, self.Ws, self.strides, self.Wc, 1.0, self.mode)
-        deep_out = self.fcn(x)
+        deep_out = self.fcn(x, torch.ones(x.shape[0], x.shape[1]), None, None)
         out, eta = O.gate_forward(sbm_out, deep_out)
         loss = torch.nn.functional.cross_entropy(out, y) + O.sbm_loss(self.Wc, self.Ws, 0.1, 0.1) \
             + torch.nn.functional.cross_entropy(sbm_out, y)

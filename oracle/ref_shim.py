@@ -44,7 +44,9 @@ def load_reference():
     saved = {k: sys.modules.get(k) for k in (
         "utils", "utils.shapelet_util", "models", "models.Shapelet", "models.FullyConvNet",
         "models.PatchTST", "models.TimesNet", "models.Transformer", "models.ResNet",
-        "seaborn", "matplotlib", "matplotlib.colors", "matplotlib.pyplot", "sklearn.manifold")}
+        "seaborn", "matplotlib", "matplotlib.colors", "matplotlib.pyplot", "sklearn.manifold",
+        "layers", "layers.Embed", "layers.SelfAttention_Family", "layers.Transformer_EncDec", "utils.masking",
+        "reformer_pytorch")}
     try:
         # stubs for absent plotting deps pulled in by utils/shapelet_util.py:8-11
         for n in ("seaborn", "matplotlib", "matplotlib.colors", "matplotlib.pyplot"):
@@ -65,10 +67,21 @@ def load_reference():
         sys.modules["models"] = mpkg
         sys.modules["models.Shapelet"] = shp
         sys.modules["models.FullyConvNet"] = fcn
-        for n in ("PatchTST", "TimesNet", "Transformer", "ResNet"):
+        for n in ("PatchTST", "TimesNet", "ResNet"):
             ph = types.ModuleType("models." + n)
             ph.Model = type("Unavailable" + n, (), {})
             sys.modules["models." + n] = ph
+        # the Transformer expert: its layers import reformer_pytorch (absent) for an unused attention variant
+        rp = types.ModuleType("reformer_pytorch")
+        rp.LSHSelfAttention = object
+        sys.modules["reformer_pytorch"] = rp
+        upkg.masking = _load("utils.masking", "utils/masking.py")
+        lpkg = types.ModuleType("layers")
+        sys.modules["layers"] = lpkg
+        for n in ("Embed", "SelfAttention_Family", "Transformer_EncDec"):
+            setattr(lpkg, n, _load("layers." + n, "layers/%s.py" % n))
+        trf = _load("_ignref_Transformer", "model/Transformer.py")
+        sys.modules["models.Transformer"] = trf
         ign = _load("_ignref_InterpGN", "model/InterpGN.py")
     finally:
         for k, v in saved.items():
@@ -80,6 +93,7 @@ def load_reference():
         Shapelet=shp.Shapelet, DistThresholdShapelet=shp.DistThresholdShapelet,
         ShapeBottleneckModel=shp.ShapeBottleneckModel, DistThresholdSBM=shp.DistThresholdSBM,
         ShapeletDistanceFunc=shp.ShapeletDistanceFunc, pearson_corrcoef=shp.pearson_corrcoef,
-        InterpGN=ign.InterpGN, FullyConvNetwork=fcn.FullyConvNetwork, ModelInfo=util.ModelInfo)
+        InterpGN=ign.InterpGN, FullyConvNetwork=fcn.FullyConvNetwork, Transformer=trf.Model,
+        ModelInfo=util.ModelInfo)
     _cache["ns"] = ns
     return ns

@@ -94,6 +94,7 @@ def model_case(name, cfg_kw, B, seed, gating_value=None, cls="InterpGN"):
                           sbm_cls="linear", dropout=0., lambda_reg=0.1, lambda_div=0.1, dnn_type="FCN")
     for k, v in cfg_kw.items():
         setattr(cfg, k, v)
+    keep_deep_grads = cfg.dnn_type != "FCN"      # small expert: keep its gradients too
     torch.manual_seed(seed)
     model = getattr(ns, cls)(cfg)
     model.train()
@@ -118,7 +119,9 @@ def model_case(name, cfg_kw, B, seed, gating_value=None, cls="InterpGN"):
     for k, v in model.state_dict().items():
         out["sd::" + k] = np_(v)
     for k, v in model.named_parameters():
-        if k.startswith("deep_model."):      # not our kernels' gradients: keep a checksum only
+        if v.grad is None:                    # e.g. the unused temporal embedding of the Transformer expert
+            continue
+        if k.startswith("deep_model.") and not keep_deep_grads:      # not our kernels' gradients: keep a checksum only
             out["gradsum::" + k] = np.array([float(v.grad.double().sum()), float(v.grad.double().abs().sum())])
         else:
             out["grad::" + k] = np_(v.grad)
@@ -147,3 +150,8 @@ if __name__ == "__main__":
     model_case("model_jv_sbm", jv, B=4, seed=0, cls="ShapeBottleneckModel")
     model_case("model_jv_lts", jv, B=4, seed=0, cls="DistThresholdSBM")
     model_case("model_small_chisco", dict(enc_in=7, num_class=3, seq_len=120), B=2, seed=42)
+    # Transformer deep expert (BASELINE config 5 in miniature): run.py defaults scaled down
+    model_case("model_small_transformer", dict(enc_in=7, num_class=5, seq_len=64, dnn_type="Transformer",
+               task_name="classification", pred_len=0, label_len=0, output_attention=False, d_model=32, embed="timeF",
+               freq="h", factor=1, n_heads=4, d_ff=64, activation="gelu", e_layers=2, dec_in=7, c_out=7, d_layers=1),
+               B=3, seed=7)

@@ -18,8 +18,16 @@ def build(name):
     g = load_golden(name)
     kw = dict(zip(g["cfg_keys"].tolist(), g["cfg_vals"].tolist()))
     cfg = SimpleNamespace(epsilon=1., distance_func=kw.get("distance_func", "euclidean"), memory_efficient=False,
-                          sbm_cls="linear", dropout=0., lambda_reg=0.1, lambda_div=0.1, dnn_type="FCN",
+                          sbm_cls="linear", dropout=0., lambda_reg=0.1, lambda_div=0.1,
+                          dnn_type=kw.get("dnn_type", "FCN"),
                           enc_in=int(kw["enc_in"]), num_class=int(kw["num_class"]), seq_len=int(kw["seq_len"]))
+    for key in ("task_name", "embed", "freq", "activation"):
+        if key in kw:
+            setattr(cfg, key, kw[key])
+    for key in ("pred_len", "label_len", "d_model", "factor", "n_heads", "d_ff", "e_layers"):
+        if key in kw:
+            setattr(cfg, key, int(kw[key]))
+    cfg.output_attention = False
     cls = DistThresholdSBM if name.endswith("lts") else ShapeBottleneckModel if name.endswith("sbm") else InterpGN
     model = cls(cfg)
     model.load_state_dict({k[4:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("sd::")})
@@ -27,7 +35,7 @@ def build(name):
 
 
 @pytest.mark.parametrize("name", ["model_jv_interpgn", "model_jv_interpgn_gate", "model_jv_interpgn_cos",
-                                  "model_jv_sbm", "model_jv_lts", "model_small_chisco"])
+                                  "model_jv_sbm", "model_jv_lts", "model_small_chisco", "model_small_transformer"])
 def test_model_matches_reference_golden(name):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False

@@ -101,3 +101,22 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+(ign_oracle|ref_shim|oracle)\b", src, re.M), f
+
+
+def test_transformer_expert_matches_reference_golden_on_cpu():
+    """The deep expert is plain PyTorch (SDPA instead of the reference's materialised attention), so its parity
+    against the reference's outputs is checkable without a GPU."""
+    from models.Transformer import Model
+    g = load_golden("model_small_transformer")
+    kw = dict(zip(g["cfg_keys"].tolist(), g["cfg_vals"].tolist()))
+    c = cfg(enc_in=int(kw["enc_in"]), num_class=int(kw["num_class"]), seq_len=int(kw["seq_len"]), task_name="classification",
+            d_model=int(kw["d_model"]), embed="timeF", freq="h", n_heads=int(kw["n_heads"]), d_ff=int(kw["d_ff"]),
+            activation="gelu", e_layers=int(kw["e_layers"]))
+    m = Model(c)
+    sd = {k[len("sd::deep_model."):]: torch.as_tensor(v) for k, v in g.items() if k.startswith("sd::deep_model.")}
+    assert sorted(sd) == sorted(m.state_dict())
+    m.load_state_dict(sd)
+    x = torch.as_tensor(g["x"])
+    with torch.no_grad():
+        out = m(x, torch.ones(x.shape[0], x.shape[1]), None, None)
+    assert torch.allclose(out, torch.as_tensor(g["dnn_preds"]), rtol=1e-4, atol=1e-5)

@@ -88,7 +88,7 @@ def test_gate_closed_form(gv):
 
 
 MODEL_CASES = ["model_jv_interpgn", "model_jv_interpgn_gate", "model_jv_interpgn_cos", "model_jv_sbm",
-               "model_jv_lts", "model_small_chisco"]
+               "model_jv_lts", "model_small_chisco", "model_small_transformer"]
 
 
 @pytest.mark.parametrize("name", MODEL_CASES)
