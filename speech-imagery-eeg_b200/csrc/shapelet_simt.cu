@@ -72,7 +72,7 @@ struct BwdArgs {
   const float* coef;    // [B][M][K][Ts] per-window coefficients a_t written by pool_bwd_kernel
   float* part;          // [nchunk][K][M][L]
   int nseg, nlb, tlb;   // t-segments per row, l-blocks, l-tiles per l-block
-  int hcap;             // L1 only: capacity (power of two) of the shapelet-value hash set; 0 = always exact
+  const unsigned char* tie;   // L1 only: [B][M][nkb] 1 = this row may contain x == w (exact path); NULL = always exact
 };
 
 struct PoolArgs {
@@ -488,7 +488,59 @@ __global__ void __launch_bounds__(256) shapelet_centred_norm_kernel(const float*
   if (lane == 0) wstat[row] = c2;
 }
 
+// L1 only.  Exact ties x == w are impossible for a series row that shares no value with the shapelet block
+// it is contracted against; this pre-pass decides that per (sample, channel, shapelet block) with a hash set
+// of the block's shapelet values in shared memory, so the hot kernel can take the 2-instruction path.
+__global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict__ xn, const float* __restrict__ W,
+                                                        unsigned char* __restrict__ tie, int B, int M, int T, int Tp,
+                                                        int K, int L, int KB, int nkb, int hcap, int bsplit) {
+  extern __shared__ unsigned hset[];
+  const int m = blockIdx.x, kblk = blockIdx.y;
+  const int k0 = kblk * KB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < hcap; i += blockDim.x) hset[i] = kHashEmpty;
+  __syncthreads();
+  const unsigned mask = hcap - 1;
+  for (int i = threadIdx.x; i < KB * L; i += blockDim.x) {
+    const int hk = i / L, l = i - hk * L;
+    if (k0 + hk >= K) continue;
+    const unsigned key = hash_key(__ldg(W + ((size_t)(k0 + hk) * M + m) * L + l));
+    unsigned h = hash_slot(key, mask);
+    while (true) {
+      const unsigned old = atomicCAS(&hset[h], kHashEmpty, key);
+      if (old == kHashEmpty || old == key) break;
+      h = (h + 1) & mask;
+    }
+  }
+  __syncthreads();
+  const int per = ceil_div(B, bsplit);
+  const int bbeg = blockIdx.z * per, bend = min(B, bbeg + per);
+  for (int b = bbeg + warp; b < bend; b += nwarp) {
+    const float* xr = xn + ((size_t)b * M + m) * Tp;
+    int hit = 0;
+    for (int t = lane; t < T; t += 32) {
+      const unsigned key = hash_key(__ldg(xr + t));
+      unsigned h = hash_slot(key, mask);
+      while (true) {
+        const unsigned v = hset[h];
+        if (v == key) { hit = 1; break; }
+        if (v == kHashEmpty) break;
+        h = (h + 1) & mask;
+      }
+    }
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) tie[((size_t)b * M + m) * nkb + kblk] = (unsigned char)hit;
+  }
+}
+
 // ---- contraction kernel: dW partials from the coefficients and the series (pure FP32-pipe work) ----
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -505,32 +557,19 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   const int nslot = g.NB * a.nseg;
   const int nitem = nslot * ntl * g.KB;                   // <= blockDim.x by construction
 
-  float* xs = smem;
-  float* ws = xs + g.NB * g.s * g.XQ;
-  float* cbuf = ws + g.KB * g.s * g.LQ;                   // coefficient rows; reused for the final reduction
-  const int cred = max(g.NB * g.KB * g.DP, kMaxThreads * LT);
-  float* wstat = cbuf + cred;
-  int* tieflag = reinterpret_cast<int*>(wstat + g.KB);    // [NB] row may contain x == w
-  unsigned* hset = reinterpret_cast<unsigned*>(tieflag + g.NB);
+  // unit stride: series and coefficient rows are double-buffered and prefetched with cp.async one pass ahead
+  const bool dbuf = g.s == 1;
+  const int xs_sz = g.NB * g.s * g.XQ;
+  const int cb_sz = max(g.NB * g.KB * g.DP, dbuf ? 0 : kMaxThreads * LT);
+  float* xs0 = smem;
+  float* cb0 = xs0 + (dbuf ? 2 : 1) * xs_sz;
+  float* ws = cb0 + max((dbuf ? 2 : 1) * cb_sz, kMaxThreads * LT);
+  float* wstat = ws + g.KB * g.s * g.LQ;
 
-  if (OP == OP_L1) {
-    load_shapelets(g, a.W, m, k0, ws, wstat);
-    if (a.hcap) {
-      for (int i = threadIdx.x; i < a.hcap; i += nthr) hset[i] = kHashEmpty;
-      __syncthreads();
-      const unsigned mask = a.hcap - 1;
-      for (int i = threadIdx.x; i < g.KB * g.L; i += nthr) {
-        const int hk = i / g.L, l = i - hk * g.L;
-        if (k0 + hk >= g.K) continue;
-        const unsigned key = hash_key(ws[((size_t)hk * g.s + l % g.s) * g.LQ + l / g.s]);
-        unsigned h = hash_slot(key, mask);
-        while (true) {
-          const unsigned old = atomicCAS(&hset[h], kHashEmpty, key);
-          if (old == kHashEmpty || old == key) break;
-          h = (h + 1) & mask;
-        }
-      }
-    }
+  if (OP == OP_L1) load_shapelets(g, a.W, m, k0, ws, wstat);
+  if (dbuf) {   // zero once: pad columns (series tail, DP - Ts) are never written by the prefetch
+    for (int i = threadIdx.x; i < 2 * xs_sz; i += nthr) xs0[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * cb_sz; i += nthr) cb0[i] = 0.f;
   }
 
   // this thread's fixed tile: 8 lags of one shapelet, one (sample slot, t-segment)
@@ -557,14 +596,36 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     for (int i = 0; i < LT; ++i) wreg[i] = ws[((size_t)kl * g.s + r) * g.LQ + q0 + i];
   }
 
+  auto prefetch = [&](int b0, int buf) {
+    const int nb = min(g.NB, bend - b0);
+    float* xd = xs0 + buf * xs_sz;
+    float* cd = cb0 + buf * cb_sz;
+    const int xrow = g.Tp / 4;
+    for (int i = threadIdx.x; i < nb * xrow; i += nthr) {
+      const int rbl = i / xrow, c = i - rbl * xrow;
+      cp_async16(xd + rbl * g.XQ + c * 4, a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp + c * 4);
+    }
+    const int crow = g.Ts / 4;
+    const int kvalid = min(g.KB, g.K - k0);
+    for (int i = threadIdx.x; i < nb * kvalid * crow; i += nthr) {
+      const int row = i / crow, c = i - row * crow;
+      const int rbl = row / kvalid, rkl = row - rbl * kvalid;
+      cp_async16(cd + ((size_t)rbl * g.KB + rkl) * g.DP + c * 4,
+                 a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c * 4);
+    }
+  };
+
+  int buf = 0;
+  if (dbuf && bbeg < bend) prefetch(bbeg, 0);
   for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
-    __syncthreads();
-    load_series(g, a.xn, nullptr, 0, m, b0, nb, xs, nullptr);
-    if (OP == OP_L1) {
-      if (threadIdx.x < g.NB) tieflag[threadIdx.x] = a.hcap ? 0 : 1;
-    }
-    {  // coefficient rows -> shared memory (coalesced 16-byte loads, many in flight)
+    if (dbuf) {
+      cp_async_commit_wait_all();
+      __syncthreads();                    // pass data visible; everyone is done with the other buffer
+      if (b0 + g.NB < bend) prefetch(b0 + g.NB, buf ^ 1);
+    } else {
+      __syncthreads();
+      load_series(g, a.xn, nullptr, 0, m, b0, nb, xs0, nullptr);
       const int rowv = g.DP / 4, tot = g.NB * g.KB * rowv;
       for (int i = threadIdx.x; i < tot; i += nthr) {
         const int row = i / rowv, c4 = (i - row * rowv) * 4;
@@ -572,29 +633,17 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rbl < nb && k0 + rkl < g.K && c4 < g.Ts)
           v = *reinterpret_cast<const float4*>(a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c4);
-        *reinterpret_cast<float4*>(cbuf + (size_t)row * g.DP + c4) = v;
-      }
-    }
-    __syncthreads();
-    if (OP == OP_L1 && a.hcap) {   // does any sample of this row equal any shapelet value?
-      const unsigned mask = a.hcap - 1;
-      for (int i = threadIdx.x; i < nb * g.T; i += nthr) {
-        const int rbl = i / g.T, t = i - rbl * g.T;
-        const unsigned key = hash_key(xs[((size_t)rbl * g.s + t % g.s) * g.XQ + t / g.s]);
-        unsigned h = hash_slot(key, mask);
-        while (true) {
-          const unsigned v = hset[h];
-          if (v == key) { tieflag[rbl] = 1; break; }
-          if (v == kHashEmpty) break;
-          h = (h + 1) & mask;
-        }
+        *reinterpret_cast<float4*>(cb0 + (size_t)row * g.DP + c4) = v;
       }
       __syncthreads();
     }
+    const float* xs = xs0 + buf * xs_sz;
+    const float* cbuf = cb0 + buf * cb_sz;
     // ---- contraction over windows, sliding along t with a 12-register ring of x
-    if (active && bl < nb && ta < tb) {
+    if (active && bl < nb && ta < tb && k0 + kl < g.K) {
       const float* xr = xs + ((size_t)bl * g.s + r) * g.XQ + q0;
       const float* cb = cbuf + ((size_t)bl * g.KB + kl) * g.DP;
+      const bool exact = OP == OP_L1 && (a.tie == nullptr || a.tie[((size_t)(b0 + bl) * g.M + m) * g.nkb + kblk] != 0);
       float xv[12];
       {
         float4 v0 = *reinterpret_cast<const float4*>(xr + ta);
@@ -627,15 +676,17 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
           if (t + 4 <= tb) { IGN_BWD_STEP(EX, 4, t) t += 4; }                                \
         }                                                                                    \
       }
-      if (OP == OP_L1 && tieflag[bl]) IGN_BWD_SWEEP(true) else IGN_BWD_SWEEP(false)
+      if (exact) IGN_BWD_SWEEP(true) else IGN_BWD_SWEEP(false)
 #undef IGN_BWD_SWEEP
 #undef IGN_BWD_STEP
     }
+    if (dbuf) buf ^= 1;
   }
 
   // ---- fixed-order reduction over (sample slot, t-segment), then one partial per chunk ----
+  if (dbuf) cp_async_commit_wait_all();
   __syncthreads();
-  float* red = cbuf;
+  float* red = cb0;
   if (active) {
     const int slot = bl * a.nseg + seg;
     float* dst = red + (((size_t)(kl * ntl + lt)) * nslot + slot) * LT;
@@ -766,13 +817,15 @@ int bwd_hash_cap(const Geo& g, int KB) {
   if (g.dist != IGN_DIST_L1) return 0;
   size_t need = 2 * (size_t)KB * g.L, cap = 256;
   while (cap < need) cap <<= 1;
-  return cap <= 16384 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path
+  return cap <= 32768 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path
 }
 
 size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
-  size_t cred = (size_t)NB * KB * g.DP;
-  if (cred < (size_t)kMaxThreads * LT) cred = (size_t)kMaxThreads * LT;
-  return (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + cred + KB + NB + bwd_hash_cap(g, KB);
+  const size_t mult = g.s == 1 ? 2 : 1;       // double-buffered for unit stride
+  const size_t xs = (size_t)NB * g.s * g.XQ, cb = (size_t)NB * KB * g.DP;
+  size_t cbt = mult * cb;
+  if (cbt < (size_t)kMaxThreads * LT) cbt = (size_t)kMaxThreads * LT;
+  return mult * xs + cbt + (size_t)KB * g.s * g.LQ + KB;
 }
 
 bool plan_bwd(Geo& g, BwdPlan& bp) {
@@ -857,7 +910,7 @@ int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   return IGN_OK;
 }
 
-struct BwdWorkspace { size_t part, coef, rowsc, wstat, total; };   // offsets/size in floats
+struct BwdWorkspace { size_t part, coef, rowsc, wstat, tie, total; };   // offsets/size in floats
 
 BwdWorkspace bwd_workspace(const ign_shapelet_desc& d, const Geo& g, const BwdPlan& bp) {
   BwdWorkspace w;
@@ -866,7 +919,8 @@ BwdWorkspace bwd_workspace(const ign_shapelet_desc& d, const Geo& g, const BwdPl
   w.coef = (w.coef + 3) / 4 * 4;                         // 16-byte aligned rows
   w.rowsc = w.coef + (size_t)d.B * d.M * d.K * g.Ts;
   w.wstat = w.rowsc + (size_t)d.B * d.M * d.K * 2;
-  w.total = w.wstat + (size_t)d.K * d.M;
+  w.tie = w.wstat + (size_t)d.K * d.M;
+  w.total = w.tie + ((size_t)d.B * d.M * g.nkb + 3) / 4;   // bytes, rounded up to floats
   return w;
 }
 
@@ -905,7 +959,19 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     IGN_CUDA(cudaGetLastError());
   }
   // 2. contraction with the series (FP32 pipe) into per-chunk partials
-  BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, bp.hcap};
+  const unsigned char* tie = nullptr;
+  if (d.dist == IGN_DIST_L1 && bp.hcap) {
+    unsigned char* tflags = reinterpret_cast<unsigned char*>(base + wo.tie);
+    const int bsplit = max(1, min(d.B, ceil_div(4 * sm_count(), d.M * g.nkb)));
+    const size_t hs = (size_t)bp.hcap * sizeof(unsigned);
+    int rc0 = set_smem(tie_check_kernel, hs);
+    if (rc0) return rc0;
+    tie_check_kernel<<<dim3(d.M, g.nkb, bsplit), 256, hs, st>>>(xn, W, tflags, d.B, d.M, d.T, d.Tp, d.K, d.L, g.KB,
+                                                               g.nkb, bp.hcap, bsplit);
+    IGN_CUDA(cudaGetLastError());
+    tie = tflags;
+  }
+  BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, tie};
   int rc = d.dist == IGN_DIST_L1 ? run_bwd<OP_L1>(g, a, bp, st) : run_bwd<OP_DOT>(g, a, bp, st);
   if (rc) return rc;
   // 3. combine
