@@ -106,7 +106,7 @@ int32_t ign_stats_pitch(int32_t T, int32_t L, int32_t stride);
 
 /* The sliding-window prefix-sum pass in the form the distance kernels consume: for G (<= 8) length groups at
  * once, per series row an fp64 prefix scan of xn and xn^2 in shared memory, then per window the fp32 norm term
- *   SQL2: st0 = ||x_w||^2      COSINE: st0 = 1/max(||x_w||,1e-8)      PEARSON: st0 = sum (x_w-mu)^2, st1 = mu
+ *   SQL2: st0 = ||x_w||^2      COSINE: st0 = 1/max(||x_w||,1e-8)      PEARSON: st0 = ||x_w-mu||, st1 = mu
  * L / stride are HOST arrays of G ints; st0_dev / st1_dev are HOST arrays of G device pointers, each
  * [B,M,ign_stats_pitch(T,L[g],stride[g])] (st1_dev may be NULL unless dist == PEARSON).
  * Reference: the norm / mean terms inside cosine_similarity, pearson_corrcoef and ShapeletDistanceFunc
@@ -127,10 +127,13 @@ int32_t ign_window_stats(const float* xn_dev, int32_t B, int32_t M, int32_t T, i
  *   dstore_dev  optional [B,M,K,Tw] (Tw = ign_padded_windows) all window distances, kept for backward
  *               (the soft-max statistics are recomputed from it); NULL in inference.
  * Engine: precision FP32 -> CUDA-core kernels; 3XTF32 / TF32 -> tcgen05 kernel (stride 1, T' <= 2048;
- * other geometries run on the FP32 engine). */
+ * other geometries run on the FP32 engine).  The tcgen05 engine needs ign_shapelet_forward_workspace(desc)
+ * bytes of 128-byte-aligned scratch (the pre-swizzled shifted-shapelet tiles); 0 bytes / NULL otherwise. */
+size_t ign_shapelet_forward_workspace(const ign_shapelet_desc* desc);
 int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,
                              const float* W_dev, const float* threshold_dev, float* p_dev, float* dmin_dev,
-                             int32_t* argmin_dev, float* dstore_dev, void* stream);
+                             int32_t* argmin_dev, float* dstore_dev, void* workspace_dev, size_t workspace_bytes,
+                             void* stream);
 
 /* bytes of scratch ign_shapelet_backward needs for this problem */
 size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* desc);

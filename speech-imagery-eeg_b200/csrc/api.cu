@@ -110,8 +110,16 @@ int32_t ign_window_stats(const float* xn, int32_t B, int32_t M, int32_t T, int32
   return launch_window_stats(xn, sg, B, M, T, dist, (cudaStream_t)stream);
 }
 
+size_t ign_shapelet_forward_workspace(const ign_shapelet_desc* d) {
+  if (check_desc(d, "shapelet_forward_workspace")) return 0;
+  if (d->precision != IGN_PREC_FP32 && d->precision != IGN_PREC_BF16 && shapelet_fwd_tc_supported(*d))
+    return shapelet_fwd_tc_workspace(*d);
+  return 0;
+}
+
 int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const float* st0, const float* W,
-                             const float* thr, float* p, float* dmin, int32_t* argmin, float* dstore, void* stream) {
+                             const float* thr, float* p, float* dmin, int32_t* argmin, float* dstore,
+                             void* ws, size_t ws_bytes, void* stream) {
   int rc = check_desc(d, "shapelet_forward");
   if (rc) return rc;
   IGN_REQUIRE(xn && W && p && dmin, "shapelet_forward: null pointer");
@@ -126,7 +134,7 @@ int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const 
   // tcgen05 engine for the cross-term distances; geometries it does not cover (stride > 1, more than 2048
   // windows per series) run on the exact-fp32 CUDA-core engine instead
   if (d->precision != IGN_PREC_FP32 && shapelet_fwd_tc_supported(*d))
-    return launch_shapelet_fwd_tc(*d, xn, st0, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
+    return launch_shapelet_fwd_tc(*d, xn, st0, W, thr, p, dmin, argmin, dstore, ws, ws_bytes, (cudaStream_t)stream);
   return launch_shapelet_fwd_simt(*d, xn, st0, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
 }
 
@@ -183,9 +191,10 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
   IGN_CUDA(cudaStreamCreate(&st));
   float *x = nullptr, *xn = nullptr, *W = nullptr, *out = nullptr;
   void* pre = nullptr;
+  void* fws = nullptr;
   const size_t nx = (size_t)B * T * M, nxn = (size_t)B * M * Tp, nf = (size_t)B * Kmax * M;
   auto cleanup = [&]() {
-    cudaFree(x); cudaFree(xn); cudaFree(W); cudaFree(out); cudaFree(pre);
+    cudaFree(x); cudaFree(xn); cudaFree(W); cudaFree(out); cudaFree(pre); cudaFree(fws);
     cudaStreamDestroy(st);
   };
 #define IGN_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return IGN_ERR_CUDA; } } while (0)
@@ -193,6 +202,13 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
   IGN_TRY(cudaMalloc(&xn, nxn * 4));
   IGN_TRY(cudaMalloc(&W, wmax * 4));
   IGN_TRY(cudaMalloc(&out, nf * 2 * 4));
+  size_t fws_bytes = 0;
+  for (int g = 0; g < G; ++g) {
+    ign_shapelet_desc dd{B, M, T, Tp, K[g], L[g], stride[g], eps, dist, IGN_POOL_RBF_MAX, precision};
+    const size_t nb = ign_shapelet_forward_workspace(&dd);
+    fws_bytes = nb > fws_bytes ? nb : fws_bytes;
+  }
+  if (fws_bytes) IGN_TRY(cudaMalloc(&fws, fws_bytes));
   size_t soff[kMaxStatGroups + 1] = {0};
   if (dist != IGN_DIST_L1) {
     for (int g = 0; g < G; ++g) soff[g + 1] = soff[g] + (size_t)B * M * stats_pitch(T, L[g], stride[g]);
@@ -212,7 +228,7 @@ int32_t ign_sbm_transform_host(const float* x_host, int32_t B, int32_t T, int32_
     ign_shapelet_desc d{B, M, T, Tp, K[g], L[g], stride[g], eps, dist, IGN_POOL_RBF_MAX, precision};
     const size_t n = (size_t)B * K[g] * M;
     IGN_TRY(cudaMemcpyAsync(W, W_host[g], (size_t)K[g] * M * L[g] * 4, cudaMemcpyHostToDevice, st));
-    rc = ign_shapelet_forward(&d, xn, pre ? sbase + soff[g] : nullptr, W, nullptr, out, out + nf, nullptr, nullptr, st);
+    rc = ign_shapelet_forward(&d, xn, pre ? sbase + soff[g] : nullptr, W, nullptr, out, out + nf, nullptr, nullptr, fws, fws_bytes, st);
     if (rc) break;
     hp.resize(n); hd.resize(n);
     IGN_TRY(cudaMemcpyAsync(hp.data(), out, n * 4, cudaMemcpyDeviceToHost, st));

@@ -58,9 +58,10 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
                              cudaStream_t st);
 int tc_profile_read(unsigned long long* host16, int reset);
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d);
+size_t shapelet_fwd_tc_workspace(const ign_shapelet_desc& d);
 int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const float* st0,
                            const float* W, const float* thr, float* p, float* dmin, int* argmin, float* dstore,
-                           cudaStream_t st);
+                           void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int B, int C, int use_gate,
                     float gv, cudaStream_t st);
 int launch_gate_bwd(const float* s, const float* z, const float* go, const float* ge, float* gs,

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) prefix_kernel(const float* __restrict__ x
 // Sliding-window statistics for all length groups in one pass: per series row an fp64 prefix scan of x and
 // x^2 in shared memory, then for every group g and window t the norm term its distance needs, as fp32:
 //   sql2    st0 = ||x_w||^2            cosine  st0 = 1/max(||x_w||,1e-8)
-//   pearson st0 = sum (x_w-mu)^2, st1 = mu
+//   pearson st0 = sqrt(sum (x_w-mu)^2), st1 = mu
 // Rows are written coalesced with pitch SP_g (windows rounded up to 16, pad = 0).  One warp per row.
 __global__ void __launch_bounds__(256) window_stats_kernel(const float* __restrict__ xn, const StatGroups G,
                                                            int rows, int T, int Tp, int dist) {
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) window_stats_kernel(const float* __restri
         else if (dist == IGN_DIST_COSINE) a = 1.f / fmaxf(sqrtf((float)sxx), 1e-8f);
         else {
           const double sx = P1[j0 + L] - P1[j0];
-          a = (float)fmax(sxx - sx * sx / (double)L, 0.0);
+          a = (float)sqrt(fmax(sxx - sx * sx / (double)L, 0.0));
           b = (float)(sx / (double)L);
         }
       }

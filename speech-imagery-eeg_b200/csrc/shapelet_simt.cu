@@ -111,7 +111,7 @@ __device__ void load_shapelets(const Geo& g, const float* __restrict__ W, int m,
         for (int l = lane; l < g.L; l += 32) { float w = __ldg(src + l) - mean; c2 = fmaf(w, w, c2); }
 #pragma unroll
         for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-        stat = c2;                                   // sum (w-mean)^2
+        stat = sqrtf(c2);                            // ||w-mean||
       } else if (g.dist == IGN_DIST_COSINE) {
         stat = 1.f / fmaxf(sqrtf(s2), 1e-8f);        // 1/max(||w||,eps)
       } else {
@@ -240,7 +240,7 @@ __device__ __forceinline__ float finish_distance(int dist, float raw, float invL
   if (OP == OP_L1) return raw * invL;
   if (dist == IGN_DIST_SQL2) return fmaxf((xstat + wstat - 2.f * raw) * invL, 0.f);
   if (dist == IGN_DIST_COSINE) return 1.f - raw * xstat * wstat;
-  return 1.f - __fdividef(raw, sqrtf(xstat * wstat) + 1e-8f);
+  return 1.f - __fdividef(raw, xstat * wstat + 1e-8f);   // xstat = ||x_w-mu||, wstat = ||w-mean|| (sqrt hoisted)
 }
 
 struct ArgVal { float v; int i; };
@@ -458,11 +458,11 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
           coef = c * a.st0[srow + t];
           sc0 = fmaf(c, 1.f - d, sc0);
         } else {
-          const float sxc = a.st0[srow + t], mu = a.st1[srow + t];
-          const float root = sqrtf(sxc * wst), D = root + 1e-8f;
+          const float sxn = a.st0[srow + t], mu = a.st1[srow + t];     // ||x_w-mu||, mu
+          const float D = sxn * wst + 1e-8f;                            // wst = ||w-mean||
           coef = __fdividef(c, D);
           sc0 = fmaf(coef, mu, sc0);
-          sc1 += __fdividef(c * (1.f - d) * sxc, root * D);
+          sc1 += __fdividef(c * (1.f - d) * sxn, wst * D);              // Sx/(root*D) = ||x||/(||w|| D)
         }
       }
     }
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   if (lane == 0) { a.rowsc[(size_t)row * 2] = sc0; a.rowsc[(size_t)row * 2 + 1] = sc1; }
 }
 
-// sum (w - mean)^2 per (k, m) shapelet row (pearson backward).  One warp per row.
+// ||w - mean|| per (k, m) shapelet row (pearson backward).  One warp per row.
 __global__ void __launch_bounds__(256) shapelet_centred_norm_kernel(const float* __restrict__ W,
                                                                    float* __restrict__ wstat, int rows, int L) {
   const int lane = threadIdx.x & 31;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) shapelet_centred_norm_kernel(const float*
   float c2 = 0.f;
   for (int l = lane; l < L; l += 32) { const float v = w[l] - mean; c2 = fmaf(v, v, c2); }
   c2 = warp_sum(c2);
-  if (lane == 0) wstat[row] = c2;
+  if (lane == 0) wstat[row] = sqrtf(c2);
 }
 
 // L1 only.  Exact ties x == w are impossible for a series row that shares no value with the shapelet block

@@ -44,7 +44,8 @@ _SIGNATURES = {
     "ign_stats_pitch": (c_int32, [c_int32, c_int32, c_int32]),
     "ign_window_stats": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), c_int32,
                                    POINTER(_P), POINTER(_P), _P]),
-    "ign_shapelet_forward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 9),
+    "ign_shapelet_forward_workspace": (c_size_t, [POINTER(ShapeletDesc)]),
+    "ign_shapelet_forward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 9 + [c_size_t, _P]),
     "ign_shapelet_backward_workspace": (c_size_t, [POINTER(ShapeletDesc)]),
     "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 10 + [c_size_t, _P]),
     "ign_gate_forward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P]),

@@ -213,10 +213,12 @@ class _ShapeletTransform(torch.autograd.Function):
         if need_grad:
             Tw = C.padded_windows(T, L, int(stride))
             dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
+        fws_bytes = int(C.lib.ign_shapelet_forward_workspace(byref(desc)))
+        fws = torch.empty((fws_bytes,), dtype=torch.uint8, device=dev) if fws_bytes else None
         with torch.cuda.device(dev):
-            C.check(STATS.call("shapelet_fwd/%s/L%d" % (dist, L), 1, lambda: C.lib.ign_shapelet_forward(
+            C.check(STATS.call("shapelet_fwd/%s/L%d" % (dist, L), 2 if fws_bytes else 1, lambda: C.lib.ign_shapelet_forward(
                 byref(desc), _ptr(xn), _ptr(st0), _ptr(Wc), _ptr(thr), _ptr(out[0]), _ptr(out[1]),
-                _ptr(idx), _ptr(dstore), _stream())), "ign_shapelet_forward")
+                _ptr(idx), _ptr(dstore), _ptr(fws), fws_bytes, _stream())), "ign_shapelet_forward")
         ctx.set_materialize_grads(False)
         ctx.desc = desc
         ctx.dist = dist

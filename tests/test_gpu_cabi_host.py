@@ -69,17 +69,17 @@ def test_instnorm_and_prefix_kernels():
         torch.testing.assert_close(c0[:, :, :Tw].double().cpu(), 1.0 / sxx.sqrt().clamp_min(1e-8), rtol=1e-6, atol=1e-7)
         q0, q1 = pack.window_stats("pearson", L, s)
         torch.testing.assert_close(q1[:, :, :Tw].double().cpu(), sx / L, rtol=1e-6, atol=1e-6)
-        torch.testing.assert_close(q0[:, :, :Tw].double().cpu(), (sxx - sx * sx / L).clamp_min(0), rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(q0[:, :, :Tw].double().cpu(), (sxx - sx * sx / L).clamp_min(0).sqrt(), rtol=1e-5, atol=1e-4)
 
 
 def test_bad_arguments_return_status_not_crash():
     from ctypes import byref
     from layers import ign_cabi as C
     d = C.ShapeletDesc(2, 3, 10, 12, 4, 11, 1, 1.0, 0, 0, 0)
-    rc = C.lib.ign_shapelet_forward(byref(d), *([None] * 9))
+    rc = C.lib.ign_shapelet_forward(byref(d), *([None] * 9), 0, None)
     assert rc == 1 and "T < L" in C.last_error()
     d = C.ShapeletDesc(2, 3, 16, 16, 4, 5, 1, 1.0, 2, 0, 0)
     x = torch.zeros(2, 3, 16, device="cuda")
     rc = C.lib.ign_shapelet_forward(byref(d), x.data_ptr(), None, x.data_ptr(), None, x.data_ptr(),
-                                    x.data_ptr(), None, None, None)
+                                    x.data_ptr(), None, None, None, 0, None)
     assert rc == 1 and "window statistics" in C.last_error()

@@ -11,7 +11,8 @@ from layers import ign_cabi as C  # noqa: E402
 from layers.shapelet_ops import instance_norm, shapelet_transform  # noqa: E402
 
 NAMES = ["prod wait empty", "prod build", "prod fence+arrive", "prod wait rows", "mma wait tempty", "mma wait full",
-         "mma issue+commit", "epi wait tfull", "epi drain+math", "epi reduce"]
+         "mma issue+commit", "epi wait tfull", "epi drain+math", "epi reduce", "setup: bars+alloc", "producer prologue",
+         "producer loop end", "epilogue end", "mma end", "CTA lifetime"]
 B, M, T, K = 256, 125, 1000, 5
 x = torch.randn(B, T, M, device="cuda")
 pack = instance_norm(x)
@@ -35,7 +36,13 @@ for dist in sys.argv[1].split(","):
             RB = 128 // RI
             ntiles = M * ((B + RB - 1) // RB)
             nstage = ntiles * ((L + 15 + 31) // 32)
+            nchunk = min(max(1, -(-4 * 148 // M)), -(-B // RB))
+            bpc = -(-(-(-B // nchunk)) // RB) * RB
+            nctas = M * (-(-B // bpc))
             print(f"{dist} {prec} L={L}: {e0.elapsed_time(e1):.3f} ms, tiles {ntiles}, stages {nstage}")
             for i, n in enumerate(NAMES):
+                if i >= 10:
+                    print(f"   {n:20s} {buf[i] / 1e6:9.2f} Mcyc total  {buf[i] / nctas:9.1f} cyc per CTA ({nctas} CTAs)")
+                    continue
                 per = buf[i] / (nstage if i in (0, 1, 2, 5, 6) else ntiles)
                 print(f"   {n:20s} {buf[i] / 1e6:9.2f} Mcyc total  {per:9.1f} cyc per {'stage' if i in (0, 1, 2, 5, 6) else 'tile'}")
