@@ -36,15 +36,16 @@ __global__ void __launch_bounds__(kNormThreads) instnorm_tile_kernel(const float
 
   // fill: each warp instruction reads TPW rows x CT channels (CT*4 contiguous bytes per row)
   const int rows_per_iter = kNormWarps * TPW;
-  for (int t0 = warp * TPW + dt; t0 < T; t0 += rows_per_iter * 4) {
-    float v[4];
+  constexpr int UN = 16;                                   // loads in flight per thread (fills the DRAM pipe)
+  for (int t0 = warp * TPW + dt; t0 < T; t0 += rows_per_iter * UN) {
+    float v[UN];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UN; ++u) {
       const int t = t0 + u * rows_per_iter;
       v[u] = (mv && t < T) ? __ldg(xb + (size_t)t * M) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UN; ++u) {
       const int t = t0 + u * rows_per_iter;
       if (t < T) tile[t * P + c] = v[u];
     }

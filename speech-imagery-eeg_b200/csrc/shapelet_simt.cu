@@ -243,6 +243,14 @@ __device__ __forceinline__ float finish_distance(int dist, float raw, float invL
   return 1.f - __fdividef(raw, xstat * wstat + 1e-8f);   // xstat = ||x_w-mu||, wstat = ||w-mean|| (sqrt hoisted)
 }
 
+// ex2.approx.ftz: 2 ulp, flushes denormals (p < 1e-38 -> 0); used only for backward soft-max weights
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 struct ArgVal { float v; int i; };
 __device__ __forceinline__ ArgVal warp_argmax_first(float v, int i) {
 #pragma unroll
@@ -408,15 +416,16 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   const size_t o = ((size_t)b * g.K + k) * g.M + m;
   const float gk = a.g[o];
   const float eps = g.eps, m2e2 = -2.f * eps * eps;
+  const float qscale = -eps * eps * kLog2e;              // p = exp(-(eps d)^2) = 2^(qscale d^2)
   float Zs = 0.f, S1s = 0.f, shift = 0.f;
   int ih;
   if (g.pool == IGN_POOL_RBF_MAX) {
     float pmx = -1.f; int imx = 0x7fffffff;
 #pragma unroll 4
     for (int t = lane; t < g.Tw; t += 32) {
-      const float ed = eps * dr[t];
-      const float p = __expf(-(ed * ed));
-      const float e = __expf(p);
+      const float d = dr[t];
+      const float p = fast_ex2(qscale * d * d);
+      const float e = fast_ex2(p * kLog2e);
       Zs += e; S1s = fmaf(e, p, S1s);
       if (p > pmx) { pmx = p; imx = t; }
     }
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
 #pragma unroll 4
     for (int t = lane; t < g.Tw; t += 32) {
       const float d = dr[t];
-      const float e = __expf(-(d - shift));
+      const float e = fast_ex2((shift - d) * kLog2e);
       Zs += e; S1s = fmaf(e, d, S1s);
     }
   }
@@ -436,19 +445,18 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   const size_t srow = (size_t)bm * a.SP;
   float* dst = a.coef + (size_t)row * g.Ts;
   float sc0 = 0.f, sc1 = 0.f;
-#pragma unroll 2
+#pragma unroll 4
   for (int t = lane; t < g.Ts; t += 32) {
     float coef = 0.f;
     if (t < g.Tw) {
       const float d = dr[t];
       float c;
       if (g.pool == IGN_POOL_RBF_MAX) {
-        const float ed = eps * d;
-        const float p = __expf(-(ed * ed));
-        const float soft = __expf(p) * invZ;
+        const float p = fast_ex2(qscale * d * d);
+        const float soft = fast_ex2(p * kLog2e) * invZ;
         c = gk * ((t == ih ? 1.f : 0.f) + soft * (p - bar)) * p * (m2e2 * d);
       } else {
-        const float soft = __expf(-(d - shift)) * invZ;
+        const float soft = fast_ex2((shift - d) * kLog2e) * invZ;
         c = gk * ((t == ih ? 1.f : 0.f) - soft * (d - bar));
       }
       if (g.dist == IGN_DIST_L1 || g.dist == IGN_DIST_SQL2) {
