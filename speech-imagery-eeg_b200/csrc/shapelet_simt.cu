@@ -45,13 +45,15 @@ namespace {
 constexpr int OP_L1 = 0;
 constexpr int OP_DOT = 1;
 constexpr int kMaxThreads = 256;
-constexpr int LT = 8;  // lags per thread in backward
+constexpr int LT = 8;   // lags per thread in backward (16 was measured slower: fewer items, lower occupancy)
 
 struct Geo {  // geometry shared by forward and backward
   int B, M, T, Tp, K, L, s;
   int Tw;      // number of windows
   int Ts;      // pitch of dstore rows (Tw rounded to 4)
   int DP;      // pitch of smem d/c rows (Tw rounded to 8)
+  int CP;      // backward: pitch of coefficient rows in smem, DP skewed to 12 mod 32 words (conflict-free
+               // LDS.128 when consecutive lanes read consecutive shapelets' rows)
   int XQ;      // pitch of one residue row of x in smem
   int LQ;      // pitch of one residue row of w in smem (ceil(L/s) rounded to 8)
   int KK, KB, nkb;
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   // unit stride: series and coefficient rows are double-buffered and prefetched with cp.async one pass ahead
   const bool dbuf = g.s == 1;
   const int xs_sz = g.NB * g.s * g.XQ;
-  const int cb_sz = max(g.NB * g.KB * g.DP, dbuf ? 0 : kMaxThreads * LT);
+  const int cb_sz = max(g.NB * g.KB * g.CP, dbuf ? 0 : kMaxThreads * LT);
   float* xs0 = smem;
   float* cb0 = xs0 + (dbuf ? 2 : 1) * xs_sz;
   float* ws = cb0 + max((dbuf ? 2 : 1) * cb_sz, kMaxThreads * LT);
@@ -584,9 +586,9 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   const bool active = threadIdx.x < nitem;
   int lt = 0, kl = 0, seg = 0, bl = 0;
   if (active) {
-    int it = threadIdx.x;
-    lt = it % ntl; it /= ntl;
+    int it = threadIdx.x;          // shapelet index fastest: neighbouring lanes share the x address (broadcast)
     kl = it % g.KB; it /= g.KB;
+    lt = it % ntl; it /= ntl;
     seg = it % a.nseg; bl = it / a.nseg;
   }
   const int ltg = lt_beg + lt;
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     for (int i = threadIdx.x; i < nb * kvalid * crow; i += nthr) {
       const int row = i / crow, c = i - row * crow;
       const int rbl = row / kvalid, rkl = row - rbl * kvalid;
-      cp_async16(cd + ((size_t)rbl * g.KB + rkl) * g.DP + c * 4,
+      cp_async16(cd + ((size_t)rbl * g.KB + rkl) * g.CP + c * 4,
                  a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c * 4);
     }
   };
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rbl < nb && k0 + rkl < g.K && c4 < g.Ts)
           v = *reinterpret_cast<const float4*>(a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c4);
-        *reinterpret_cast<float4*>(cb0 + (size_t)row * g.DP + c4) = v;
+        *reinterpret_cast<float4*>(cb0 + (size_t)row * g.CP + c4) = v;
       }
       __syncthreads();
     }
@@ -650,27 +652,28 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     // ---- contraction over windows, sliding along t with a 12-register ring of x
     if (active && bl < nb && ta < tb && k0 + kl < g.K) {
       const float* xr = xs + ((size_t)bl * g.s + r) * g.XQ + q0;
-      const float* cb = cbuf + ((size_t)bl * g.KB + kl) * g.DP;
+      const float* cb = cbuf + ((size_t)bl * g.KB + kl) * g.CP;
       const bool exact = OP == OP_L1 && (a.tie == nullptr || a.tie[((size_t)(b0 + bl) * g.M + m) * g.nkb + kblk] != 0);
-      float xv[12];
-      {
-        float4 v0 = *reinterpret_cast<const float4*>(xr + ta);
-        float4 v1 = *reinterpret_cast<const float4*>(xr + ta + 4);
-        xv[0] = v0.x; xv[1] = v0.y; xv[2] = v0.z; xv[3] = v0.w;
-        xv[4] = v1.x; xv[5] = v1.y; xv[6] = v1.z; xv[7] = v1.w;
+      constexpr int RING = LT + 4;      // 12: three 4-window steps per ring revolution
+      static_assert(LT == 8, "the sweep below unrolls RING/4 == 3 steps");
+      float xv[RING];
+#pragma unroll
+      for (int i = 0; i < LT; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + ta + i);
+        xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
       }
 #define IGN_BWD_STEP(EX, BASE, TQ)                                                           \
       {                                                                                      \
-        float4 nx = *reinterpret_cast<const float4*>(xr + (TQ) + 8);                         \
-        xv[((BASE) + 8) % 12] = nx.x; xv[((BASE) + 9) % 12] = nx.y;                          \
-        xv[((BASE) + 10) % 12] = nx.z; xv[((BASE) + 11) % 12] = nx.w;                        \
+        float4 nx = *reinterpret_cast<const float4*>(xr + (TQ) + LT);                        \
+        xv[((BASE) + LT) % RING] = nx.x; xv[((BASE) + LT + 1) % RING] = nx.y;                \
+        xv[((BASE) + LT + 2) % RING] = nx.z; xv[((BASE) + LT + 3) % RING] = nx.w;            \
         const float4 c4 = *reinterpret_cast<const float4*>(cb + (TQ));                       \
         const float4 h4 = make_float4(0.5f * c4.x, 0.5f * c4.y, 0.5f * c4.z, 0.5f * c4.w);   \
         _Pragma("unroll") for (int i = 0; i < LT; ++i) {                                     \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.x, h4.x, xv[((BASE) + i + 0) % 12], wreg[i]);   \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.y, h4.y, xv[((BASE) + i + 1) % 12], wreg[i]);   \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.z, h4.z, xv[((BASE) + i + 2) % 12], wreg[i]);   \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.w, h4.w, xv[((BASE) + i + 3) % 12], wreg[i]);   \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.x, h4.x, xv[((BASE) + i + 0) % RING], wreg[i]); \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.y, h4.y, xv[((BASE) + i + 1) % RING], wreg[i]); \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.z, h4.z, xv[((BASE) + i + 2) % RING], wreg[i]); \
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.w, h4.w, xv[((BASE) + i + 3) % RING], wreg[i]); \
         }                                                                                    \
       }
 #define IGN_BWD_SWEEP(EX)                                                                    \
@@ -679,10 +682,8 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
         for (; t + 12 <= tb; t += 12) {                                                      \
           IGN_BWD_STEP(EX, 0, t) IGN_BWD_STEP(EX, 4, t + 4) IGN_BWD_STEP(EX, 8, t + 8)       \
         }                                                                                    \
-        if (t + 4 <= tb) {                                                                   \
-          IGN_BWD_STEP(EX, 0, t) t += 4;                                                     \
-          if (t + 4 <= tb) { IGN_BWD_STEP(EX, 4, t) t += 4; }                                \
-        }                                                                                    \
+        if (t + 4 <= tb) { IGN_BWD_STEP(EX, 0, t) t += 4;                                    \
+          if (t + 4 <= tb) { IGN_BWD_STEP(EX, 4, t) t += 4; } }                              \
       }
       if (exact) IGN_BWD_SWEEP(true) else IGN_BWD_SWEEP(false)
 #undef IGN_BWD_SWEEP
@@ -771,9 +772,10 @@ bool base_geo(const ign_shapelet_desc& d, Geo& g) {
   g.Tw = num_windows(d.T, d.L, d.stride);
   g.Ts = round_up(g.Tw, 4);
   g.DP = round_up(g.Tw, 8);
+  g.CP = g.DP + ((12 - g.DP % 32) + 32) % 32;
   const int Lq = ceil_div(d.L, d.stride);
   g.LQ = round_up(Lq, 8);
-  g.XQ = round_up(max(g.DP + g.LQ + 8, ceil_div(d.T, d.stride) + 8), 4);
+  g.XQ = round_up(max(g.DP + g.LQ + 8, ceil_div(d.T, d.stride) + 8), 4);   // covers t + LT + 3 + q0 < DP + LQ
   g.KK = pick_kk(d.K);
   g.dist = d.dist; g.pool = d.pool; g.eps = d.eps;
   return g.Tw > 0;
@@ -830,7 +832,7 @@ int bwd_hash_cap(const Geo& g, int KB) {
 
 size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
   const size_t mult = g.s == 1 ? 2 : 1;       // double-buffered for unit stride
-  const size_t xs = (size_t)NB * g.s * g.XQ, cb = (size_t)NB * KB * g.DP;
+  const size_t xs = (size_t)NB * g.s * g.XQ, cb = (size_t)NB * KB * g.CP;
   size_t cbt = mult * cb;
   if (cbt < (size_t)kMaxThreads * LT) cbt = (size_t)kMaxThreads * LT;
   return mult * xs + cbt + (size_t)KB * g.s * g.LQ + KB;
