@@ -378,7 +378,9 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
 // L1 backward accumulates A[l] = sum_t c_t ([x>w] + 0.5 [x==w]); the finalize kernel forms
 // sum_t c_t sign(x-w) = 2 A[l] - sum_t c_t  (sign(0) = 0 exactly, as torch's abs backward).
 // Exact ties x == w are impossible for a series row that shares no value with the CTA's shapelets; that is
-// checked per row against a hash set of the shapelet values, and such rows take the 2-instruction path.
+// decided per row by tie_check_kernel, and such rows take the 2-instruction path (FSETP + predicated FADD).
+// (An FFMA.SAT-built indicator on the FMA pipe was measured at the same speed — both forms are issue-bound at
+//  two instructions per element — and is inexact for |x-w| < 2^-60, so the compare form is kept.)
 template <int OP, bool EXACT>
 __device__ __forceinline__ float bwd_op(float acc, float c, float hc, float x, float w) {
   if (OP == OP_L1) {
@@ -390,6 +392,8 @@ __device__ __forceinline__ float bwd_op(float acc, float c, float hc, float x, f
 }
 
 constexpr unsigned kHashEmpty = 0x7fc00001u;   // a NaN payload: never equal to a series value
+constexpr int kTieBitmapLog2 = 19;             // 2^19-bit (64 KB) filter in front of the exact hash set
+constexpr int kTieBitmapWords = (1 << kTieBitmapLog2) / 32;
 __device__ __forceinline__ unsigned hash_key(float v) {
   unsigned b = __float_as_uint(v);
   return b == 0x80000000u ? 0u : b;            // -0 == +0
@@ -504,17 +508,21 @@ __global__ void __launch_bounds__(256) shapelet_centred_norm_kernel(const float*
 __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict__ xn, const float* __restrict__ W,
                                                         unsigned char* __restrict__ tie, int B, int M, int T, int Tp,
                                                         int K, int L, int KB, int nkb, int hcap, int bsplit) {
-  extern __shared__ unsigned hset[];
+  extern __shared__ unsigned hset[];                       // [hcap] exact set, then [kTieBitmapWords] bitmap filter
+  unsigned* bitmap = hset + hcap;
   const int m = blockIdx.x, kblk = blockIdx.y;
   const int k0 = kblk * KB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int i = threadIdx.x; i < hcap; i += blockDim.x) hset[i] = kHashEmpty;
+  for (int i = threadIdx.x; i < kTieBitmapWords; i += blockDim.x) bitmap[i] = 0u;
   __syncthreads();
   const unsigned mask = hcap - 1;
   for (int i = threadIdx.x; i < KB * L; i += blockDim.x) {
     const int hk = i / L, l = i - hk * L;
     if (k0 + hk >= K) continue;
     const unsigned key = hash_key(__ldg(W + ((size_t)(k0 + hk) * M + m) * L + l));
+    const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2);
+    atomicOr(&bitmap[hb >> 5], 1u << (hb & 31));
     unsigned h = hash_slot(key, mask);
     while (true) {
       const unsigned old = atomicCAS(&hset[h], kHashEmpty, key);
@@ -526,16 +534,24 @@ __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict_
   const int per = ceil_div(B, bsplit);
   const int bbeg = blockIdx.z * per, bend = min(B, bbeg + per);
   for (int b = bbeg + warp; b < bend; b += nwarp) {
-    const float* xr = xn + ((size_t)b * M + m) * Tp;
-    int hit = 0;
-    for (int t = lane; t < T; t += 32) {
-      const unsigned key = hash_key(__ldg(xr + t));
-      unsigned h = hash_slot(key, mask);
-      while (true) {
-        const unsigned v = hset[h];
-        if (v == key) { hit = 1; break; }
-        if (v == kHashEmpty) break;
-        h = (h + 1) & mask;
+    const float4* xr = reinterpret_cast<const float4*>(xn + ((size_t)b * M + m) * Tp);   // pad samples are 0: a
+    int hit = 0;                                                                          // spurious hit is harmless
+    for (int t4 = lane; t4 < Tp / 4; t4 += 32) {
+      const float4 v = __ldg(xr + t4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned key = hash_key(vv[e]);
+        const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2);
+        if ((bitmap[hb >> 5] >> (hb & 31)) & 1u) {          // rare: confirm in the exact set
+          unsigned h = hash_slot(key, mask);
+          while (true) {
+            const unsigned q = hset[h];
+            if (q == key) { hit = 1; break; }
+            if (q == kHashEmpty) break;
+            h = (h + 1) & mask;
+          }
+        }
       }
     }
     hit = __any_sync(0xffffffffu, hit);
@@ -825,9 +841,9 @@ struct BwdPlan { int nseg, nlb, tlb, nchunk, threads, hcap; size_t smem_bytes; }
 
 int bwd_hash_cap(const Geo& g, int KB) {
   if (g.dist != IGN_DIST_L1) return 0;
-  size_t need = 2 * (size_t)KB * g.L, cap = 256;
+  size_t need = 4 * (size_t)KB * g.L, cap = 256;
   while (cap < need) cap <<= 1;
-  return cap <= 32768 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path
+  return cap <= 32768 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path (128 KB + 64 KB smem)
 }
 
 size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
@@ -973,7 +989,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   if (d.dist == IGN_DIST_L1 && bp.hcap) {
     unsigned char* tflags = reinterpret_cast<unsigned char*>(base + wo.tie);
     const int bsplit = max(1, min(d.B, ceil_div(4 * sm_count(), d.M * g.nkb)));
-    const size_t hs = (size_t)bp.hcap * sizeof(unsigned);
+    const size_t hs = ((size_t)bp.hcap + kTieBitmapWords) * sizeof(unsigned);
     int rc0 = set_smem(tie_check_kernel, hs);
     if (rc0) return rc0;
     tie_check_kernel<<<dim3(d.M, g.nkb, bsplit), 256, hs, st>>>(xn, W, tflags, d.B, d.M, d.T, d.Tp, d.K, d.L, g.KB,
