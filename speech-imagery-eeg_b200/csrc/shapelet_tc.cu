@@ -157,6 +157,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a fully converged warp.  Code under this predicate is provably single-threaded, so ptxas emits
+// the uniform-datapath instructions (UTCHMMA, UTCBAR, UBLKCP) straight-line; under `lane == 0` it wraps every
+// one of them in an ELECT / BRA.U.ANY loop, measured at 64 cycles per MMA issue against a 40-cycle dispatch
+// floor (profiles/r1d_ubench_umma_dispatch.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -485,8 +495,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       if (e == 0) TC_ADD(9, te0);
     }
   } else {
-    // =================================================================== MMA ISSUER (one thread)
-    if (lane == 0) {
+    // =================================================================== MMA ISSUER (one elected thread)
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_tf32(kRows, g.N);
       uint32_t it = 0;
       for (int tile = 0; tile < ntile; ++tile) {
