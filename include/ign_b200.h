@@ -76,6 +76,8 @@ int32_t ign_device_check(int32_t device);
 
 /* debug: role-level cycle counters of the tcgen05 kernel (only in builds with -DIGN_TC_PROFILE) */
 int32_t ign_debug_tc_profile(uint64_t* host16, int32_t reset);
+/* debug: clock64() event trace of CTA 0 of the last tcgen05 launch, [12 roles][32 tiles][4 events] (same builds) */
+int32_t ign_debug_tc_trace(int64_t* host, int32_t n);
 
 /* pitch (floats) of one normalised series row: T rounded up to a multiple of 4 (16-byte rows) */
 int32_t ign_padded_len(int32_t T);
@@ -101,12 +103,14 @@ int32_t ign_prefix_pitch(int32_t T);
 int32_t ign_window_prefix(const float* xn_dev, double* pre1_dev, double* pre2_dev,
                           int32_t B, int32_t M, int32_t T, void* stream);
 
-/* pitch (floats) of one window-statistics row: T' rounded up to a multiple of 16 (zero padded) */
+/* pitch (floats) of one window-statistics row: T' rounded up to a multiple of 16 */
 int32_t ign_stats_pitch(int32_t T, int32_t L, int32_t stride);
 
 /* The sliding-window prefix-sum pass in the form the distance kernels consume: for G (<= 8) length groups at
  * once, per series row an fp64 prefix scan of xn and xn^2 in shared memory, then per window the fp32 norm term
  *   SQL2: st0 = ||x_w||^2      COSINE: st0 = 1/max(||x_w||,1e-8)      PEARSON: st0 = ||x_w-mu||, st1 = mu
+ * The pad slots t >= T' of st0 hold an ignore marker (+inf for SQL2, NaN for COSINE / PEARSON: the resulting
+ * distance is +inf / NaN and never wins the min over time); st1 pads are 0.
  * L / stride are HOST arrays of G ints; st0_dev / st1_dev are HOST arrays of G device pointers, each
  * [B,M,ign_stats_pitch(T,L[g],stride[g])] (st1_dev may be NULL unless dist == PEARSON).
  * Reference: the norm / mean terms inside cosine_similarity, pearson_corrcoef and ShapeletDistanceFunc

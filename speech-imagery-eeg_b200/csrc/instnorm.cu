@@ -258,8 +258,12 @@ __global__ void __launch_bounds__(256) window_stats_kernel(const float* __restri
     const int L = G.L[gi], st = G.s[gi], Tw = G.Tw[gi], SP = G.SP[gi];
     float* o0 = G.st0[gi] + (size_t)row * SP;
     float* o1 = need1 ? G.st1[gi] + (size_t)row * SP : nullptr;
+    // Pad windows (t >= Tw) carry an "ignore me" marker instead of a norm term, so that the distance kernels need
+    // no per-window validity logic: +inf for SQL2 (distance +inf), NaN for COSINE / PEARSON (distance NaN, which
+    // the min reductions — FMNMX returns the non-NaN operand — skip).
+    const float pad = dist == IGN_DIST_SQL2 ? INFINITY : __int_as_float(0x7fc00000);
     for (int t = lane; t < SP; t += 32) {
-      float a = 0.f, b = 0.f;
+      float a = pad, b = 0.f;
       if (t < Tw) {
         const int j0 = t * st;
         const double sxx = P2[j0 + L] - P2[j0];

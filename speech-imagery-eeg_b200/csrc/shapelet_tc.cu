@@ -12,8 +12,8 @@
 //  * the overlapping rows are never materialised in HBM, L2 or even shared memory: each producer thread owns
 //    one accumulator row, reads its 32-sample segment of the raw series row (bank-skewed layout, conflict-free
 //    LDS.128) and writes it straight into TENSOR MEMORY with tcgen05.st; the MMA takes A from TMEM
-//    (tcgen05.mma [d], [a_tmem], b_desc).  Shared-memory bandwidth — the limit of an smem-A design at N = 80,
-//    measured at ~1220 cycles per k-block against 480 MMA cycles — is left to the B tiles alone.
+//    (tcgen05.mma [d], [a_tmem], b_desc), which dispatches at the 128*N/256-cycle floor (40 cycles for N = 80,
+//    profiles/r1d_ubench_umma_dispatch.txt; A from shared memory costs 52).
 //
 // Precision: tcgen05 has no fp32 kind.  kind::tf32 reads fp32 bits and drops the low 13 mantissa bits, so
 // the "hi" operand is the raw fp32 value and lo = x - trunc_tf32(x) is formed by the producers.
@@ -21,16 +21,32 @@
 //   IGN_PREC_TF32  : hi*hi only             (own, looser tolerance)
 //
 //  * the shifted-shapelet operand depends only on (channel, k-block): a small pre-pass writes it to a workspace
-//    already in the 128B-swizzled K-major tile image (hi | lo), and the main kernel streams one tile per
-//    stage with a single 1-D bulk TMA copy (cp.async.bulk + mbarrier complete_tx) — no producer instructions.
+//    already in the 128B-swizzled K-major tile image (hi | lo), and a dedicated warp streams one tile per
+//    stage with a single 1-D bulk TMA copy (cp.async.bulk + mbarrier complete_tx).
+//
+// Persistent kernel: one CTA per SM walks a contiguous range of the (channel, shapelet block, sample tile) list,
+// so there is no wave-quantisation tail and the TMEM allocation, barriers and the pipeline state live for the
+// whole launch.
 // TMEM map (512 columns): accumulators at 0 and 128 (double buffered), A stages at 256 + 64 s (hi 32 | lo 32).
-// Roles (one CTA per SM, 288 threads):
-//   warps 0-3  producers: cp.async the next series rows, tcgen05.st the A stage, arrive on full[stage];
-//              thread 0 also arms full[stage] with the byte count and issues the bulk TMA copy of the B tile
-//   warps 4-7  epilogue : tcgen05.ld the accumulator (TMEM lanes 32*(w%4)..), cross -> distance with the
-//                         prefix-sum window norms, coalesced store of d, per-row arg-min candidates
-//   warp  8    one elected thread issues tcgen05.mma (M=128, N=16*KG, K=8) and tcgen05.commit
-// Pipelines: smem full/empty per stage (producers <-> MMA), TMEM full/empty per accumulator (MMA <-> epilogue).
+// Two rings: A stages in tensor memory (4), B stages in shared memory (as deep as fits: the bulk-copy latency of a
+// 20 KB tile is ~2000 cycles against 480 MMA cycles per stage); when the ring holds every k-block of a (channel,
+// shapelet block) run the B tiles are loaded once per run and stay resident.
+// Roles (608 threads):
+//   warps 0-7   producers: tcgen05.st the A stage (hi = raw fp32, lo = x - trunc_tf32(x)), arrive on fullA[stage].
+//               Warp w owns TMEM lanes 32 (w%4)..; the two warps of a lane quarter take alternate stages, so the
+//               LDS -> split -> tcgen05.st -> wait latency of one stage hides under the other warp's stage.
+//   warps 8-15  epilogue : tcgen05.ld the accumulator (two warps per lane quarter, alternate shapelets), cross ->
+//               distance with the window norm terms, coalesced store of d, per-row minimum; the arg-min of a
+//               (sample, shapelet) pair is formed with redux.sync inside the warp and published as one packed
+//               64-bit word (ordered distance | window index: first index wins ties) to the warp's own cell — no
+//               atomics; one rotating warp per tile merges the four lane-quarter cells and writes p / d_min /
+//               arg-min, the other seven only bar.arrive and move on.
+//   warp 16     one elected thread issues tcgen05.mma (M=128, N=16*KG, K=8) and tcgen05.commit
+//   warp 17     one elected thread streams the B tiles (bulk TMA)
+//   warp 18     loads the next tiles' series rows (cp.async into the bank-skewed layout) and hands them to the
+//               producers through mbarriers — the producers never meet a CTA-wide barrier
+// Pipelines: fullA/emptyA (producers <-> MMA), fullB/emptyB (TMA <-> MMA), TMEM full/empty per accumulator
+// (MMA <-> epilogue).
 #include "ign_common.cuh"
 
 #include <math.h>
@@ -41,13 +57,18 @@ namespace {
 constexpr int kShifts = 16;            // P
 constexpr int kRows = 128;             // UMMA M
 constexpr int kKBlock = 32;            // fp32 elements per 128-byte swizzle row
-constexpr int kProducerThreads = 128;
-constexpr int kEpilogueThreads = 128;
-constexpr int kThreadsTC = kProducerThreads + kEpilogueThreads + 32;
-constexpr int kWshPad = 16;            // zero floats left of each shifted shapelet row
-constexpr int kMaxStages = 4;
+constexpr int kProdWarps = 8, kEpiWarps = 8;
+constexpr int kProducerThreads = kProdWarps * 32;
+constexpr int kEpilogueThreads = kEpiWarps * 32;
+constexpr int kMmaWarp = kProdWarps + kEpiWarps, kTmaWarp = kMmaWarp + 1, kRowWarp = kMmaWarp + 2;
+constexpr int kThreadsTC = (kRowWarp + 1) * 32;
+constexpr int kAStages = 4;            // A ring (tensor memory)
+constexpr int kMaxBStages = 12;        // B ring (shared memory): as deep as fits, resident when it holds all k-blocks
 constexpr int kAccCols = 128;          // TMEM columns reserved per accumulator (N <= 128)
 constexpr int kAStageCols = 64;        // TMEM columns per A stage: 32 hi + 32 lo
+constexpr int kMaxAcc = 4;             // accumulators in flight (2, or 3-4 when N is small and the tiles are short)
+constexpr int kMaxRB = 8;              // samples per tile (bounds the arg-min cell arrays)
+constexpr unsigned long long kSlotEmpty = 0xffffffffffffffffull;
 
 struct TcGeo {
   int B, M, T, Tp, K, L;
@@ -57,17 +78,21 @@ struct TcGeo {
   int N;               // 16*KG
   int NKB;             // 32-wide k-blocks: ceil((L+15)/32)
   int XR;              // floats per series row in smem
-  int nstage;
-  int bpc;             // samples per CTA chunk
+  int nacc, accp;      // accumulators in flight and their TMEM column pitch
+  int ncb;             // arg-min cell generations / finaliser barrier ids in flight: a power of two >= nacc + 2
+  int nbs, resident;   // B ring depth; 1 = the ring holds every k-block of a (channel, shapelet block) run
+  int tpm;             // sample tiles per (channel, shapelet block): ceil(B / RB)
+  int ntiles;          // M * nkb * tpm
   int dist, pool, split;
   float eps;
 };
 
 struct TcArgs {
-  const float* xn; const float* st0; const float* W; const float* thr;   // st0: window statistics [B,M,SP]
+  const float* xn; const float* st0; const float* thr;   // st0: window statistics [B,M,SP]
   float* p; float* dmin; int* argmin; float* dstore;
   int SP;
   const uint8_t* btiles;   // [M][nkb][NKB][stage_bytes] pre-swizzled B stage images
+  const float* wstat;      // [M][nkb][8] shapelet statistic of the distance mode (pre-pass)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -80,18 +105,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the waiting thread is parked by the hardware (woken when the phase
+  // completes) instead of polling — with 18 warps per SM the polling loops otherwise eat the issue slots of the
+  // warps doing the work (measured: 73 M polling instructions per launch in the producer loop alone).
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   unsigned spins = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(200000u)
         : "memory");
-    if (!done && ++spins > (1u << 24)) __trap();   // a pipeline bug must fail fast, never hang the GPU
+    if (!done && ++spins > (1u << 14)) __trap();   // a pipeline bug must fail fast, never hang the GPU
   }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -203,7 +231,11 @@ __device__ unsigned long long g_tc_prof[16];
 #define TC_ADD(slot, t0) (tc_prof_local[slot] += (unsigned long long)(clock64() - (t0)))   // flushed once at CTA end
 #define TC_DECL() unsigned long long tc_prof_local[16] = {0}
 #define TC_FLUSH() do { for (int i_ = 0; i_ < 16; ++i_) if (tc_prof_local[i_]) atomicAdd(&g_tc_prof[i_], tc_prof_local[i_]); } while (0)
+// event trace of CTA 0: [role lane 0..11][local tile 0..31][slot 0..3] = clock64()
+__device__ long long g_tc_trace[12 * 32 * 4];
+#define TC_TRACE(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 32) g_tc_trace[((role) * 32 + (tile)) * 4 + (slot)] = clock64(); } while (0)
 #else
+#define TC_TRACE(role, tile, slot) ((void)0)
 #define TC_CLK() 0ll
 #define TC_ADD(slot, t0) ((void)(t0))
 #define TC_DECL() ((void)0)
@@ -215,24 +247,41 @@ __device__ unsigned long long g_tc_prof[16];
 // (shapelet u, shift j), 32 fp32 columns, 128-byte rows, 16-byte chunks XOR-swizzled with (n & 7); the hi image
 // (raw fp32, truncated to tf32 by the tensor core) is followed by the lo image when the 3xTF32 split is on.
 //   B[n][c] = w'[u][32 kb + c - j]   (0 outside the shapelet; w' = w - mean for pearson)
-__global__ void __launch_bounds__(128) tc_build_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int M,
-                                                         int K, int L, int KG, int nkb, int NKB, int N, int split,
-                                                         int centre) {
+// The kb == 0 CTAs also write the per-shapelet statistic the epilogue needs (same arithmetic as the FP32 engine):
+//   SQL2 ||w||^2, COSINE 1/max(||w||,1e-8), PEARSON ||w-mean||.
+__global__ void __launch_bounds__(128) tc_build_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ out,
+                                                         float* __restrict__ wstat, int M, int K, int L, int KG,
+                                                         int nkb, int NKB, int N, int split, int dist) {
   __shared__ float s_mean[16];
   const int m = blockIdx.x, kblk = blockIdx.y, kb = blockIdx.z;
   const int k0 = kblk * KG;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool centre = dist == IGN_DIST_PEARSON;
   for (int u = warp; u < KG; u += 4) {
-    float mean = 0.f;
-    if (centre && k0 + u < K) {
+    float mean = 0.f, stat = 0.f;
+    if (k0 + u < K && (centre || kb == 0)) {
       const float* src = W + ((size_t)(k0 + u) * M + m) * L;
-      float s1 = 0.f;
-      for (int l = lane; l < L; l += 32) s1 += __ldg(src + l);
+      float s1 = 0.f, s2 = 0.f;
+      for (int l = lane; l < L; l += 32) { const float w = __ldg(src + l); s1 += w; s2 = fmaf(w, w, s2); }
 #pragma unroll
-      for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      mean = s1 / (float)L;
+      for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      if (centre) {
+        mean = s1 / (float)L;
+        float c2 = 0.f;
+        for (int l = lane; l < L; l += 32) { const float w = __ldg(src + l) - mean; c2 = fmaf(w, w, c2); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        stat = sqrtf(c2);
+      } else if (dist == IGN_DIST_COSINE) {
+        stat = 1.f / fmaxf(sqrtf(s2), 1e-8f);
+      } else {
+        stat = s2;
+      }
     }
-    if (lane == 0) s_mean[u] = mean;
+    if (lane == 0) {
+      s_mean[u] = mean;
+      if (kb == 0) wstat[((size_t)m * nkb + kblk) * 8 + u] = stat;
+    }
   }
   __syncthreads();
   const int b_bytes = N * 128;
@@ -253,169 +302,221 @@ __global__ void __launch_bounds__(128) tc_build_b_kernel(const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------- kernel helpers
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// order-preserving map float -> uint32 (smaller float <=> smaller key), total for all non-NaN values
+__device__ __forceinline__ uint32_t ordered_key(float d) {
+  const uint32_t u = __float_as_uint(d);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_val(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct TileCoord { int m, kblk, b0; };
+__device__ __forceinline__ TileCoord tile_coord(const TcGeo& g, int w) {
+  TileCoord c;
+  const int mk = w / g.tpm;
+  c.b0 = (w - mk * g.tpm) * g.RB;
+  c.m = mk / g.nkb;
+  c.kblk = mk - c.m * g.nkb;
+  return c;
+}
+
 // ---------------------------------------------------------------- kernel
+// Which (tile, k-block) steps load / wait for / release a B stage.  Resident mode: stage = k-block, loaded on the
+// first tile of a (channel, shapelet block) run and released on its last; streaming mode: a plain ring.
+struct RunFlags { bool first, last; };
+__device__ __forceinline__ RunFlags run_flags(const TcGeo& g, int w, int wbeg, int wend) {
+  const int mk = w / g.tpm;
+  RunFlags f;
+  f.first = (w == wbeg) || ((w - 1) / g.tpm != mk);
+  f.last = (w == wend - 1) || ((w + 1) / g.tpm != mk);
+  return f;
+}
+
+// Merge the four lane-quarter cells of every (sample, shapelet) pair of tile `w` (local index n) and write the pooled
+// outputs.  Executed by one warp, after all eight epilogue warps have published the tile (named barrier).
+__device__ __forceinline__ void finalize_tile(const TcGeo& g, const TcArgs& a, const unsigned long long* cells,
+                                              const float* celld, int n, int w, int lane) {
+  bar_sync(2 + (n & (g.ncb - 1)), kEpilogueThreads);
+  const TileCoord tc = tile_coord(g, w);
+  const int npair = g.RB * g.KG;
+  const int nb = min(g.RB, g.B - tc.b0);
+  const unsigned long long* cbuf = cells + (size_t)(n & (g.ncb - 1)) * 4 * npair;
+  const float* dbuf = celld + (size_t)(n & (g.ncb - 1)) * 4 * npair * 16;
+  for (int pair = lane; pair < npair; pair += 32) {
+    const int rbl = pair / g.KG, kl = pair - rbl * g.KG;
+    const int k = tc.kblk * g.KG + kl;
+    if (rbl >= nb || k >= g.K) continue;
+    unsigned long long pk = cbuf[pair];
+    int qw = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {        // (ordered min | first window of the row): the earlier row wins ties
+      const unsigned long long o = cbuf[q * npair + pair];
+      if (o < pk) { pk = o; qw = q; }
+    }
+    const float dmn = ordered_val((uint32_t)(pk >> 32));
+    const float4* dc = reinterpret_cast<const float4*>(dbuf + (size_t)(qw * npair + pair) * 16);
+    int jj = 15;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      const float4 d4 = dc[j];
+      if (d4.w == dmn) jj = 4 * j + 3;
+      if (d4.z == dmn) jj = 4 * j + 2;
+      if (d4.y == dmn) jj = 4 * j + 1;
+      if (d4.x == dmn) jj = 4 * j;
+    }
+    const int imn = (int)(uint32_t)pk + jj;
+    const size_t o = ((size_t)(tc.b0 + rbl) * g.K + k) * g.M + tc.m;
+    float pv;
+    if (g.pool == IGN_POOL_RBF_MAX) { const float ed = g.eps * dmn; pv = expf(-(ed * ed)); }
+    else pv = 1.f / (1.f + expf(-(a.thr[(size_t)k * g.M + tc.m] - dmn)));
+    a.p[o] = pv; a.dmin[o] = dmn;
+    if (a.argmin) a.argmin[o] = imn;
+  }
+}
+
+template <int DIST>
 __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const TcGeo g, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const long long t_entry = TC_CLK();
   TC_DECL();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x, k0 = blockIdx.y * g.KG;
-  const int bbeg = blockIdx.z * g.bpc, bend = min(g.B, bbeg + g.bpc);
-  const int ntile = (bend - bbeg + g.RB - 1) / g.RB;
+  // this CTA's contiguous tile range (balanced to within one tile)
+  const int wbeg = (int)(((long long)g.ntiles * blockIdx.x) / gridDim.x);
+  const int wend = (int)(((long long)g.ntiles * (blockIdx.x + 1)) / gridDim.x);
 
   // ---- shared memory carve-up (stage tiles first: they need 1024-byte alignment) ----
   const int b_bytes = g.N * 128;
   const int stage_bytes = b_bytes * (g.split ? 2 : 1);
   uint8_t* stage0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* ptr = stage0 + (size_t)g.nstage * stage_bytes;
-  float* xbuf = reinterpret_cast<float*>(ptr);                      // [2][RB][XR]
+  uint8_t* ptr = stage0 + (size_t)g.nbs * stage_bytes;
+  float* xbuf = reinterpret_cast<float*>(ptr);                      // [2][RB][XR] series rows (double buffered)
   ptr += (size_t)2 * g.RB * g.XR * sizeof(float);
-  float* cand_d = reinterpret_cast<float*>(ptr);                    // [128][KG]
-  ptr += (size_t)kRows * g.KG * sizeof(float);
-  int* cand_i = reinterpret_cast<int*>(ptr);
-  ptr += (size_t)kRows * g.KG * sizeof(int);
-  float* wstat = reinterpret_cast<float*>(ptr);                     // [KG] written and read by the epilogue warps only
-  ptr += 16 * sizeof(float);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ptr);                // full[3], empty[3], tfull[2], tempty[2]
-  uint64_t* full = bars; uint64_t* empty = bars + kMaxStages;
-  uint64_t* tfull = bars + 2 * kMaxStages; uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* celld = reinterpret_cast<float*>(ptr);                     // [ncb][4][RB][KG][16] winner rows' distances
+  ptr += (size_t)g.ncb * 4 * g.RB * g.KG * 16 * sizeof(float);
+  unsigned long long* cells = reinterpret_cast<unsigned long long*>(ptr);   // [ncb][4][RB][KG] ordered min | first window of the row
+  ptr += (size_t)g.ncb * 4 * g.RB * g.KG * sizeof(unsigned long long);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ptr);
+  uint64_t* fullA = bars; uint64_t* emptyA = fullA + kAStages;
+  uint64_t* fullB = emptyA + kAStages; uint64_t* emptyB = fullB + kMaxBStages;
+  uint64_t* tfull = emptyB + kMaxBStages; uint64_t* tempty = tfull + kMaxAcc;
+  uint64_t* rowfull = tempty + kMaxAcc; uint64_t* rowempty = rowfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rowempty + 2);
 
-  const int acc_cols = kAccCols;                                    // column pitch of one accumulator
-  const uint32_t tmem_cols = 512;                                   // 2 accumulators + kMaxStages A stages
-  const uint32_t a_col0 = 2 * kAccCols;
+  const uint32_t tmem_cols = 512;                                   // nacc accumulators in columns [0,256) + kAStages A stages
+  const uint32_t a_col0 = 256;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full[s], kProducerThreads / 32 + 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpilogueThreads / 32); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }   // 4 producer warps
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int i = 0; i < kMaxAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&rowfull[i], 1); mbar_init(&rowempty[i], kProdWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TC_ADD(10, t_entry);       // barrier init + TMEM alloc
 
-  if (warp < 4) {
+  if (warp < kProdWarps) {
     // =================================================================== PRODUCERS
-    const int p = threadIdx.x;                                      // 0..127
-    for (int i = p; i < 2 * g.RB * g.XR; i += kProducerThreads) xbuf[i] = 0.f;
-    bar_sync(1, kProducerThreads);
-    // first tile's series rows.  Rows are stored bank-skewed (4 floats of padding after every 32) so that the
-    // 128 producer threads, whose segments start 16 samples apart, read with conflict-free LDS.128.
-    auto prefetch_rows = [&](int tile, int buf) {
-      const int b0 = bbeg + tile * g.RB;
-      const int chunks = g.Tp / 4;
-      for (int i = p; i < g.RB * chunks; i += kProducerThreads) {
-        const int bl = i / chunks, c = i - bl * chunks;
-        if (b0 + bl < bend)
-          cp_async16(xbuf + ((size_t)buf * g.RB + bl) * g.XR + c * 4 + 4 * (c >> 3),
-                     a.xn + ((size_t)(b0 + bl) * g.M + m) * g.Tp + c * 4);
-      }
-      cp_async_commit();
-    };
-    if (ntile > 0) prefetch_rows(0, 0);
-    if (p == 0) TC_ADD(11, t_entry);                 // producer prologue done
-    // Per-thread constants.  A: this thread owns accumulator row p = bl*RI + i, i.e. samples 16 i + 32 kb + (0..31)
-    // of series bl.  B task u covers shapelet u, shift j = p >> 3, 16-byte chunk c = p & 7.
-    const int a_bl = p / g.RI, a_i = p - a_bl * g.RI;
+    const int p = threadIdx.x;                                      // 0..255
+    (void)p;
+    const int row = (warp & 3) * 32 + lane;                         // accumulator row = TMEM lane
+    const int grp = warp >> 2;                                      // takes the stages with (it & 1) == grp
+    // this thread's row: samples 16 i + 32 kb + (0..31) of series bl
+    const int a_bl = row / g.RI, a_i = row - a_bl * g.RI;
     int a_off[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int idx = a_i * kShifts + 4 * c;
       a_off[c] = a_bl < g.RB ? a_bl * g.XR + idx + 4 * (idx >> 5) : -1;
     }
-    const uint8_t* bsrc = a.btiles + ((size_t)m * g.nkb + blockIdx.y) * g.NKB * (size_t)stage_bytes;
-    const uint32_t a_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + a_col0;
+    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0;
     uint32_t it = 0;                                                 // global stage counter
-    for (int tile = 0; tile < ntile; ++tile) {
-      const int buf = tile & 1;
-      const int nb = min(g.RB, bend - (bbeg + tile * g.RB));
+    for (int w = wbeg; w < wend; ++w) {
+      const int buf = (w - wbeg) & 1;
+      const TileCoord tc = tile_coord(g, w);
+      const int nb = min(g.RB, g.B - tc.b0);
       long long tr0 = TC_CLK();
-      cp_async_wait_all();
-      bar_sync(1, kProducerThreads);      // rows of this tile landed; everyone is done with the other buffer
+      mbar_wait(&rowfull[buf], ((w - wbeg) >> 1) & 1);               // this tile's series rows are in shared memory
+      if (lane == 0 && (warp & 3) == 0) TC_TRACE(9 + grp, w - wbeg, 0);
       if (p == 0) TC_ADD(3, tr0);
-      if (tile + 1 < ntile) prefetch_rows(tile + 1, buf ^ 1);
       const float* xb = xbuf + (size_t)buf * g.RB * g.XR;
       const bool a_live = a_off[0] >= 0 && a_bl < nb;
       for (int kb = 0; kb < g.NKB; ++kb, ++it) {
-        const int s = it % g.nstage;
-        const uint32_t ph = (it / g.nstage) & 1;
-        long long tp0 = TC_CLK();
-        mbar_wait(&empty[s], ph ^ 1);                                // passes immediately on the first lap
-        tc_fence_after();
-        if (p == 0) {   // B stage: one bulk TMA copy of the pre-swizzled tile image, counted in bytes on full[s]
-          mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-          tma_bulk_g2s(stage0 + (size_t)s * stage_bytes, bsrc + (size_t)kb * stage_bytes, (uint32_t)stage_bytes, &full[s]);
-          TC_ADD(0, tp0);
-        }
-        tp0 = TC_CLK();
-        // A stage -> tensor memory: 32 columns of raw fp32 (the MMA truncates to tf32 = hi) and 32 of lo
-        {
-          uint32_t hi[32], lo[32];
+        if ((int)(it & 1) != grp) continue;
+        const int s = it % kAStages;
+        const uint32_t ph = (it / kAStages) & 1;
+        // A stage -> tensor memory: 32 columns of raw fp32 (the MMA truncates to tf32 = hi) and 32 of lo.
+        // The shared-memory reads do not depend on the stage being free: issue them before the wait.
+        float4 v[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a_live) v = *reinterpret_cast<const float4*>(xb + a_off[c] + kb * 36);   // 32 samples + 4 pad
-            const float4 l4 = tf32_lo(v);
-            hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
-            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
-            lo[4 * c] = __float_as_uint(l4.x); lo[4 * c + 1] = __float_as_uint(l4.y);
-            lo[4 * c + 2] = __float_as_uint(l4.z); lo[4 * c + 3] = __float_as_uint(l4.w);
-          }
-          tmem_st32(a_lane + s * kAStageCols, hi);
-          if (g.split) tmem_st32(a_lane + s * kAStageCols + 32, lo);
+        for (int c = 0; c < 8; ++c) {
+          v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a_live) v[c] = *reinterpret_cast<const float4*>(xb + a_off[c] + kb * 36);   // 32 samples + 4 pad
         }
-        if (p == 0) TC_ADD(1, tp0);
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 l4 = tf32_lo(v[c]);
+          hi[4 * c] = __float_as_uint(v[c].x); hi[4 * c + 1] = __float_as_uint(v[c].y);
+          hi[4 * c + 2] = __float_as_uint(v[c].z); hi[4 * c + 3] = __float_as_uint(v[c].w);
+          lo[4 * c] = __float_as_uint(l4.x); lo[4 * c + 1] = __float_as_uint(l4.y);
+          lo[4 * c + 2] = __float_as_uint(l4.z); lo[4 * c + 3] = __float_as_uint(l4.w);
+        }
+        long long tp0 = TC_CLK();
+        mbar_wait(&emptyA[s], ph ^ 1);                               // passes immediately on the first lap
+        tc_fence_after();
+        if (p == 0) TC_ADD(0, tp0);
         tp0 = TC_CLK();
+        tmem_st32(a_lane + s * kAStageCols, hi);
+        if (g.split) tmem_st32(a_lane + s * kAStageCols + 32, lo);
         tmem_st_wait();                                              // A columns written
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
-        if (p == 0) TC_ADD(2, tp0);
+        if (lane == 0) mbar_arrive(&fullA[s]);
+        if (lane == 0 && (warp & 3) == 0) { if (kb < 2) TC_TRACE(9 + grp, w - wbeg, 1); TC_TRACE(9 + grp, w - wbeg, 2); }
+        if (p == 0) TC_ADD(1, tp0);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rowempty[buf]);                    // this warp no longer reads the tile's rows
     }
-  } else if (warp < 8) {
+  } else if (warp < kMmaWarp) {
     // =================================================================== EPILOGUE
-    const int e = threadIdx.x - kProducerThreads;                   // 0..127 = accumulator row
-    const int ew = warp - 4;                                        // TMEM lane quarter
+    const int ew = warp - kProdWarps;                               // 0..7
+    const int quarter = ew & 3, half = ew >> 2;                     // TMEM lane quarter; shapelets kl = half, half+2, ..
+    const int e = quarter * 32 + lane;                              // accumulator row
+    const int et = threadIdx.x - kProducerThreads;                  // 0..255
     const int bl = e / g.RI, i = e - bl * g.RI;
+    const int t0 = i * kShifts;
     const float invL = 1.f / (float)g.L;
-    for (int kl = ew; kl < g.KG; kl += 4) {       // shapelet statistics (same arithmetic as the FP32 engine)
-      const int k = k0 + kl;
-      float stat = 0.f;
-      if (k < g.K) {
-        const float* src = a.W + ((size_t)k * g.M + m) * g.L;
-        float s1 = 0.f, s2 = 0.f;
-        for (int l = lane; l < g.L; l += 32) { const float w = __ldg(src + l); s1 += w; s2 = fmaf(w, w, s2); }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-        if (g.dist == IGN_DIST_PEARSON) {
-          const float mean = s1 / (float)g.L;
-          float c2 = 0.f;
-          for (int l = lane; l < g.L; l += 32) { const float w = __ldg(src + l) - mean; c2 = fmaf(w, w, c2); }
-#pragma unroll
-          for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-          stat = sqrtf(c2);
-        } else if (g.dist == IGN_DIST_COSINE) {
-          stat = 1.f / fmaxf(sqrtf(s2), 1e-8f);
-        } else {
-          stat = s2;
-        }
-      }
-      if (lane == 0) wstat[kl] = stat;
-    }
+    const int nst = min(4, max(0, (g.Ts - t0) / 4));                // float4 stores per distance row segment (Ts % 4 == 0)
+    const int npair = g.RB * g.KG;
+    const int cells_per_buf = 4 * npair;
+    for (int q = et; q < g.ncb * cells_per_buf; q += kEpilogueThreads) cells[q] = kSlotEmpty;
     bar_sync(2, kEpilogueThreads);
-    for (int tile = 0; tile < ntile; ++tile) {
-      const int acc = tile & 1;
-      const int b0 = bbeg + tile * g.RB;
-      const int nb = min(g.RB, bend - b0);
-      const bool row_live = bl < g.RB && bl < nb;
-      const int b = b0 + bl;
-      const int t0 = i * kShifts;
-      // this row's 16 window norm terms (fp32, from the window-statistics pass): four 16-byte loads issued
-      // before the accumulator wait so their latency hides under the MMAs of this tile
+    // the samples this warp's 32 rows belong to (row -> sample is the same for every tile, so a cell
+    // (quarter, sample, shapelet) is either rewritten by exactly one warp on every tile or stays empty for ever)
+    const int bl_lo = __shfl_sync(0xffffffffu, bl, 0);
+    const int bl_hi = min(__shfl_sync(0xffffffffu, bl, 31), g.RB - 1);
+    int n = 0;                                                      // local tile counter
+    for (int w = wbeg; w < wend; ++w, ++n) {
+      const int acc = n % g.nacc;
+      const TileCoord tc = tile_coord(g, w);
+      const int m = tc.m, k0 = tc.kblk * g.KG;
+      const int nb = min(g.RB, g.B - tc.b0);
+      const bool row_live = bl < nb;                                // (bl < RB is implied: nb <= RB)
+      const int b = tc.b0 + bl;
+      unsigned long long* cbuf = cells + (size_t)(n & (g.ncb - 1)) * cells_per_buf;
+      float* dbuf = celld + (size_t)(n & (g.ncb - 1)) * cells_per_buf * 16;
+      // this row's 16 window norm terms (fp32, from the window-statistics pass) and the shapelet statistics:
+      // loads issued before the accumulator wait so their latency hides under the MMAs of this tile
       float4 xs4[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) xs4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -424,135 +525,238 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
 #pragma unroll
         for (int j = 0; j < 4; ++j) xs4[j] = __ldg(sp + j);
       }
+      const float* wsp = a.wstat + ((size_t)m * g.nkb + tc.kblk) * 8;
+      float wst_next = half < g.KG ? __ldg(wsp + half) : 0.f;
       long long te0 = TC_CLK();
-      mbar_wait(&tfull[acc], (tile >> 1) & 1);
-      if (e == 0) TC_ADD(7, te0);
+      mbar_wait(&tfull[acc], (n / g.nacc) & 1);
+      if (lane == 0) TC_TRACE(ew, n, 0);
+      if (et == 0) TC_ADD(7, te0);
       te0 = TC_CLK();
       tc_fence_after();
       const float xst[16] = {xs4[0].x, xs4[0].y, xs4[0].z, xs4[0].w, xs4[1].x, xs4[1].y, xs4[1].z, xs4[1].w,
                              xs4[2].x, xs4[2].y, xs4[2].z, xs4[2].w, xs4[3].x, xs4[3].y, xs4[3].z, xs4[3].w};
-      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * acc_cols);
-      for (int kl = 0; kl < g.KG; ++kl) {
-        uint32_t v[16];
-        tmem_ld16(trow + kl * 16, v);
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.accp);
+      float* drow = (a.dstore && row_live) ? a.dstore + (((size_t)b * g.M + m) * g.K + k0) * g.Ts + t0 : nullptr;
+      uint32_t v[16];
+      if (half < g.KG) tmem_ld16(trow + half * 16, v);
+#pragma unroll 1
+      for (int kl = half; kl < g.KG; kl += 2) {
         tmem_ld_wait();
+        float raw[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) raw[j] = __uint_as_float(v[j]);
+        if (kl + 2 < g.KG) tmem_ld16(trow + (kl + 2) * 16, v);       // next shapelet's columns load under this one's math
         const int k = k0 + kl;
-        float best = INFINITY; int bi = 0x7fffffff;
+        const float wst = wst_next;
+        if (kl + 2 < g.KG) wst_next = __ldg(wsp + kl + 2);
         float dv[16];
-        const float wst = wstat[kl];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float raw = __uint_as_float(v[j]);
-          float d;
-          if (g.dist == IGN_DIST_SQL2) d = fmaxf((xst[j] + wst - 2.f * raw) * invL, 0.f);
-          else if (g.dist == IGN_DIST_COSINE) d = 1.f - raw * xst[j] * wst;
-          else d = 1.f - __fdividef(raw, xst[j] * wst + 1e-8f);          // norms hoisted; no IEEE slow paths on zeros
-          const bool valid = row_live && k < g.K && (t0 + j) < g.Tw;
-          dv[j] = valid ? d : 0.f;
-          if (valid && d < best) { best = d; bi = t0 + j; }
+          if (DIST == IGN_DIST_SQL2) dv[j] = fmaxf((xst[j] + wst - 2.f * raw[j]) * invL, 0.f);
+          else if (DIST == IGN_DIST_COSINE) dv[j] = 1.f - raw[j] * xst[j] * wst;
+          else dv[j] = 1.f - __fdividef(raw[j], xst[j] * wst + 1e-8f);   // norms hoisted; no IEEE slow paths on zeros
         }
-        if (a.dstore && row_live && k < g.K) {
-          float* dg = a.dstore + (((size_t)b * g.M + m) * g.K + k) * g.Ts + t0;
+        const bool kvalid = k < g.K;
+        // pad windows (t >= T') got NaN / +inf from the statistics pass: fminf skips them, no per-window masks
+        float best = fminf(fminf(fminf(dv[0], dv[1]), fminf(dv[2], dv[3])), fminf(fminf(dv[4], dv[5]), fminf(dv[6], dv[7])));
+        best = fminf(best, fminf(fminf(fminf(dv[8], dv[9]), fminf(dv[10], dv[11])), fminf(fminf(dv[12], dv[13]), fminf(dv[14], dv[15]))));
+        if (drow && kvalid) {
+          float4* dg = reinterpret_cast<float4*>(drow + (size_t)kl * g.Ts);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            if (t0 + j < g.Ts) *reinterpret_cast<float4*>(dg + j) = make_float4(dv[j], dv[j + 1], dv[j + 2], dv[j + 3]);
+          for (int j = 0; j < 4; ++j)
+            if (j < nst) dg[j] = make_float4(dv[4 * j], dv[4 * j + 1], dv[4 * j + 2], dv[4 * j + 3]);
         }
-        cand_d[e * g.KG + kl] = best;
-        cand_i[e * g.KG + kl] = bi;
+        // arg-min of each (sample, shapelet) pair over this warp's rows: redux.min on the ordered key; the first
+        // row holding the minimum publishes (key | its first window) and its 16 distances to the warp's own cell —
+        // plain stores, no atomics, no intra-warp round trip; the window inside the row is found by the finaliser
+        const uint32_t key = (row_live && kvalid) ? ordered_key(best) : 0xffffffffu;
+        for (int sb = bl_lo; sb <= bl_hi; ++sb) {
+          const bool mine = bl == sb;
+          const uint32_t wmin = __reduce_min_sync(0xffffffffu, mine ? key : 0xffffffffu);
+          const unsigned hit = __ballot_sync(0xffffffffu, mine && key == wmin);
+          if (lane == __ffs(hit) - 1) {
+            const int cell = (quarter * g.RB + sb) * g.KG + kl;
+            float4* dc = reinterpret_cast<float4*>(dbuf + (size_t)cell * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dc[j] = make_float4(dv[4 * j], dv[4 * j + 1], dv[4 * j + 2], dv[4 * j + 3]);
+            cbuf[cell] = ((unsigned long long)wmin << 32) | (unsigned)t0;
+          }
+        }
       }
+      __threadfence_block();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);                      // this warp's quarter of the accumulator is drained
-      if (e == 0) TC_ADD(8, te0);
-      te0 = TC_CLK();
-      bar_sync(2, kEpilogueThreads);
-      // per (sample, shapelet) arg-min over the RI rows of that sample, first index on ties: one warp per pair
-      for (int pair = ew; pair < g.RB * g.KG; pair += 4) {
-        const int rbl = pair / g.KG, kl = pair - rbl * g.KG;
-        const int k = k0 + kl;
-        if (rbl >= nb || k >= g.K) continue;
-        float dmn = INFINITY; int imn = 0x7fffffff;
-        for (int ii = lane; ii < g.RI; ii += 32) {
-          const float d = cand_d[(rbl * g.RI + ii) * g.KG + kl];
-          if (d < dmn) { dmn = d; imn = cand_i[(rbl * g.RI + ii) * g.KG + kl]; }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          const float od = __shfl_xor_sync(0xffffffffu, dmn, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, imn, o);
-          if (od < dmn || (od == dmn && oi < imn)) { dmn = od; imn = oi; }
-        }
-        if (lane == 0) {
-          const size_t o = ((size_t)(b0 + rbl) * g.K + k) * g.M + m;
-          float pv;
-          if (g.pool == IGN_POOL_RBF_MAX) { const float ed = g.eps * dmn; pv = expf(-(ed * ed)); }
-          else pv = 1.f / (1.f + expf(-(a.thr[(size_t)k * g.M + m] - dmn)));
-          a.p[o] = pv; a.dmin[o] = dmn;
-          if (a.argmin) a.argmin[o] = imn;
-        }
+      if (lane == 0) mbar_arrive(&tempty[acc]);                      // this warp's share of the accumulator is drained
+      if (lane == 0) TC_TRACE(ew, n, 1);
+      if (et == 0) TC_ADD(8, te0);
+      // One rotating warp (tile & 7) finalises each tile, ONE TILE LATE: at the end of tile n the finaliser of tile
+      // n-1 syncs on that tile's barrier, which the other seven warps only arrived at — so nobody ever waits for a
+      // slower warp of the same tile, and there is no serial chain through the finalisers.
+      // Barrier ids and cell buffers rotate over ncb >= nacc + 2 tiles: a warp can reach the barrier (or rewrite the
+      // cells) of tile n-1+ncb only after the MMAs of that tile, which need every warp's tempty arrival of tile
+      // n-1+ncb-nacc >= n+1, which the finaliser of tile n-1 issues after it has left the barrier of tile n-1.
+      if ((n & (kEpiWarps - 1)) != ew) bar_arrive(2 + (n & (g.ncb - 1)), kEpilogueThreads);
+      if (n > 0 && ((n - 1) & (kEpiWarps - 1)) == ew) {
+        te0 = TC_CLK();
+        finalize_tile(g, a, cells, celld, n - 1, w - 1, lane);
+        if (lane == 0) TC_TRACE(ew, n, 2);
+        if (lane == 0) TC_ADD(9, te0);
       }
-      bar_sync(2, kEpilogueThreads);                                 // cand arrays free for the next tile
-      if (e == 0) TC_ADD(9, te0);
     }
-  } else {
+    if (n > 0 && ((n - 1) & (kEpiWarps - 1)) == ew) finalize_tile(g, a, cells, celld, n - 1, wend - 1, lane);
+    if (lane == 0) TC_FLUSH();
+  } else if (warp == kMmaWarp) {
     // =================================================================== MMA ISSUER (one elected thread)
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_tf32(kRows, g.N);
-      uint32_t it = 0;
-      for (int tile = 0; tile < ntile; ++tile) {
-        const int acc = tile & 1;
+      // ring positions and phases are carried incrementally: no divisions in the issue loop
+      int sa = 0, sbr = 0, acc = 0;
+      uint32_t pha = 0, phb = 0, phacc = 0;
+      int n = 0, run = -1;
+      for (int w = wbeg; w < wend; ++w, ++n) {
+        const RunFlags rf = run_flags(g, w, wbeg, wend);
+        if (rf.first) ++run;
         long long tm0 = TC_CLK();
-        mbar_wait(&tempty[acc], ((tile >> 1) & 1) ^ 1);              // passes immediately for the first two tiles
+        mbar_wait(&tempty[acc], phacc ^ 1);                          // passes immediately on the first lap
+        TC_TRACE(8, n, 0);
         TC_ADD(4, tm0);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
-        for (int kb = 0; kb < g.NKB; ++kb, ++it) {
-          const int s = it % g.nstage;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.accp);
+        for (int kb = 0; kb < g.NKB; ++kb) {
+          int sbi;
           tm0 = TC_CLK();
-          mbar_wait(&full[s], (it / g.nstage) & 1);
+          if (g.resident) {
+            sbi = kb;
+            if (rf.first) mbar_wait(&fullB[sbi], run & 1);
+          } else {
+            sbi = sbr;
+            mbar_wait(&fullB[sbi], phb);
+          }
+          TC_ADD(2, tm0);
+          tm0 = TC_CLK();
+          mbar_wait(&fullA[sa], pha);
+          if (kb == 0) TC_TRACE(8, n, 1);
+          if (kb == g.NKB - 1) TC_TRACE(8, n, 2);
           TC_ADD(5, tm0);
           tm0 = TC_CLK();
           tc_fence_after();
-          const uint32_t sb_hi = smem_u32(stage0 + (size_t)s * stage_bytes);
+          const uint32_t sb_hi = smem_u32(stage0 + (size_t)sbi * stage_bytes);
           const uint32_t sb_lo = sb_hi + b_bytes;
-          const uint32_t a_hi = tmem_base + a_col0 + s * kAStageCols, a_lo = a_hi + 32;
+          const uint32_t a_hi = tmem_base + a_col0 + sa * kAStageCols, a_lo = a_hi + 32;
+          if (g.split) {
 #pragma unroll
-          for (int k8 = 0; k8 < kKBlock / 8; ++k8) {
-            const uint32_t koff = k8 * 32;                           // 8 tf32 = 32 bytes inside the swizzle atom
-            if (g.split) {                                           // small terms first
+            for (int k8 = 0; k8 < kKBlock / 8; ++k8) {               // small terms first
+              const uint32_t koff = k8 * 32;                         // 8 tf32 = 32 bytes inside the swizzle atom
               umma_tf32_ts(d_tmem, a_lo + k8 * 8, umma_desc_sw128(sb_hi + koff), idesc, (kb | k8) != 0);
               umma_tf32_ts(d_tmem, a_hi + k8 * 8, umma_desc_sw128(sb_lo + koff), idesc, 1);
               umma_tf32_ts(d_tmem, a_hi + k8 * 8, umma_desc_sw128(sb_hi + koff), idesc, 1);
-            } else {
-              umma_tf32_ts(d_tmem, a_hi + k8 * 8, umma_desc_sw128(sb_hi + koff), idesc, (kb | k8) != 0);
             }
+          } else {
+#pragma unroll
+            for (int k8 = 0; k8 < kKBlock / 8; ++k8)
+              umma_tf32_ts(d_tmem, a_hi + k8 * 8, umma_desc_sw128(sb_hi + k8 * 32), idesc, (kb | k8) != 0);
           }
-          umma_commit(&empty[s]);                                    // stage reusable once these MMAs retire
+          umma_commit(&emptyA[sa]);                                  // A stage reusable once these MMAs retire
+          if (!g.resident || rf.last) umma_commit(&emptyB[sbi]);
           TC_ADD(6, tm0);
+          if (++sa == kAStages) { sa = 0; pha ^= 1; }
+          if (++sbr == g.nbs) { sbr = 0; phb ^= 1; }
         }
         umma_commit(&tfull[acc]);                                    // accumulator complete
+        TC_TRACE(8, n, 3);
+        if (++acc == g.nacc) { acc = 0; phacc ^= 1; }
+      }
+      TC_ADD(14, t_entry);
+      TC_FLUSH();
+    }
+    __syncwarp();
+  } else if (warp == kTmaWarp) {
+    // =================================================================== B-TILE LOADER (one elected thread)
+    if (elect_one()) {
+      uint32_t itb = 0;
+      int run = -1;
+      for (int w = wbeg; w < wend; ++w) {
+        const RunFlags rf = run_flags(g, w, wbeg, wend);
+        if (rf.first) ++run;
+        if (g.resident && !rf.first) continue;
+        const TileCoord tc = tile_coord(g, w);
+        const uint8_t* bsrc = a.btiles + ((size_t)tc.m * g.nkb + tc.kblk) * g.NKB * (size_t)stage_bytes;
+        for (int kb = 0; kb < g.NKB; ++kb, ++itb) {
+          int sbi; uint32_t par;
+          if (g.resident) { sbi = kb; par = (uint32_t)(run & 1) ^ 1u; }
+          else { sbi = itb % g.nbs; par = ((itb / g.nbs) & 1) ^ 1u; }
+          mbar_wait(&emptyB[sbi], par);                              // the MMAs that read this stage have retired
+          mbar_arrive_expect_tx(&fullB[sbi], (uint32_t)stage_bytes);
+          tma_bulk_g2s(stage0 + (size_t)sbi * stage_bytes, bsrc + (size_t)kb * stage_bytes, (uint32_t)stage_bytes, &fullB[sbi]);
+        }
       }
     }
     __syncwarp();
   }
 
+  if (warp == kRowWarp) {
+    // =================================================================== SERIES-ROW LOADER (one warp)
+    // Rows are stored bank-skewed (4 floats of padding after every 32) so that the 128 row owners, whose segments
+    // start 16 samples apart, read with conflict-free LDS.128.  Double buffered: tile n+1 loads under tile n.
+    for (int i = lane; i < 2 * g.RB * g.XR; i += 32) xbuf[i] = 0.f;
+    __syncwarp();
+    const int chunks = g.Tp / 4;
+    int n = 0;
+    for (int w = wbeg; w < wend; ++w, ++n) {
+      const int buf = n & 1;
+      if (n >= 2) mbar_wait(&rowempty[buf], ((n >> 1) - 1) & 1);      // every producer warp is done with tile n-2
+      const TileCoord tc = tile_coord(g, w);
+      for (int bl = 0; bl < g.RB; ++bl) {
+        if (tc.b0 + bl >= g.B) break;
+        float* dst = xbuf + ((size_t)buf * g.RB + bl) * g.XR;
+        const float* src = a.xn + ((size_t)(tc.b0 + bl) * g.M + tc.m) * g.Tp;
+        for (int c = lane; c < chunks; c += 32) cp_async16(dst + c * 4 + 4 * (c >> 3), src + c * 4);
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rowfull[buf]);
+    }
+  }
+
   if (threadIdx.x == 0) TC_ADD(12, t_entry);         // producer thread 0 finished its loop
   if (threadIdx.x == kProducerThreads) TC_ADD(13, t_entry);   // epilogue thread 0 finished
-  if (threadIdx.x == 256) TC_ADD(14, t_entry);       // MMA thread finished
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
-  if (threadIdx.x == 0) TC_ADD(15, t_entry);         // CTA lifetime
-  if (threadIdx.x == 0 || threadIdx.x == kProducerThreads || threadIdx.x == 256) TC_FLUSH();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, tmem_cols);
+  if (threadIdx.x == 0) { TC_ADD(15, t_entry); TC_FLUSH(); }  // CTA lifetime
 }
 
-size_t tc_smem_bytes(const TcGeo& g, int nstage) {
-  const size_t stage = (size_t)(g.N * 128) * (g.split ? 2 : 1);
-  return nstage * stage + (size_t)2 * g.RB * g.XR * 4 + (size_t)kRows * g.KG * 8 + 64 +
-         (2 * kMaxStages + 4) * 8 + 16 + 1024;
+size_t tc_smem_fixed(const TcGeo& g) {   // everything except the B ring
+  return (size_t)2 * g.RB * g.XR * 4 + (size_t)g.ncb * 4 * g.RB * g.KG * (8 + 64) +
+         (2 * kAStages + 2 * kMaxBStages + 2 * kMaxAcc + 4) * 8 + 16 + 1024;
+}
+size_t tc_stage_bytes(const TcGeo& g) { return (size_t)(g.N * 128) * (g.split ? 2 : 1); }
+
+// B ring depth: resident (every k-block of a run stays in shared memory) when it fits, else as deep as fits
+bool tc_plan_ring(TcGeo& g) {
+  const size_t cap = (size_t)max_optin_smem();
+  const size_t fixed = tc_smem_fixed(g), stage = tc_stage_bytes(g);
+  if (fixed + 2 * stage > cap) return false;
+  const int fit = (int)min((size_t)kMaxBStages, (cap - fixed) / stage);
+  g.resident = g.NKB <= fit ? 1 : 0;
+  g.nbs = g.resident ? g.NKB : fit;
+  return true;
 }
 
 }  // namespace
+
+int tc_trace_read(long long* host, int n) {
+#ifdef IGN_TC_PROFILE
+  IGN_CUDA(cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(long long) * (size_t)min(n, 12 * 32 * 4)));
+  return IGN_OK;
+#else
+  (void)host; (void)n;
+  set_error("library built without -DIGN_TC_PROFILE");
+  return IGN_ERR_UNSUPPORTED;
+#endif
+}
 
 int tc_profile_read(unsigned long long* host16, int reset) {
 #ifdef IGN_TC_PROFILE
@@ -569,22 +773,34 @@ int tc_profile_read(unsigned long long* host16, int reset) {
 static void tc_geo(const ign_shapelet_desc& d, TcGeo& g) {
   g.B = d.B; g.M = d.M; g.T = d.T; g.Tp = d.Tp; g.K = d.K; g.L = d.L;
   g.Tw = num_windows(d.T, d.L, 1); g.Ts = round_up(g.Tw, 4);
-  g.RI = ceil_div(g.Tw, kShifts); g.RB = max(1, min(kRows / g.RI, d.B));
+  g.RI = ceil_div(g.Tw, kShifts); g.RB = max(1, min(min(kRows / g.RI, d.B), kMaxRB));
   g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb); g.N = 16 * g.KG;   // N <= 128 = kAccCols
   g.NKB = ceil_div(d.L + kShifts - 1, kKBlock);
   {  // bank-skewed series rows: 36 floats per 32 samples
     const int span = max(d.Tp, (g.RI - 1) * kShifts + g.NKB * kKBlock) + 32;
     g.XR = round_up(span + 4 * (span / 32) + 8, 4);
   }
+  g.tpm = ceil_div(d.B, g.RB);
+  g.ntiles = d.M * g.nkb * g.tpm;
   g.dist = d.dist; g.pool = d.pool; g.eps = d.eps;
   g.split = d.precision == IGN_PREC_3XTF32 ? 1 : 0;
+  // Short tiles (few k-blocks) finish their MMAs faster than the epilogue drains an accumulator: keep three
+  // accumulators in flight when they fit the 256 TMEM columns reserved for them.
+  g.nacc = (g.NKB <= 7 && g.N <= 80) ? 3 : 2;
+  g.accp = g.nacc == 3 ? 80 : kAccCols;
+  g.ncb = g.nacc == 3 ? 8 : 4;
+  g.nbs = 2; g.resident = 0;
 }
 
-// bytes of the pre-swizzled B-tile workspace the tcgen05 forward needs
+static size_t tc_btile_bytes(const ign_shapelet_desc& d, const TcGeo& g) {
+  return (size_t)d.M * g.nkb * g.NKB * (size_t)(g.N * 128) * (g.split ? 2 : 1);   // a multiple of 128
+}
+
+// bytes of workspace the tcgen05 forward needs: pre-swizzled B tiles, then the per-shapelet statistics
 size_t shapelet_fwd_tc_workspace(const ign_shapelet_desc& d) {
   TcGeo g;
   tc_geo(d, g);
-  return (size_t)d.M * g.nkb * g.NKB * (size_t)(g.N * 128) * (g.split ? 2 : 1);
+  return tc_btile_bytes(d, g) + (size_t)d.M * g.nkb * 8 * sizeof(float);
 }
 
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d) {
@@ -592,7 +808,9 @@ bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d) {
   if (d.precision != IGN_PREC_3XTF32 && d.precision != IGN_PREC_TF32) return false;
   const int Tw = num_windows(d.T, d.L, 1);
   if (Tw <= 0 || ceil_div(Tw, kShifts) > kRows) return false;     // one sample must fit a 128-row tile
-  return true;
+  TcGeo g;
+  tc_geo(d, g);
+  return tc_plan_ring(g);
 }
 
 int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const float* st0,
@@ -603,25 +821,21 @@ int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   const size_t need = shapelet_fwd_tc_workspace(d);
   if (!ws || ws_bytes < need) { set_error("shapelet_forward(tcgen05): workspace %zu < %zu bytes (ign_shapelet_forward_workspace)", ws_bytes, need); return IGN_ERR_INVALID; }
   if (((uintptr_t)ws & 127) != 0) { set_error("shapelet_forward(tcgen05): workspace must be 128-byte aligned"); return IGN_ERR_INVALID; }
-  const size_t cap = (size_t)max_optin_smem();
-  g.nstage = kMaxStages;
-  while (g.nstage > 1 && tc_smem_bytes(g, g.nstage) > cap) --g.nstage;
-  if (tc_smem_bytes(g, g.nstage) > cap) { set_error("shapelet_forward(tcgen05): L=%d K=%d does not fit shared memory", d.L, d.K); return IGN_ERR_UNSUPPORTED; }
-  // 1. shifted-shapelet operand, once per launch, already in the swizzled tile image
-  tc_build_b_kernel<<<dim3(d.M, g.nkb, g.NKB), 128, 0, st>>>(W, reinterpret_cast<uint8_t*>(ws), d.M, d.K, d.L, g.KG,
-                                                            g.nkb, g.NKB, g.N, g.split, d.dist == IGN_DIST_PEARSON);
+  if (!tc_plan_ring(g)) { set_error("shapelet_forward(tcgen05): L=%d K=%d does not fit shared memory", d.L, d.K); return IGN_ERR_UNSUPPORTED; }
+  uint8_t* btiles = reinterpret_cast<uint8_t*>(ws);
+  float* wstat = reinterpret_cast<float*>(btiles + tc_btile_bytes(d, g));
+  // 1. shifted-shapelet operand + shapelet statistics, once per launch, already in the swizzled tile image
+  tc_build_b_kernel<<<dim3(d.M, g.nkb, g.NKB), 128, 0, st>>>(W, btiles, wstat, d.M, d.K, d.L, g.KG, g.nkb, g.NKB, g.N,
+                                                            g.split, d.dist);
   IGN_CUDA(cudaGetLastError());
-  // 2. main kernel, one CTA per SM: spread (channel, shapelet block) over batch chunks to ~4 waves
-  const int per_chunk = d.M * g.nkb;
-  int nchunk = max(1, ceil_div(4 * sm_count(), per_chunk));
-  nchunk = min(nchunk, ceil_div(d.B, g.RB));
-  g.bpc = round_up(ceil_div(d.B, nchunk), g.RB);
-  // the kernel allocates all 512 TMEM columns: keep it to one CTA per SM by asking for more than half the smem
-  const size_t smem = max(tc_smem_bytes(g, g.nstage), (size_t)118 * 1024);
-  IGN_CUDA(cudaFuncSetAttribute(shapelet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TcArgs a{xn, st0, W, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, 1), reinterpret_cast<const uint8_t*>(ws)};
-  dim3 grid(d.M, g.nkb, ceil_div(d.B, g.bpc));
-  shapelet_fwd_tc_kernel<<<grid, kThreadsTC, smem, st>>>(g, a);
+  // 2. main kernel: persistent, one CTA per SM (the kernel owns all 512 TMEM columns of its SM)
+  const size_t smem = max(tc_smem_fixed(g) + g.nbs * tc_stage_bytes(g), (size_t)118 * 1024);   // > half the SM: one CTA per SM
+  TcArgs a{xn, st0, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, 1), btiles, wstat};
+  const int grid = min(sm_count(), g.ntiles);
+  auto kern = d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2>
+            : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE> : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON>;
+  IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreadsTC, smem, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "ign_last_error": (c_char_p, []),
     "ign_device_check": (c_int32, [c_int32]),
     "ign_debug_tc_profile": (c_int32, [_P, c_int32]),
+    "ign_debug_tc_trace": (c_int32, [_P, c_int32]),
     "ign_padded_len": (c_int32, [c_int32]),
     "ign_num_windows": (c_int32, [c_int32, c_int32, c_int32]),
     "ign_padded_windows": (c_int32, [c_int32, c_int32, c_int32]),

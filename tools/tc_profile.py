@@ -10,9 +10,10 @@ import torch  # noqa: E402
 from layers import ign_cabi as C  # noqa: E402
 from layers.shapelet_ops import instance_norm, shapelet_transform  # noqa: E402
 
-NAMES = ["prod wait empty", "prod build", "prod fence+arrive", "prod wait rows", "mma wait tempty", "mma wait full",
-         "mma issue+commit", "epi wait tfull", "epi drain+math", "epi reduce", "setup: bars+alloc", "producer prologue",
+NAMES = ["prod wait emptyA", "prod build+arrive", "mma wait fullB", "prod wait rows", "mma wait tempty", "mma wait fullA",
+         "mma issue+commit", "epi wait tfull", "epi drain+math", "epi finalize", "setup: bars+alloc", "-",
          "producer loop end", "epilogue end", "mma end", "CTA lifetime"]
+# slots 0,1,3 are timed by producer thread 0 (half of the stages), 7,8 by epilogue thread 0, 9 by every finaliser
 B, M, T, K = 256, 125, 1000, 5
 x = torch.randn(B, T, M, device="cuda")
 pack = instance_norm(x)
@@ -33,16 +34,14 @@ for dist in sys.argv[1].split(","):
                 C.check(C.lib.ign_debug_tc_profile(buf, 1), "profile")
             Tw = T - L + 1
             RI = (Tw + 15) // 16
-            RB = 128 // RI
+            RB = min(128 // RI, 32)
             ntiles = M * ((B + RB - 1) // RB)
             nstage = ntiles * ((L + 15 + 31) // 32)
-            nchunk = min(max(1, -(-4 * 148 // M)), -(-B // RB))
-            bpc = -(-(-(-B // nchunk)) // RB) * RB
-            nctas = M * (-(-B // bpc))
-            print(f"{dist} {prec} L={L}: {e0.elapsed_time(e1):.3f} ms, tiles {ntiles}, stages {nstage}")
+            nctas = 148
+            print(f"{dist} {prec} L={L}: {e0.elapsed_time(e1):.3f} ms, tiles {ntiles} ({ntiles / nctas:.1f} per CTA), stages {nstage}")
             for i, n in enumerate(NAMES):
                 if i >= 10:
-                    print(f"   {n:20s} {buf[i] / 1e6:9.2f} Mcyc total  {buf[i] / nctas:9.1f} cyc per CTA ({nctas} CTAs)")
+                    print(f"   {n:20s} {buf[i] / 1e6:9.2f} Mcyc total  {buf[i] / nctas:11.1f} cyc per CTA")
                     continue
-                per = buf[i] / (nstage if i in (0, 1, 2, 5, 6) else ntiles)
-                print(f"   {n:20s} {buf[i] / 1e6:9.2f} Mcyc total  {per:9.1f} cyc per {'stage' if i in (0, 1, 2, 5, 6) else 'tile'}")
+                div = nstage / 2 if i in (0, 1) else nstage if i in (2, 5, 6) else ntiles
+                print(f"   {n:20s} {buf[i] / 1e6:9.2f} Mcyc total  {buf[i] / div:9.1f} cyc per {'stage' if i in (0, 1, 2, 5, 6) else 'tile'}")
