@@ -490,7 +490,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
   } else if (warp < kMmaWarp) {
     // =================================================================== EPILOGUE
     const int ew = warp - kProdWarps;                               // 0..7
-    const int quarter = ew & 3, half = ew >> 2;                     // TMEM lane quarter; shapelets kl = half, half+2, ..
+    const int quarter = ew & 3;                                     // TMEM lane quarter
+    // The two warps of a quarter take alternate shapelets (kl = half, half+2, ..) and swap parity every tile, so an
+    // odd shapelet count (3 + 2 for K = 5) balances out over two tiles — the accumulator ring absorbs the rest.
     const int e = quarter * 32 + lane;                              // accumulator row
     const int et = threadIdx.x - kProducerThreads;                  // 0..255
     const int bl = e / g.RI, i = e - bl * g.RI;
@@ -508,6 +510,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     int n = 0;                                                      // local tile counter
     for (int w = wbeg; w < wend; ++w, ++n) {
       const int acc = n % g.nacc;
+      const int half = (ew >> 2) ^ (n & 1);
       const TileCoord tc = tile_coord(g, w);
       const int m = tc.m, k0 = tc.kblk * g.KG;
       const int nb = min(g.RB, g.B - tc.b0);
