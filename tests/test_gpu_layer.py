@@ -273,3 +273,59 @@ def test_tcgen05_falls_back_for_strided_windows():
     a = run_layer(xn, W, 3, 1.0, "cosine", precision="3xtf32")
     b = run_layer(xn, W, 3, 1.0, "cosine")
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# Multi-tile geometries: every CTA of the persistent tcgen05 kernel walks many tiles here (ring wrap-around, phase
+# flips, rotating finaliser, cell-buffer reuse, resident and streaming B rings, runs that change channel inside a
+# CTA's range, ragged last tiles), checked against the exact-fp32 engine, itself pinned to the oracle above.
+TC_BIG = [
+    # B,   M,   T,    K,  L
+    (250, 125, 1000, 5, 100),     # resident B ring, 3 accumulators, 2 samples per tile
+    (250, 125, 1000, 5, 200),     # resident, 7 k-blocks
+    (250, 125, 1000, 5, 300),     # streaming B ring (10 k-blocks do not fit)
+    (250, 125, 1000, 5, 500),     # streaming, 4 samples per tile, ragged last tile of every channel
+    (301, 40, 200, 13, 50),       # two shapelet blocks (K > 8), 8 samples per tile (cap), ragged
+    (517, 64, 64, 3, 8),          # short series: 4 window groups per sample, rows mostly idle
+    (96, 125, 1500, 1, 700),      # single shapelet, 23 k-blocks, 51 window groups
+]
+
+
+@pytest.mark.parametrize("shape", TC_BIG)
+def test_tcgen05_many_tiles_vs_fp32_engine(shape):
+    B, M, T, K, L = shape
+    torch.manual_seed(1000 + L + K)
+    xn = torch.randn(B, M, T, device=DEV)
+    W = torch.randn(K, M, L, device=DEV)
+    g = torch.randn(B, K, M, device=DEV)
+    for dist in ("cosine", "sql2"):
+        p32, d32, i32, dW32, _ = run_layer(xn, W, 1, 0.9, dist, g=g)
+        ptc, dtc, itc, dWtc, _ = run_layer(xn, W, 1, 0.9, dist, g=g, precision="3xtf32")
+        assert_close(dtc, d32, 2e-5, 2e-6, f"{dist} {shape} dmin")
+        assert_close(ptc, p32, 2e-5, 2e-6, f"{dist} {shape} p")
+        Tw = T - L + 1
+        assert int(itc.min()) >= 0 and int(itc.max()) < Tw
+        # indices agree except at near-ties between two windows (the engines round the cross term differently)
+        diff = itc != i32
+        assert float(diff.float().mean()) < 2e-3, f"{dist} {shape}: {int(diff.sum())} argmin differences"
+        # the saved distances drive the backward: same gradient from either engine's forward — except for the
+        # shapelet rows of the few (sample, shapelet, channel) triples whose best window is a near-tie and flips
+        # between the engines (the hard one-hot then moves to the other window): bound their number, not their size
+        scale = float(dW32.abs().max())
+        bad = (dWtc - dW32).abs() > 1e-4 * scale + 1e-4 * dW32.abs()
+        assert int(bad.sum()) <= L * (int(diff.sum()) + 2), f"{dist} {shape} dW: {int(bad.sum())} elements differ"
+        assert float((dWtc - dW32).abs().median()) < 1e-5 * scale
+    # bit-determinism of the tensor-core engine
+    ptc2, dtc2, itc2, dWtc2, _ = run_layer(xn, W, 1, 0.9, "sql2", g=g, precision="3xtf32")
+    assert torch.equal(ptc, ptc2) and torch.equal(dtc, dtc2) and torch.equal(itc, itc2) and torch.equal(dWtc, dWtc2)
+
+
+def test_tcgen05_lts_pooling_many_tiles():
+    """DistThresholdShapelet pooling (sigmoid(threshold - min d)) through the tensor-core engine, squared-L2 arithmetic."""
+    torch.manual_seed(5)
+    B, M, T, K, L = 200, 30, 400, 6, 60
+    xn, W = torch.randn(B, M, T, device=DEV), torch.randn(K, M, L, device=DEV)
+    thr = torch.randn(1, K, M, device=DEV)
+    a = run_layer(xn, W, 1, 1.0, "sql2", pool="lts_min", thr=thr)
+    b = run_layer(xn, W, 1, 1.0, "sql2", pool="lts_min", thr=thr, precision="3xtf32")
+    assert_close(b[1], a[1], 2e-5, 2e-6, "lts dmin")
+    assert_close(b[0], a[0], 2e-5, 2e-6, "lts p")
