@@ -38,7 +38,7 @@ FP32_LANES_PER_SM = 128
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step")
@@ -84,16 +84,20 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def mark(self):
+        """Samples taken before this call (process start-up, idle clocks) are not part of the timed region."""
+        self.first = len(self.lines)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -106,7 +110,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -287,20 +291,41 @@ def main():
         exp.train_step(x, y, mask, 0, step_no)
     # ---------------- device-resident timed region ----------------
     sampler = ClockSampler(exp.local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
-    STATS.reset(timing=True)
+        time.sleep(0.5)          # let nvidia-smi start up outside the timed region (its launch cost 2-5 ms of step 1)
+    barrier()
+    sampler.mark()
+    STATS.reset(timing=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = []
     e0.record()
     for _ in range(a.steps):
         step_no += 1
         exp.train_step(x, y, mask, 0, step_no)
+        marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0:      # per-step spread of the timed region (diagnostic, stderr)
+        prev, per = e0, []
+        for mk in marks:
+            per.append(prev.elapsed_time(mk)); prev = mk
+        sys.stderr.write("per-step ms: " + " ".join("%.2f" % v for v in per) + "\n")
     clocks = sampler.stop() if rank == 0 else None
     launches = STATS.launches
+    # per-kernel durations for the rooflines: the same steps once more with a CUDA-event pair around every C-ABI
+    # call, on the stream the kernels run on (kept out of the timed region above so that it is unperturbed)
+    ksteps = min(a.steps, 5)
+    STATS.reset(timing=True)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(ksteps):
+        step_no += 1
+        exp.train_step(x, y, mask, 0, step_no)
+    k1.record()
+    barrier()
+    ms_kernel_region = k0.elapsed_time(k1)
     kern = STATS.summary()
     STATS.reset(timing=False)
     value = world * B * a.steps / (ms_total * 1e-3)
@@ -359,7 +384,7 @@ def main():
     rooflines = []
     for fam, f in sorted(fams.items(), key=lambda kv: -kv[1]["ms"]):
         avg_ms = f["ms"] / max(1, f["launches"])
-        r = {"kernel": fam, "launches": f["launches"], "avg_ms": avg_ms, "share_of_step": f["ms"] / ms_total}
+        r = {"kernel": fam, "launches": f["launches"], "avg_ms": avg_ms, "share_of_step": f["ms"] / ms_kernel_region}
         if f["ops"]:
             ach = f["ops"] / (f["ms"] * 1e-3) / 1e12
             if fam == "shapelet_fwd" and not l1 and a.precision in ("3xtf32", "tf32"):
@@ -401,7 +426,7 @@ def main():
         "roofline": dominant, "rooflines": rooflines, "cpu_baseline": cpu,
         "shapelet_layer": {"fwd_tflops": fams.get("shapelet_fwd", {}).get("ops", 0) / max(1e-9, fams.get("shapelet_fwd", {}).get("ms", 0) * 1e-3) / 1e12,
                            "bwd_tflops": fams.get("shapelet_bwd", {}).get("alg", 0) / max(1e-9, fams.get("shapelet_bwd", {}).get("ms", 0) * 1e-3) / 1e12,
-                           "share_of_step": sum(f["ms"] for k, f in fams.items() if k.startswith("shapelet")) / ms_total},
+                           "share_of_step": sum(f["ms"] for k, f in fams.items() if k.startswith("shapelet")) / ms_kernel_region},
         "allreduce_bytes_per_step": exp.grads.nbytes() if world > 1 else 0,
     }
     emit(line)

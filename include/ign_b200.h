@@ -166,6 +166,17 @@ int32_t ign_gate_backward(const float* sbm_out_dev, const float* deep_out_dev, c
                           const float* g_eta_dev, float* g_sbm_dev, float* g_deep_dev, int32_t B,
                           int32_t C, int32_t use_gate, float gating_value, void* stream);
 
+/* Shapelet diversity regulariser of ShapeBottleneckModel.loss (Shapelet.py:223-230) for one length group:
+ *   div = (1/(M K K)) * sum_{m, a != b} exp(-|| W[b,m,:] - W[a,m,:] + 1e-6 ||_2)
+ * forward writes coef_dev [M,K,K] (= exp(-d)/d, 0 on the diagonal; the backward's input) and
+ * ign_diversity_partials(K) * M partial sums to partial_dev; div = sum(partial) / (M K K), summed by the caller.
+ * backward: dW_dev [K,M,L] = gout * d div / dW (overwritten); gout_dev points to ONE float on the device. */
+int32_t ign_diversity_partials(int32_t K);
+int32_t ign_diversity_forward(const float* W_dev, float* coef_dev, float* partial_dev, int32_t K, int32_t M,
+                              int32_t L, void* stream);
+int32_t ign_diversity_backward(const float* W_dev, const float* coef_dev, const float* gout_dev, float* dW_dev,
+                               int32_t K, int32_t M, int32_t L, void* stream);
+
 /* Host-buffer convenience call (inference): the whole shapelet transform of ShapeBottleneckModel.forward
  * (Shapelet.py:186-196) for G length groups with HOST pointers; copies in, launches, copies out and
  * synchronises.  x_host [B,T,M]; W_host[g] [K[g],M,L[g]]; probs_host/dists_host [B, sum_g K[g]*M]. */

@@ -157,6 +157,21 @@ int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const
   return launch_shapelet_bwd_simt(*d, xn, st0, st1, W, g, dstore, dmin, argmin, dW, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int32_t ign_diversity_partials(int32_t K) { return K <= 0 ? 0 : diversity_blocks(K) * diversity_blocks(K); }
+
+int32_t ign_diversity_forward(const float* W, float* coef, float* partial, int32_t K, int32_t M, int32_t L, void* stream) {
+  IGN_REQUIRE(W && coef && partial, "diversity_forward: null pointer");
+  IGN_REQUIRE(K > 0 && M > 0 && L > 0, "diversity_forward: bad shape K=%d M=%d L=%d", K, M, L);
+  return launch_diversity_fwd(W, coef, partial, K, M, L, (cudaStream_t)stream);
+}
+
+int32_t ign_diversity_backward(const float* W, const float* coef, const float* gout, float* dW, int32_t K, int32_t M,
+                               int32_t L, void* stream) {
+  IGN_REQUIRE(W && coef && gout && dW, "diversity_backward: null pointer");
+  IGN_REQUIRE(K > 0 && M > 0 && L > 0, "diversity_backward: bad shape K=%d M=%d L=%d", K, M, L);
+  return launch_diversity_bwd(W, coef, gout, dW, K, M, L, (cudaStream_t)stream);
+}
+
 int32_t ign_gate_forward(const float* s, const float* z, float* out, float* eta, int32_t B, int32_t C,
                          int32_t use_gate, float gv, void* stream) {
   IGN_REQUIRE(s && z && out && eta, "gate_forward: null pointer");

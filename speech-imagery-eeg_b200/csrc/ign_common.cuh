@@ -68,6 +68,11 @@ int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int 
 int launch_gate_bwd(const float* s, const float* z, const float* go, const float* ge, float* gs,
                     float* gz, int B, int C, int use_gate, float gv, cudaStream_t st);
 
+int diversity_blocks(int K);
+int launch_diversity_fwd(const float* W, float* coef, float* partial, int K, int M, int L, cudaStream_t st);
+int launch_diversity_bwd(const float* W, const float* coef, const float* gout, float* dW, int K, int M, int L,
+                         cudaStream_t st);
+
 int max_optin_smem();  // per-block opt-in shared memory of the current device (cached)
 int sm_count();
 

@@ -49,6 +49,9 @@ _SIGNATURES = {
     "ign_shapelet_forward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 9 + [c_size_t, _P]),
     "ign_shapelet_backward_workspace": (c_size_t, [POINTER(ShapeletDesc)]),
     "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 10 + [c_size_t, _P]),
+    "ign_diversity_partials": (c_int32, [c_int32]),
+    "ign_diversity_forward": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
+    "ign_diversity_backward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),
     "ign_gate_forward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P]),
     "ign_gate_backward": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_float, _P]),
     "ign_sbm_transform_host": (c_int32, [_P, c_int32, c_int32, c_int32, c_int32, POINTER(_P),

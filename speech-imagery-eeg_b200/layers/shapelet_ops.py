@@ -275,6 +275,41 @@ def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: 
         return _ShapeletTransform.apply(W, threshold, pack, stride, eps, dist, pool, precision)
 
 
+class _Diversity(torch.autograd.Function):
+    """mean_{m, a != b} exp(-||w_b - w_a + 1e-6||) of one length group (Shapelet.py:223-230), one launch each way."""
+
+    @staticmethod
+    def forward(ctx, W):
+        Wc = W.detach().to(torch.float32).contiguous()
+        K, M, L = Wc.shape
+        coef = torch.empty((M, K, K), dtype=torch.float32, device=Wc.device)
+        part = torch.empty((M * int(C.lib.ign_diversity_partials(K)),), dtype=torch.float32, device=Wc.device)
+        with torch.cuda.device(Wc.device):
+            C.check(STATS.call("diversity_fwd", 1, lambda: C.lib.ign_diversity_forward(
+                _ptr(Wc), _ptr(coef), _ptr(part), K, M, L, _stream())), "ign_diversity_forward")
+        ctx.save_for_backward(Wc, coef)
+        return part.sum() / float(M * K * K)
+
+    @staticmethod
+    def backward(ctx, gout):
+        Wc, coef = ctx.saved_tensors
+        K, M, L = Wc.shape
+        g = gout.detach().to(torch.float32).reshape(1).contiguous()
+        dW = torch.empty_like(Wc)
+        with torch.cuda.device(Wc.device):
+            C.check(STATS.call("diversity_bwd", 1, lambda: C.lib.ign_diversity_backward(
+                _ptr(Wc), _ptr(coef), _ptr(g), _ptr(dW), K, M, L, _stream())), "ign_diversity_backward")
+        return dW
+
+
+def shapelet_diversity(W: torch.Tensor) -> torch.Tensor:
+    """Diversity term of one Shapelet layer's weights [K,M,L] (scalar), fused CUDA path."""
+    _require_cuda(W, "shapelet weights")
+    _check_device(W.device)
+    with torch.autocast(device_type="cuda", enabled=False):
+        return _Diversity.apply(W)
+
+
 class _GiniGate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sbm_out, deep_out, gating_value):

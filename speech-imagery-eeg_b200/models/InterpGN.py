@@ -22,6 +22,7 @@ class InterpGN(nn.Module):
         super().__init__()
         self.configs = configs
         self.sbm = ShapeBottleneckModel(configs=configs, num_shapelet=num_shapelet, shapelet_len=shapelet_len)
+        self.sbm.loss_in_parent = True             # forward() below evaluates the regulariser once
         if configs.dnn_type not in dnn_dict:
             raise ValueError(f"dnn_type {configs.dnn_type!r} is not built in this framework "
                              f"(available: {sorted(dnn_dict)})")

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from layers.shapelet_ops import SeriesPack, instance_norm, resolve_dist, shapelet_transform
+from layers.shapelet_ops import SeriesPack, instance_norm, resolve_dist, shapelet_diversity, shapelet_transform
 from utils.shapelet_util import ModelInfo
 
 
@@ -121,6 +121,7 @@ class ShapeBottleneckModel(nn.Module):
         self.lambda_reg = configs.lambda_reg      # L1 on classifier weights
         self.lambda_div = configs.lambda_div      # shapelet diversity
         self.last_indices = None                  # argmin_t d [B,K,M] per group of the latest forward
+        self.loss_in_parent = False               # True when wrapped by InterpGN (it calls loss() itself)
 
     def _build_layers(self, configs, num_shapelet, shapelet_len):
         precision = getattr(configs, "shapelet_precision", "fp32")
@@ -154,8 +155,10 @@ class ShapeBottleneckModel(nn.Module):
             out = self.output_layer(self.dropout(self.attention(shapelet_probs)))
         else:
             raise ValueError(f"unknown sbm_cls {cls!r}")
-        return out, ModelInfo(d=shapelet_dists, p=shapelet_probs, shapelet_preds=out, preds=out,
-                              loss=self.loss().unsqueeze(0))
+        # (InterpGN evaluates the regulariser itself, InterpGN.py:58; the reference computes it here as well and
+        #  throws this copy away — the parent sets loss_in_parent to skip the duplicate)
+        loss = None if self.loss_in_parent else self.loss().unsqueeze(0)
+        return out, ModelInfo(d=shapelet_dists, p=shapelet_probs, shapelet_preds=out, preds=out, loss=loss)
 
     def step(self):
         with torch.no_grad():                               # Shapelet.py:212-215
@@ -171,7 +174,10 @@ class ShapeBottleneckModel(nn.Module):
         nn.PairwiseDistance's eps, added to the difference)."""
         total = 0.
         for layer in self.shapelets:
-            w = layer.weights.permute(1, 0, 2)                               # [M,K,L]
+            if layer.weights.is_cuda:                                        # one fused launch each way per group
+                total = total + shapelet_diversity(layer.weights)
+                continue
+            w = layer.weights.permute(1, 0, 2)                               # [M,K,L]  (host-side logic tests)
             dist = (w.unsqueeze(1) - w.unsqueeze(2) + 1e-6).norm(dim=-1)      # [M,K,K]
             off = 1.0 - torch.eye(w.shape[1], device=w.device, dtype=w.dtype)
             total = total + (torch.exp(-dist) * off).mean()

@@ -329,3 +329,25 @@ def test_tcgen05_lts_pooling_many_tiles():
     b = run_layer(xn, W, 1, 1.0, "sql2", pool="lts_min", thr=thr, precision="3xtf32")
     assert_close(b[1], a[1], 2e-5, 2e-6, "lts dmin")
     assert_close(b[0], a[0], 2e-5, 2e-6, "lts p")
+
+
+@pytest.mark.parametrize("K,M,L", [(5, 12, 3), (5, 125, 100), (1, 3, 9), (37, 4, 50), (10, 7, 301)])
+def test_diversity_regulariser_vs_reference_formula(K, M, L):
+    """Fused diversity kernels against the reference's broadcast formula (Shapelet.py:223-230) and its autograd."""
+    from layers.shapelet_ops import shapelet_diversity
+    torch.manual_seed(K + M + L)
+    W = torch.randn(K, M, L, dtype=torch.float64)
+    Wr = W.clone().requires_grad_(True)
+    w = Wr.permute(1, 0, 2)
+    dist = (w.unsqueeze(1) - w.unsqueeze(2) + 1e-6).norm(dim=-1)
+    ref = (torch.exp(-dist) * (1.0 - torch.eye(K, dtype=torch.float64))).mean()
+    (3.0 * ref).backward()
+    Wd = W.float().to(DEV).requires_grad_(True)
+    out = shapelet_diversity(Wd)
+    (3.0 * out).backward()
+    torch.cuda.synchronize()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-9
+    scale = float(Wr.grad.abs().max())
+    assert_close(Wd.grad, Wr.grad.float(), 1e-4, 1e-5 * scale + 1e-12, "diversity dW")
+    out2 = shapelet_diversity(Wd.detach())
+    assert float(out2) == float(out)          # deterministic
