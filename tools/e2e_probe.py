@@ -1,3 +1,5 @@
+"""Probe: cost of the host->device batch path of one training step (resident / sequential copy / DevicePrefetcher /
+hand-rolled double buffer) and whether a concurrent H2D copy disturbs the L1 forward kernel.  Run on a GPU box."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "speech-imagery-eeg_b200"))
