@@ -73,6 +73,22 @@ def _shape_for(args):
     return UEA_SHAPES.get(getattr(args, "dataset", ""), (6, 100, 4))
 
 
+def loso_dataset(args):
+    """One synthetic multi-subject set for leave-one-subject-out evaluation (exp/loso.py): every sample carries a
+    subject id (`.subject`), and each subject adds its own per-channel gain and offset so that held-out subjects
+    are a genuine distribution shift, as between the CHISCO participants."""
+    channels, seq_len, num_class = _shape_for(args)
+    subjects = max(2, int(getattr(args, "syn_subjects", 1)))
+    n = int(getattr(args, "syn_train", 512)) + int(getattr(args, "syn_val", 128)) + int(getattr(args, "syn_test", 128))
+    ds = SyntheticSeries(channels, seq_len, num_class, n, 4242 + 1000 * max(0, int(getattr(args, "seed", 0))),
+                         subjects=subjects)
+    g = torch.Generator().manual_seed(97)
+    gain = 1.0 + 0.2 * torch.randn(subjects, 1, channels, generator=g)
+    offset = 0.3 * torch.randn(subjects, 1, channels, generator=g)
+    ds.x = ds.x * gain[ds.subject] + offset[ds.subject]
+    return ds
+
+
 def data_provider(args, flag):
     """flag in {'train','val','test'} (reference data_factory.py:29).  Under data-parallel training the
     train split is sharded by rank (every rank draws a disjoint seeded shard)."""

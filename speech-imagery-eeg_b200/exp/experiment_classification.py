@@ -48,18 +48,26 @@ def get_dnn_model(configs):
 class Experiment(object):
     model_dict = {'InterpGN': InterpGN, 'SBM': ShapeBottleneckModel, 'LTS': DistThresholdSBM, 'DNN': get_dnn_model}
 
-    def __init__(self, args, load_data=True):
-        """load_data=False (bench.py) skips the loaders; args.seq_len/enc_in/num_class must then be set."""
+    def __init__(self, args, load_data=True, loaders=None, independent=False):
+        """load_data=False (bench.py) skips the loaders; args.seq_len/enc_in/num_class must then be set.
+        loaders=((train_ds, train_dl), (val_ds, val_dl), (test_ds, test_dl)) injects prepared splits (LOSO folds);
+        independent=True trains this rank's own model: no gradient all-reduce, no parameter broadcast, every rank
+        logs and checkpoints (exp/loso.py)."""
         self.args = args
         self.rank, self.local_rank, self.world = init_distributed()
-        args.rank, args.world_size = self.rank, self.world
-        self.is_main = self.rank == 0
+        self.independent = independent
+        args.rank, args.world_size = (0, 1) if independent else (self.rank, self.world)
+        self.is_main = self.rank == 0 or independent
         if not torch.cuda.is_available():
             raise RuntimeError("the ign_b200 training path needs a CUDA device (no CPU fallback)")
         self.device = torch.device('cuda', self.local_rank)
         torch.cuda.set_device(self.device)
 
-        if load_data:
+        if loaders is not None:
+            (self.train_data, self.train_loader), (self.val_data, self.val_loader), \
+                (self.test_data, self.test_loader) = loaders
+            self._get_params_from_data()
+        elif load_data:
             self.train_data, self.train_loader = data_provider(args, flag="train")
             self.val_data, self.val_loader = data_provider(args, flag="val")
             self.test_data, self.test_loader = data_provider(args, flag="test")
@@ -68,7 +76,7 @@ class Experiment(object):
         # same Adam(lr) as the reference (:283); the fused CUDA implementation is one kernel per step
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.args.lr, fused=True)
         self.scheduler = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(self.optimizer, T_0=self.args.train_epochs)
-        self.grads = FlatGradAllReduce(self.model, self.world)
+        self.grads = FlatGradAllReduce(self.model, 1 if independent else self.world)
         a = self.args
         self.checkpoint_dir = "./checkpoints/{}/{}/dnn-{}_seed-{}_k-{}_div-{}_reg-{}_eps-{}_beta-{}_dfunc-{}_cls-{}".format(
             a.model, a.dataset, a.dnn_type, a.seed, a.num_shapelet, a.lambda_div, a.lambda_reg, a.epsilon,
@@ -180,7 +188,7 @@ class Experiment(object):
             if stopper.early_stop:
                 self.log("Early stopping")
                 break
-        if self.world > 1:
+        if self.world > 1 and not self.independent:
             torch.distributed.barrier()
         best = os.path.join(self.checkpoint_dir, 'checkpoint.pth')
         if os.path.exists(best):

@@ -32,6 +32,7 @@ FLAGS = [
     # new in this framework
     ("--shapelet_precision", str, "fp32"), ("--syn_shape", str, None), ("--syn_train", int, 512),
     ("--syn_val", int, 128), ("--syn_test", int, 128), ("--syn_subjects", int, 1),
+    ("--loso", "store_true", False),      # leave-one-subject-out: one fold per subject, folds spread over the ranks
 ]
 
 
@@ -62,10 +63,49 @@ def set_seed(seed):
     torch.backends.cudnn.benchmark = False
 
 
+def run_loso(args):
+    """Leave-one-subject-out (exp/loso.py): fold f trains on rank f % world, results are gathered at the end."""
+    from data_provider.data_factory import collate_fn, loso_dataset
+    from exp import loso
+    from exp.experiment_classification import Experiment
+    from exp.parallel import init_distributed
+    rank, _, world = init_distributed()
+    seed = 0 if args.seed == -1 else args.seed
+    set_seed(seed)
+    args.seed = seed
+    ds = loso_dataset(args)
+    folds = loso.loso_folds(ds.subject, seed=seed)
+    mine, local = loso.folds_of_rank(len(folds), world, rank), {}
+    for f in mine:
+        subject = folds[f][0]
+        tr, va, te = loso.fold_loaders(ds, folds[f], args.batch_size, collate_fn, args.num_workers,
+                                       pin_memory=torch.cuda.is_available())
+        args.dataset_tag = f"loso-s{subject}"
+        exp = Experiment(args, loaders=((ds, tr), (ds, va), (ds, te)), independent=True)
+        exp.checkpoint_dir = os.path.join(exp.checkpoint_dir, f"loso_subject_{subject}")
+        print(f"[rank {rank}] fold {f + 1}/{len(folds)}: held-out subject {subject}, "
+              f"{len(folds[f][1])} train / {len(folds[f][2])} val / {len(folds[f][3])} test samples", flush=True)
+        exp.train()
+        loss, res, _ = exp.test(save_csv=False)
+        local[f] = (subject, loss, None if res is None else res.accuracy)
+        torch.cuda.empty_cache()
+    merged = loso.gather_results(local, world)
+    mean_acc, rows = loso.summarize(merged)
+    if rank == 0:
+        for subject, loss, acc in rows:
+            print(f"LOSO subject {subject}: test loss {loss:.4f}  accuracy {acc if acc is None else round(100 * acc, 2)}%")
+        print(f"LOSO mean accuracy over {len(rows)} subjects: {100 * mean_acc:.2f}%")
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+    return merged
+
+
 def main(argv=None):
     args = get_args(argv)
     if args.task_name != "classification":
         raise SystemExit("only --task_name classification is built on the B200 hot path")
+    if args.loso:
+        return run_loso(args)
     from exp.experiment_classification import Experiment
     seeds = [0, 42, 1234, 8237, 2023] if args.seed == -1 else [args.seed]
     results = []
