@@ -407,25 +407,45 @@ __device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) {
 // hard one-hot = first arg-max of p, Shapelet.py:79 | for lts_min the forward's argmin, :105), then the
 // coefficient a_t = dLoss/dd_t times the distance mode's norm factor, written to `coef`; two per-row
 // scalars go to `rowsc` for the finalize kernel.
+__device__ __forceinline__ void cp_async16_pool(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// Persistent warps: every warp walks rows  w, w + nwarps_total, ...  with the NEXT row's distances already in flight
+// (cp.async into the other half of its shared-memory slot) while it works on the current one — the kernel is
+// bound by how many bytes it keeps in flight, not by instructions (issue 70 %, 4.0 TB/s before this change).
+template <int POOL, int DIST>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolArgs a, int rows) {
-  extern __shared__ __align__(16) float prow[];          // [warps][DP]
+  extern __shared__ __align__(16) float prow[];          // [warps][2][DP]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int row = blockIdx.x * nwarp + warp;
-  if (row >= rows) return;
-  float* dr = prow + (size_t)warp * g.DP;
+  const int wstride = gridDim.x * nwarp;
+  float* slot = prow + (size_t)warp * 2 * g.DP;
+  auto prefetch = [&](int r, int buf) {
+    const float* src = a.dstore + (size_t)r * g.Ts;
+    float* dstp = slot + (size_t)buf * g.DP;
+    for (int t = lane * 4; t < g.Ts; t += 128) cp_async16_pool(dstp + t, src + t);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int row = blockIdx.x * nwarp + warp;
+  if (row < rows) prefetch(row, 0);
+  int buf = 0;
+  for (; row < rows; row += wstride, buf ^= 1) {
+  const int nxt = row + wstride;
+  if (nxt < rows) { prefetch(nxt, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+  else asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  float* dr = slot + (size_t)buf * g.DP;
   const int k = row % g.K, bm = row / g.K;
   const int m = bm % g.M, b = bm / g.M;
-  const float* src = a.dstore + (size_t)row * g.Ts;
-  for (int t = lane * 4; t < g.Ts; t += 128)
-    *reinterpret_cast<float4*>(dr + t) = *reinterpret_cast<const float4*>(src + t);
-  __syncwarp();
   const size_t o = ((size_t)b * g.K + k) * g.M + m;
   const float gk = a.g[o];
-  const float eps = g.eps, m2e2 = -2.f * eps * eps;
+  const float eps = g.eps;
   const float qscale = -eps * eps * kLog2e;              // p = exp(-(eps d)^2) = 2^(qscale d^2)
   float Zs = 0.f, S1s = 0.f, shift = 0.f;
   int ih;
-  if (g.pool == IGN_POOL_RBF_MAX) {
+  if (POOL == IGN_POOL_LTS_MIN) { shift = a.dmin[o]; ih = a.argmin[o]; }
+  __syncwarp();
+  if (POOL == IGN_POOL_RBF_MAX) {
     float pmx = -1.f; int imx = 0x7fffffff;
 #pragma unroll 4
     for (int t = lane; t < g.Tw; t += 32) {
@@ -437,7 +457,6 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
     }
     ih = warp_argmax_first(pmx, imx).i;
   } else {
-    shift = a.dmin[o]; ih = a.argmin[o];
 #pragma unroll 4
     for (int t = lane; t < g.Tw; t += 32) {
       const float d = dr[t];
@@ -447,43 +466,45 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   }
   Zs = warp_sum(Zs); S1s = warp_sum(S1s);
   const float invZ = 1.f / Zs, bar = S1s * invZ;
-  const float wst = (g.dist == IGN_DIST_PEARSON) ? a.wstat[(size_t)k * g.M + m] : 0.f;
+  const float wst = (DIST == IGN_DIST_PEARSON) ? a.wstat[(size_t)k * g.M + m] : 0.f;
   const size_t srow = (size_t)bm * a.SP;
   float* dst = a.coef + (size_t)row * g.Ts;
+  // constants folded once per row: c_t = gk * (hard_t + soft_t (p_t - bar)) * p_t * (-2 eps^2 d_t)   (rbf_max)
+  //                                c_t = gk * (hard_t - soft_t (d_t - bar))                             (lts_min)
+  const float gm = gk * (-2.f * eps * eps);
   float sc0 = 0.f, sc1 = 0.f;
 #pragma unroll 4
-  for (int t = lane; t < g.Ts; t += 32) {
-    float coef = 0.f;
-    if (t < g.Tw) {
-      const float d = dr[t];
-      float c;
-      if (g.pool == IGN_POOL_RBF_MAX) {
-        const float p = fast_ex2(qscale * d * d);
-        const float soft = fast_ex2(p * kLog2e) * invZ;
-        c = gk * ((t == ih ? 1.f : 0.f) + soft * (p - bar)) * p * (m2e2 * d);
-      } else {
-        const float soft = fast_ex2((shift - d) * kLog2e) * invZ;
-        c = gk * ((t == ih ? 1.f : 0.f) - soft * (d - bar));
-      }
-      if (g.dist == IGN_DIST_L1 || g.dist == IGN_DIST_SQL2) {
-        coef = c; sc0 += c;
-      } else {
-        if (g.dist == IGN_DIST_COSINE) {
-          coef = c * a.st0[srow + t];
-          sc0 = fmaf(c, 1.f - d, sc0);
-        } else {
-          const float sxn = a.st0[srow + t], mu = a.st1[srow + t];     // ||x_w-mu||, mu
-          const float D = sxn * wst + 1e-8f;                            // wst = ||w-mean||
-          coef = __fdividef(c, D);
-          sc0 = fmaf(coef, mu, sc0);
-          sc1 += __fdividef(c * (1.f - d) * sxn, wst * D);              // Sx/(root*D) = ||x||/(||w|| D)
-        }
-      }
+  for (int t = lane; t < g.Tw; t += 32) {
+    const float d = dr[t];
+    float c;
+    if (POOL == IGN_POOL_RBF_MAX) {
+      const float p = fast_ex2(qscale * d * d);
+      const float soft = fast_ex2(p * kLog2e) * invZ;
+      c = fmaf(soft, p - bar, t == ih ? 1.f : 0.f) * (p * d) * gm;
+    } else {
+      const float soft = fast_ex2((shift - d) * kLog2e) * invZ;
+      c = gk * fmaf(-soft, d - bar, t == ih ? 1.f : 0.f);
+    }
+    float coef;
+    if (DIST == IGN_DIST_L1 || DIST == IGN_DIST_SQL2) {
+      coef = c; sc0 += c;
+    } else if (DIST == IGN_DIST_COSINE) {
+      coef = c * a.st0[srow + t];
+      sc0 = fmaf(c, 1.f - d, sc0);
+    } else {
+      const float sxn = a.st0[srow + t], mu = a.st1[srow + t];     // ||x_w-mu||, mu
+      const float D = sxn * wst + 1e-8f;                            // wst = ||w-mean||
+      coef = __fdividef(c, D);
+      sc0 = fmaf(coef, mu, sc0);
+      sc1 += __fdividef(c * (1.f - d) * sxn, wst * D);              // Sx/(root*D) = ||x||/(||w|| D)
     }
     dst[t] = coef;
   }
+  if (lane < g.Ts - g.Tw) dst[g.Tw + lane] = 0.f;                    // pad windows (at most 3)
   sc0 = warp_sum(sc0); sc1 = warp_sum(sc1);
   if (lane == 0) { a.rowsc[(size_t)row * 2] = sc0; a.rowsc[(size_t)row * 2 + 1] = sc1; }
+  __syncwarp();                                         // everyone is done reading this slot half before it is refilled
+  }
 }
 
 // ||w - mean|| per (k, m) shapelet row (pearson backward).  One warp per row.
@@ -975,13 +996,27 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   {
     const int rows = d.B * d.M * d.K;
     int warps = 8;
-    while (warps > 1 && (size_t)warps * g.DP * sizeof(float) > 96 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * g.DP * sizeof(float);
+    while (warps > 1 && (size_t)warps * 2 * g.DP * sizeof(float) > 72 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 2 * g.DP * sizeof(float);
     if (smem > (size_t)max_optin_smem() - 1024) { set_error("shapelet_backward: %d windows per series do not fit shared memory", g.Tw); return IGN_ERR_UNSUPPORTED; }
-    int rc = set_smem(pool_bwd_kernel, smem);
-    if (rc) return rc;
     PoolArgs pa{gr, dstore, dmin, argmin, st0, st1, stats_pitch(d.T, d.L, d.stride), base + wo.wstat, base + wo.coef, base + wo.rowsc};
-    pool_bwd_kernel<<<ceil_div(rows, warps), warps * 32, smem, st>>>(g, pa, rows);
+    const int per_sm = max(1, min(2048 / (warps * 32), (int)(((size_t)max_optin_smem()) / (smem + 1024))));
+    const dim3 pgrid(min(ceil_div(rows, warps), sm_count() * per_sm)), pblock(warps * 32);
+#define IGN_POOL_LAUNCH(PV, DV)                                                        \
+    { int rc = set_smem(pool_bwd_kernel<PV, DV>, smem); if (rc) return rc;              \
+      pool_bwd_kernel<PV, DV><<<pgrid, pblock, smem, st>>>(g, pa, rows); }
+    if (d.pool == IGN_POOL_RBF_MAX) {
+      switch (d.dist) {
+        case IGN_DIST_L1: IGN_POOL_LAUNCH(IGN_POOL_RBF_MAX, IGN_DIST_L1) break;
+        case IGN_DIST_SQL2: IGN_POOL_LAUNCH(IGN_POOL_RBF_MAX, IGN_DIST_SQL2) break;
+        case IGN_DIST_COSINE: IGN_POOL_LAUNCH(IGN_POOL_RBF_MAX, IGN_DIST_COSINE) break;
+        default: IGN_POOL_LAUNCH(IGN_POOL_RBF_MAX, IGN_DIST_PEARSON) break;
+      }
+    } else {
+      if (d.dist == IGN_DIST_L1) IGN_POOL_LAUNCH(IGN_POOL_LTS_MIN, IGN_DIST_L1)
+      else IGN_POOL_LAUNCH(IGN_POOL_LTS_MIN, IGN_DIST_SQL2)
+    }
+#undef IGN_POOL_LAUNCH
     IGN_CUDA(cudaGetLastError());
   }
   // 2. contraction with the series (FP32 pipe) into per-chunk partials
