@@ -1023,7 +1023,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   const unsigned char* tie = nullptr;
   if (d.dist == IGN_DIST_L1 && bp.hcap) {
     unsigned char* tflags = reinterpret_cast<unsigned char*>(base + wo.tie);
-    const int bsplit = max(1, min(d.B, ceil_div(4 * sm_count(), d.M * g.nkb)));
+    const int bsplit = max(1, min(d.B, ceil_div(sm_count(), d.M * g.nkb)));
     const size_t hs = ((size_t)bp.hcap + kTieBitmapWords) * sizeof(unsigned);
     int rc0 = set_smem(tie_check_kernel, hs);
     if (rc0) return rc0;
