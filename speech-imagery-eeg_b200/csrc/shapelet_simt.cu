@@ -58,6 +58,7 @@ struct Geo {  // geometry shared by forward and backward
   int LQ;      // pitch of one residue row of w in smem (ceil(L/s) rounded to 8)
   int KK, KB, nkb;
   int NB;      // series rows resident per pass
+  int dbuf;    // forward: series rows double buffered (cp.async one pass ahead)
   int bpc;     // samples per batch chunk
   int dist, pool;
   float eps;
@@ -278,6 +279,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------
@@ -302,11 +311,50 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
   const int nitem = g.NB * ntile * nkc;
   const float Lf = 1.f / (float)g.L;   // 1/L
 
+  // Unit stride: series (and window-statistics) rows are double buffered and fetched with cp.async one pass ahead,
+  // so the load of pass i+1 hides under the distance loop of pass i (the exposed load + barrier phases cost short
+  // shapelets ~8 %: FMA pipe 74 % at L=100 against 82 % at L=500 before this change).
+  const bool dbuf = g.dbuf != 0;
+  const int xs_sz = g.NB * g.s * g.XQ, st_sz = (OP != OP_L1) ? g.NB * g.DP : 0;
+  float* xs1 = smem + round_up((int)(cand_d - smem) + 2 * g.NB * g.KB * ntile, 4);   // second buffers, 16-byte aligned, behind the candidates
+  float* st1 = xs1 + (dbuf ? xs_sz : 0);
+  auto prefetch = [&](int b0, int buf) {
+    const int nb = min(g.NB, bend - b0);
+    float* xd = buf ? xs1 : xs;
+    const int xrow = g.Tp / 4;
+    for (int i = threadIdx.x; i < nb * xrow; i += blockDim.x) {
+      const int rbl = i / xrow, c = i - rbl * xrow;
+      cp_async16(xd + rbl * g.XQ + c * 4, a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp + c * 4);
+    }
+    if (OP != OP_L1) {
+      float* sd = buf ? st1 : st0;
+      const int srow = g.DP / 4;                                     // DP <= SP: whole 16-byte chunks of the statistics row
+      for (int i = threadIdx.x; i < nb * srow; i += blockDim.x) {
+        const int rbl = i / srow, c = i - rbl * srow;
+        cp_async16(sd + rbl * g.DP + c * 4, a.st0 + ((size_t)(b0 + rbl) * g.M + m) * a.SP + c * 4);
+      }
+    }
+  };
+  if (dbuf) {   // zero once: the pad columns behind Tp are never written by the prefetch
+    for (int i = threadIdx.x; i < xs_sz; i += blockDim.x) { xs[i] = 0.f; xs1[i] = 0.f; }
+    __syncthreads();
+    if (bbeg < bend) prefetch(bbeg, 0);
+  }
+  int buf = 0;
+
   for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
-    __syncthreads();   // previous pass finished with xs/cand (and ws is written on the first pass)
-    load_series(g, a.xn, a.st0, a.SP, m, b0, nb, xs, OP != OP_L1 ? st0 : nullptr);
-    __syncthreads();
+    if (dbuf) {
+      cp_async_commit_wait_all();
+      __syncthreads();   // this pass's rows landed; everyone is done with the other buffer and with the candidates
+      if (b0 + g.NB < bend) prefetch(b0 + g.NB, buf ^ 1);
+    } else {
+      __syncthreads();   // previous pass finished with xs/cand (and ws is written on the first pass)
+      load_series(g, a.xn, a.st0, a.SP, m, b0, nb, xs, OP != OP_L1 ? st0 : nullptr);
+      __syncthreads();
+    }
+    const float* xcur = (dbuf && buf) ? xs1 : xs;
+    const float* stcur = (dbuf && buf) ? st1 : st0;
     // ---- phase 1: distances + register epilogue ----
     for (int item = threadIdx.x; item < nitem; item += blockDim.x) {
       const int tt = item % ntile;
@@ -315,10 +363,10 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
       if (bl >= nb || k0 + kc * KK >= g.K) continue;
       const int t0 = tt * TT;
       float acc[TT][KK];
-      distance_item<OP, KK, TT>(g, xs + bl * g.s * g.XQ, ws + kc * KK * g.s * g.LQ, t0, acc);
+      distance_item<OP, KK, TT>(g, xcur + bl * g.s * g.XQ, ws + kc * KK * g.s * g.LQ, t0, acc);
       float xst[TT];
 #pragma unroll
-      for (int j = 0; j < TT; ++j) xst[j] = (OP != OP_L1) ? st0[bl * g.DP + t0 + j] : 0.f;
+      for (int j = 0; j < TT; ++j) xst[j] = (OP != OP_L1) ? stcur[bl * g.DP + t0 + j] : 0.f;
       const int b = b0 + bl;
 #pragma unroll
       for (int k = 0; k < KK; ++k) {
@@ -369,7 +417,9 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
         if (a.argmin) a.argmin[o] = mn.i;
       }
     }
+    buf ^= 1;
   }
+  if (dbuf) cp_async_commit_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -581,13 +631,6 @@ __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict_
 }
 
 // ---- contraction kernel: dW partials from the coefficients and the series (pure FP32-pipe work) ----
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
 template <int OP>
 __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -826,15 +869,17 @@ int plan_bpc(const Geo& g, int ctas_per_bchunk, int NB) {
 }
 
 size_t fwd_smem_floats(const Geo& g, int NB, int KB, int ntile) {
-  size_t f = (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + KB + (size_t)2 * NB * KB * ntile;
-  if (g.dist != IGN_DIST_L1) f += (size_t)NB * g.DP;
-  return f;
+  const size_t mult = g.dbuf ? 2 : 1;         // series / statistics rows double buffered
+  size_t f = mult * (size_t)NB * g.s * g.XQ + (size_t)KB * g.s * g.LQ + KB + (size_t)2 * NB * KB * ntile;
+  if (g.dist != IGN_DIST_L1) f += mult * (size_t)NB * g.DP;
+  return f + 4;                                // alignment slack of the second buffers
 }
 
 struct FwdPlan { int threads; size_t smem_bytes; };
 
 bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
-  const size_t cap_soft = 96 * 1024, cap_hard = (size_t)max_optin_smem() - 1024;
+  g.dbuf = 0;
+  const size_t cap_soft = 111 * 1024, cap_hard = (size_t)max_optin_smem() - 1024;   // two CTAs per SM
   const int Kpad = round_up(g.K, g.KK);
   const int ntile = g.DP / TT;
   int KB = min(Kpad, 8 * g.KK);
@@ -842,14 +887,27 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
   if (fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_hard) return false;
   const size_t cap = fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_soft ? cap_hard : cap_soft;
   const int nkc = KB / g.KK;
-  // resident rows: fill whole rounds of the thread block (idle lanes in the last round are the waste)
+  // resident rows: fill whole rounds of the thread block (idle lanes in the last round are the waste).  Double
+  // buffering the rows is taken only when it costs no lane efficiency (it halves the rows that fit).
   int best = 1, bthr = 32; double beff = -1.0;
-  for (int NB = 1; NB <= min(g.B, 64); ++NB) {
-    if (fwd_smem_floats(g, NB, KB, ntile) * 4 > cap) break;
-    const int nitem = NB * ntile * nkc;
-    const int thr = min(kMaxThreads, round_up(nitem, 32));
-    const double e = (double)nitem / (double)(ceil_div(nitem, thr) * thr);
-    if (e > beff + 0.01) { beff = e; best = NB; bthr = thr; }
+  auto search = [&](int& obest, int& othr, double& oeff) {
+    obest = 1; othr = 32; oeff = -1.0;
+    for (int NB = 1; NB <= min(g.B, 64); ++NB) {
+      if (fwd_smem_floats(g, NB, KB, ntile) * 4 > cap) break;
+      const int nitem = NB * ntile * nkc;
+      const int thr = min(kMaxThreads, round_up(nitem, 32));
+      const double e = (double)nitem / (double)(ceil_div(nitem, thr) * thr);
+      if (e > oeff + 0.01) { oeff = e; obest = NB; othr = thr; }
+    }
+  };
+  g.dbuf = 0;
+  search(best, bthr, beff);
+  if (g.s == 1) {
+    int b2, t2; double e2;
+    g.dbuf = 1;
+    search(b2, t2, e2);
+    if (fwd_smem_floats(g, 1, KB, ntile) * 4 <= cap && e2 >= beff - 0.015) { best = b2; bthr = t2; beff = e2; }
+    else g.dbuf = 0;
   }
   g.KB = KB; g.nkb = ceil_div(Kpad, KB); g.NB = best;
   g.bpc = plan_bpc(g, g.M * g.nkb, best);
