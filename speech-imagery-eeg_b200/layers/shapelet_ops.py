@@ -191,7 +191,7 @@ class _ShapeletTransform(torch.autograd.Function):
     """One length group: window distance + pooling over time, with the saved-statistics backward."""
 
     @staticmethod
-    def forward(ctx, W, threshold, pack: SeriesPack, stride, eps, dist, pool, precision):
+    def forward(ctx, W, threshold, pack: SeriesPack, stride, eps, dist, pool, precision, track):
         xn = pack.xn
         B, M, T, Tp = pack.B, pack.M, pack.T, pack.Tp
         K, M2, L = W.shape
@@ -204,8 +204,10 @@ class _ShapeletTransform(torch.autograd.Function):
         desc = C.ShapeletDesc(B, M, T, Tp, K, L, int(stride), float(eps), C.DIST[dist], C.POOL[pool],
                               C.PRECISION[precision])
         st0, _ = pack.window_stats(dist, L, stride)
-        # (grad mode is always off inside Function.forward; needs_input_grad is False under torch.no_grad())
-        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        # Grad mode is always off inside Function.forward and needs_input_grad mirrors requires_grad even under
+        # torch.no_grad(), so the caller's grad mode is passed in: evaluation loops must not pay for the 1.9 GB of
+        # saved window distances.
+        need_grad = bool(track and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]))
         dev = xn.device
         out = torch.empty((2, B, K, M), dtype=torch.float32, device=dev)     # p, dmin
         idx = torch.empty((B, K, M), dtype=torch.int32, device=dev)         # argmin_t d
@@ -240,7 +242,7 @@ class _ShapeletTransform(torch.autograd.Function):
         if g_dmin is not None:
             raise NotImplementedError("ign_b200: gradient through the reported min distance is not implemented")
         if g_p is None:
-            return (None,) * 8
+            return (None,) * 9
         g = g_p.to(torch.float32).contiguous()
         dthr = None
         if ctx.pool == "lts_min":
@@ -259,7 +261,7 @@ class _ShapeletTransform(torch.autograd.Function):
                 C.check(STATS.call("shapelet_bwd/%s/L%d" % (ctx.dist, desc.L), 2, lambda: C.lib.ign_shapelet_backward(
                     byref(desc), _ptr(pack.xn), _ptr(st0), _ptr(st1), _ptr(Wc), _ptr(g), _ptr(dstore), _ptr(out[1]),
                     _ptr(idx), _ptr(dW), _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
-        return dW, dthr, None, None, None, None, None, None
+        return dW, dthr, None, None, None, None, None, None, None
 
 
 def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: float = 1.0, dist: str = "l1",
@@ -269,10 +271,11 @@ def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: 
     _check_device(W.device)
     if pool == "lts_min" and threshold is None:
         raise RuntimeError("lts_min pooling needs a threshold")
+    track = torch.is_grad_enabled()
     # fp32 in / fp32 out regardless of autocast: the reference's distance math stays fp32 under bf16
     # autocast as well.
     with torch.autocast(device_type="cuda", enabled=False):
-        return _ShapeletTransform.apply(W, threshold, pack, stride, eps, dist, pool, precision)
+        return _ShapeletTransform.apply(W, threshold, pack, stride, eps, dist, pool, precision, track)
 
 
 class _Diversity(torch.autograd.Function):
