@@ -17,7 +17,9 @@
 //
 // Precision: tcgen05 has no fp32 kind.  kind::tf32 reads fp32 bits and drops the low 13 mantissa bits, so
 // the "hi" operand is the raw fp32 value and lo = x - trunc_tf32(x) is formed by the producers.
-//   IGN_PREC_3XTF32: hi*hi + hi*lo + lo*hi  (3 MMAs per k-step, fp32-equivalent: error ~2^-21)
+//   IGN_PREC_3XTF32: hi*hi + hi*lo + lo*hi  (fp32-equivalent: error ~2^-21).  Three N-column MMAs per k-step, or —
+//                    for long tiles, which the issuing thread paces — two: A_hi x [B_hi | B_lo] (2N columns, the lo
+//                    image simply follows the hi image in the stage) and A_lo x B_hi; the epilogue adds the halves
 //   IGN_PREC_TF32  : hi*hi only             (own, looser tolerance)
 //
 //  * the shifted-shapelet operand depends only on (channel, k-block): a small pre-pass writes it to a workspace
@@ -79,6 +81,8 @@ struct TcGeo {
   int NKB;             // 32-wide k-blocks: ceil((L+15)/32)
   int XR;              // floats per series row in smem
   int nacc, accp;      // accumulators in flight and their TMEM column pitch
+  int stack;           // 3xTF32 with [B_hi | B_lo] stacked along N: two MMAs per k-step (N and 2N) instead of three
+  int nast, acol0;     // A ring depth in use (<= kAStages) and its first TMEM column
   int ncb;             // arg-min cell generations / finaliser barrier ids in flight: a power of two >= nacc + 2
   int nbs, resident;   // B ring depth; 1 = the ring holds every k-block of a (channel, shapelet block) run
   int tpm;             // sample tiles per (channel, shapelet block): ceil(B / RB)
@@ -392,7 +396,7 @@ __device__ __forceinline__ void finalize_tile(const TcGeo& g, const TcArgs& a, c
   }
 }
 
-template <int DIST>
+template <int DIST, bool STACK>
 __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const TcGeo g, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const long long t_entry = TC_CLK();
@@ -421,7 +425,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rowempty + 2);
 
   const uint32_t tmem_cols = 512;                                   // nacc accumulators in columns [0,256) + kAStages A stages
-  const uint32_t a_col0 = 256;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }   // 4 producer warps
@@ -451,8 +454,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       const int idx = a_i * kShifts + 4 * c;
       a_off[c] = a_bl < g.RB ? a_bl * g.XR + idx + 4 * (idx >> 5) : -1;
     }
-    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0;
+    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g.acol0;
     uint32_t it = 0;                                                 // global stage counter
+    int sidx = 0; uint32_t sph = 0;                                  // A ring slot / phase of stage `it`
     for (int w = wbeg; w < wend; ++w) {
       const int buf = (w - wbeg) & 1;
       const TileCoord tc = tile_coord(g, w);
@@ -464,9 +468,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       const float* xb = xbuf + (size_t)buf * g.RB * g.XR;
       const bool a_live = a_off[0] >= 0 && a_bl < nb;
       for (int kb = 0; kb < g.NKB; ++kb, ++it) {
+        const int s = sidx;
+        const uint32_t ph = sph;
+        if (++sidx == g.nast) { sidx = 0; sph ^= 1; }
         if ((int)(it & 1) != grp) continue;
-        const int s = it % kAStages;
-        const uint32_t ph = (it / kAStages) & 1;
         // A stage -> tensor memory: 32 columns of raw fp32 (the MMA truncates to tf32 = hi) and 32 of lo.
         // The shared-memory reads do not depend on the stage being free: issue them before the wait.
         float4 v[8];
@@ -554,15 +559,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
                              xs4[2].x, xs4[2].y, xs4[2].z, xs4[2].w, xs4[3].x, xs4[3].y, xs4[3].z, xs4[3].w};
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * g.accp);
       float* drow = (a.dstore && row_live) ? a.dstore + (((size_t)b * g.M + m) * g.K + k0) * g.Ts + t0 : nullptr;
-      uint32_t v[16];
-      if (half < g.KG) tmem_ld16(trow + half * 16, v);
+      uint32_t v[16], v2[16];
+      if (half < g.KG) { tmem_ld16(trow + half * 16, v); if (STACK) tmem_ld16(trow + g.N + half * 16, v2); }
 #pragma unroll 1
       for (int kl = half; kl < g.KG; kl += 2) {
         tmem_ld_wait();
         float raw[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) raw[j] = __uint_as_float(v[j]);
-        if (kl + 2 < g.KG) tmem_ld16(trow + (kl + 2) * 16, v);       // next shapelet's columns load under this one's math
+        if (STACK) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) raw[j] += __uint_as_float(v2[j]);      // + hi*lo term of the stacked form
+        }
+        if (kl + 2 < g.KG) {                                         // next shapelet's columns load under this one's math
+          tmem_ld16(trow + (kl + 2) * 16, v);
+          if (STACK) tmem_ld16(trow + g.N + (kl + 2) * 16, v2);
+        }
         const int k = k0 + kl;
         const float wst = wst_next;
         if (kl + 2 < g.KG) wst_next = __ldg(wsp + kl + 2);
@@ -628,7 +640,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       const uint32_t idesc = umma_idesc_tf32(kRows, g.N);
       const uint32_t bdesc0 = (smem_u32(stage0) & 0x3FFFFu) >> 4;    // descriptor low word of B stage 0, hi image
       const uint32_t bstage16 = (uint32_t)stage_bytes >> 4, bimg16 = (uint32_t)b_bytes >> 4;
-      const uint32_t a_tmem0 = tmem_base + a_col0;
+      const uint32_t a_tmem0 = tmem_base + (uint32_t)g.acol0;
+      const uint32_t idesc2 = umma_idesc_tf32(kRows, 2 * g.N);        // stacked [B_hi | B_lo] form
       // ring positions and phases are carried incrementally: no divisions in the issue loop
       int sa = 0, sbr = 0, acc = 0;
       uint32_t pha = 0, phb = 0, phacc = 0;
@@ -664,7 +677,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
           const uint32_t bd_hi = bdesc0 + (uint32_t)sbi * bstage16;
           const uint32_t bd_lo = bd_hi + bimg16;
           const uint32_t a_hi = a_tmem0 + sa * kAStageCols, a_lo = a_hi + 32;
-          if (g.split) {
+          if (STACK) {
+            // the lo image follows the hi image in the stage (80-row multiples of the 1024-byte swizzle atom), so a
+            // 2N-row descriptor over the hi image IS [B_hi | B_lo]: columns [0,N) collect hi*hi + lo*hi, [N,2N) hi*lo
+#pragma unroll
+            for (int k8 = 0; k8 < kKBlock / 8; ++k8) {
+              umma_tf32_ts_lo(d_tmem, a_hi + k8 * 8, bd_hi + 2 * k8, idesc2, (kb | k8) != 0);
+              umma_tf32_ts_lo(d_tmem, a_lo + k8 * 8, bd_hi + 2 * k8, idesc, 1);
+            }
+          } else if (g.split) {
 #pragma unroll
             for (int k8 = 0; k8 < kKBlock / 8; ++k8) {               // small terms first; 8 tf32 = 32 bytes = 2 units
               umma_tf32_ts_lo(d_tmem, a_lo + k8 * 8, bd_hi + 2 * k8, idesc, (kb | k8) != 0);
@@ -679,7 +700,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
           umma_commit(&emptyA[sa]);                                  // A stage reusable once these MMAs retire
           if (!g.resident || rf.last) umma_commit(&emptyB[sbi]);
           TC_ADD(6, tm0);
-          if (++sa == kAStages) { sa = 0; pha ^= 1; }
+          if (++sa == g.nast) { sa = 0; pha ^= 1; }
           if (++sbr == g.nbs) { sbr = 0; phb ^= 1; }
         }
         umma_commit(&tfull[acc]);                                    // accumulator complete
@@ -809,6 +830,12 @@ static void tc_geo(const ign_shapelet_desc& d, TcGeo& g) {
   g.nacc = (g.NKB <= 7 && g.N <= 80) ? 3 : 2;
   g.accp = g.nacc == 3 ? 80 : kAccCols;
   g.ncb = g.nacc == 3 ? 8 : 4;
+  g.stack = 0; g.nast = kAStages; g.acol0 = 256;
+  // Long tiles are paced by the MMA-issuing thread: with [B_hi | B_lo] stacked along N the 3xTF32 product takes two
+  // MMAs per k-step (2N and N columns) instead of three.  Two 2N-column accumulators + three A stages fill TMEM.
+  if (g.split && g.nacc == 2 && 4 * g.N + 3 * kAStageCols <= 512) {
+    g.stack = 1; g.accp = 2 * g.N; g.acol0 = 4 * g.N; g.nast = min(kAStages, (512 - g.acol0) / kAStageCols);
+  }
   g.nbs = 2; g.resident = 0;
 }
 
@@ -852,8 +879,12 @@ int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   const size_t smem = max(tc_smem_fixed(g) + g.nbs * tc_stage_bytes(g), (size_t)118 * 1024);   // > half the SM: one CTA per SM
   TcArgs a{xn, st0, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, 1), btiles, wstat};
   const int grid = min(sm_count(), g.ntiles);
-  auto kern = d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2>
-            : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE> : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON>;
+  auto kern = g.stack ? (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, true>
+                         : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, true>
+                                                     : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON, true>)
+                      : (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, false>
+                         : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, false>
+                                                     : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON, false>);
   IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreadsTC, smem, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
