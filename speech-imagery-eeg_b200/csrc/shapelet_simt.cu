@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
   // so the load of pass i+1 hides under the distance loop of pass i (the exposed load + barrier phases cost short
   // shapelets ~8 %: FMA pipe 74 % at L=100 against 82 % at L=500 before this change).
   const bool dbuf = g.dbuf != 0;
-  const int xs_sz = g.NB * g.s * g.XQ, st_sz = (OP != OP_L1) ? g.NB * g.DP : 0;
+  const int xs_sz = g.NB * g.s * g.XQ;
   float* xs1 = smem + round_up((int)(cand_d - smem) + 2 * g.NB * g.KB * ntile, 4);   // second buffers, 16-byte aligned, behind the candidates
   float* st1 = xs1 + (dbuf ? xs_sz : 0);
   auto prefetch = [&](int b0, int buf) {
