@@ -93,9 +93,22 @@ def data_provider(args, flag):
     """flag in {'train','val','test'} (reference data_factory.py:29).  Under data-parallel training the
     train split is sharded by rank (every rank draws a disjoint seeded shard)."""
     real_root = getattr(args, "root_path", None)
-    if args.data != "synthetic" and real_root and os.path.isdir(real_root):
+    if args.data == "UEA" and real_root and os.path.isdir(real_root):
+        # real archive on disk: the sktime-free .ts reader with the reference's preprocessing (data_provider/uea.py)
+        from data_provider import uea
+        ds = uea.UEADataset(real_root, flag=flag)
+        world, rank = getattr(args, "world_size", 1), getattr(args, "rank", 0)
+        if flag == "train" and world > 1:                      # data parallel: disjoint shard per rank
+            keep = list(range(rank, len(ds), world))
+            ds.x, ds.y = [ds.x[i] for i in keep], ds.y[keep]
+        max_len = int(getattr(args, "seq_len", 0) or ds.max_seq_len)
+        loader = DataLoader(ds, batch_size=args.batch_size, shuffle=(flag == "train"), num_workers=args.num_workers,
+                            drop_last=False, collate_fn=lambda b: uea.collate_fn(b, max_len=max_len),
+                            pin_memory=torch.cuda.is_available())
+        return ds, loader
+    if args.data in ("EEG", "EEG3") and real_root and os.path.isdir(real_root):
         raise NotImplementedError(
-            "real UEA/.fif ingestion is outside the B200 hot path (SURVEY.md §8 f3); use --data synthetic")
+            "CHISCO .fif ingestion (mne) is outside the B200 hot path (SURVEY.md §8 f3); use --data synthetic")
     channels, seq_len, num_class = _shape_for(args)
     n = {"train": getattr(args, "syn_train", 512), "val": getattr(args, "syn_val", 128),
          "test": getattr(args, "syn_test", 128)}[flag]
