@@ -63,6 +63,9 @@ size_t shapelet_fwd_tc_workspace(const ign_shapelet_desc& d);
 int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const float* st0,
                            const float* W, const float* thr, float* p, float* dmin, int* argmin, float* dstore,
                            void* ws, size_t ws_bytes, cudaStream_t st);
+bool shapelet_bwd_tc_supported(const ign_shapelet_desc& d);
+int shapelet_bwd_tc_chunks(const ign_shapelet_desc& d);
+int launch_shapelet_bwd_tc(const ign_shapelet_desc& d, const float* xn, const float* coef, float* part, cudaStream_t st);
 int launch_gate_fwd(const float* s, const float* z, float* out, float* eta, int B, int C, int use_gate,
                     float gv, cudaStream_t st);
 int launch_gate_bwd(const float* s, const float* z, const float* go, const float* ge, float* gs,

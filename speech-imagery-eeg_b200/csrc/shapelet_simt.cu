@@ -1020,7 +1020,8 @@ struct BwdWorkspace { size_t part, coef, rowsc, wstat, tie, total; };   // offse
 BwdWorkspace bwd_workspace(const ign_shapelet_desc& d, const Geo& g, const BwdPlan& bp) {
   BwdWorkspace w;
   w.part = 0;
-  w.coef = (size_t)bp.nchunk * d.K * d.M * d.L;
+  const int nchunk = shapelet_bwd_tc_supported(d) ? max(bp.nchunk, shapelet_bwd_tc_chunks(d)) : bp.nchunk;
+  w.coef = (size_t)nchunk * d.K * d.M * d.L;
   w.coef = (w.coef + 3) / 4 * 4;                         // 16-byte aligned rows
   w.rowsc = w.coef + (size_t)d.B * d.M * d.K * g.Ts;
   w.wstat = w.rowsc + (size_t)d.B * d.M * d.K * 2;
@@ -1077,7 +1078,16 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
 #undef IGN_POOL_LAUNCH
     IGN_CUDA(cudaGetLastError());
   }
-  // 2. contraction with the series (FP32 pipe) into per-chunk partials
+  // 2. contraction with the series into per-chunk partials: tensor pipe for the cross-term modes in the tcgen05
+  //    precisions (shapelet_tc_bwd.cu), FP32 pipe otherwise
+  if (shapelet_bwd_tc_supported(d)) {
+    int rc = launch_shapelet_bwd_tc(d, xn, base + wo.coef, base + wo.part, st);
+    if (rc) return rc;
+    shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
+                                                                d.M, d.L, shapelet_bwd_tc_chunks(d), d.dist);
+    IGN_CUDA(cudaGetLastError());
+    return IGN_OK;
+  }
   const unsigned char* tie = nullptr;
   if (d.dist == IGN_DIST_L1 && bp.hcap) {
     unsigned char* tflags = reinterpret_cast<unsigned char*>(base + wo.tie);
