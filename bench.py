@@ -387,9 +387,10 @@ def main():
         r = {"kernel": fam, "launches": f["launches"], "avg_ms": avg_ms, "share_of_step": f["ms"] / ms_kernel_region}
         if f["ops"]:
             ach = f["ops"] / (f["ms"] * 1e-3) / 1e12
-            if fam == "shapelet_fwd" and not l1 and a.precision in ("3xtf32", "tf32"):
-                # cross term on the tcgen05 pipe: algorithmic 2E flop against the TF32 peak (= half the measured bf16
-                # cuBLAS rate); the 3xTF32 split executes three MMAs per algorithmic multiply-add
+            if fam in ("shapelet_fwd", "shapelet_bwd") and not l1 and a.precision in ("3xtf32", "tf32"):
+                # cross term (forward) / coefficient contraction (backward, incl. its HBM-bound pooling pass) on the
+                # tcgen05 pipe: algorithmic 2E flop against the TF32 peak (= half the measured bf16 cuBLAS rate); the
+                # 3xTF32 split executes three MMAs per algorithmic multiply-add
                 peak = bf16_peak / 2.0
                 r.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
                          mma_passes=3 if a.precision == "3xtf32" else 1,

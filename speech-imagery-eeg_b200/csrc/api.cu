@@ -72,7 +72,10 @@ int32_t ign_device_check(int32_t device) {
 }
 
 int32_t ign_debug_tc_trace(int64_t* host, int32_t n) { return tc_trace_read(reinterpret_cast<long long*>(host), n); }
-int32_t ign_debug_tc_profile(uint64_t* host16, int32_t reset) { return tc_profile_read(reinterpret_cast<unsigned long long*>(host16), reset); }
+int32_t ign_debug_tc_profile(uint64_t* host16, int32_t reset) {
+  if (reset & 2) return bwd_tc_profile_read(reinterpret_cast<unsigned long long*>(host16), reset & 1);   // backward kernel's counters
+  return tc_profile_read(reinterpret_cast<unsigned long long*>(host16), reset);
+}
 int32_t ign_padded_len(int32_t T) { return padded_len(T); }
 int32_t ign_num_windows(int32_t T, int32_t L, int32_t stride) { return (L <= 0 || stride <= 0) ? 0 : num_windows(T, L, stride); }
 int32_t ign_padded_windows(int32_t T, int32_t L, int32_t stride) { return (L <= 0 || stride <= 0) ? 0 : padded_windows(T, L, stride); }

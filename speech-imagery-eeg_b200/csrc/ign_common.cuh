@@ -58,6 +58,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
                              cudaStream_t st);
 int tc_profile_read(unsigned long long* host16, int reset);
 int tc_trace_read(long long* host, int n);
+int bwd_tc_profile_read(unsigned long long* host16, int reset);
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d);
 size_t shapelet_fwd_tc_workspace(const ign_shapelet_desc& d);
 int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const float* st0,

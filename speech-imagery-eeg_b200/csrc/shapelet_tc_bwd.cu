@@ -41,6 +41,24 @@ constexpr int kBAStageCols = 64;       // 32 hi + 32 lo
 constexpr int kBACol0 = 256;           // accumulators live in columns [0,256), A' stages behind them
 constexpr int kBChunk = 32;            // samples per item
 
+// role-level wait accounting (debug builds only: -DIGN_TC_PROFILE); slots: 0 prod wait row, 1 prod wait emptyA,
+// 2 build wait emptyB, 3 mma wait fullB, 4 mma wait fullA, 5 mma wait accempty, 6 drain wait accfull, 7 loader wait
+// rowempty, 8 prod total, 9 build total, 10 mma total, 11 loader total
+#ifdef IGN_TC_PROFILE
+__device__ unsigned long long g_bwd_prof[16];
+#define BP_CLK() clock64()
+#define BP_ADD(slot, t0) (bp_local[slot] += (unsigned long long)(clock64() - (t0)))
+#define BP_DECL() unsigned long long bp_local[16] = {0}
+#define BP_FLUSH() do { for (int i_ = 0; i_ < 16; ++i_) if (bp_local[i_]) atomicAdd(&g_bwd_prof[i_], bp_local[i_]); } while (0)
+#else
+#define BP_CLK() 0ll
+#define BP_ADD(slot, t0) ((void)(t0))
+#define BP_DECL() ((void)0)
+#define BP_FLUSH() ((void)0)
+#endif
+
+__device__ __forceinline__ bool bp_any(long long) { return true; }
+
 struct BwdTcGeo {
   int B, M, T, Tp, K, L;
   int Tw, Ts;          // windows, coefficient row pitch
@@ -69,6 +87,8 @@ __device__ __forceinline__ ItemCoord item_coord(const BwdTcGeo& g, int w) {
 __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const BwdTcGeo g, const BwdTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  BP_DECL();
+  const long long t_entry = BP_CLK();
   const int wbeg = (int)(((long long)g.nitems * blockIdx.x) / gridDim.x);
   const int wend = (int)(((long long)g.nitems * (blockIdx.x + 1)) / gridDim.x);
 
@@ -119,7 +139,9 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
       for (int b = b0; b < b1; ++b, ++nrow) {
         const int buf = nrow & 1;
+        long long t0 = BP_CLK();
         mbar_wait(&rowfull[buf], (nrow >> 1) & 1);
+        BP_ADD(0, t0);
         const float* xs = xrow + (size_t)buf * g.XR;
         for (int kb = 0; kb < g.NKB; ++kb) {
           for (int mt = 0; mt < g.MT; ++mt, ++ia) {
@@ -136,7 +158,9 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
               hi[c] = __float_as_uint(v);
               lo[c] = __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u));
             }
+            t0 = BP_CLK();
             mbar_wait(&emptyA[s], ph ^ 1);
+            BP_ADD(1, t0);
             tc_fence_after();
             tmem_st32(a_lane + s * kBAStageCols, hi);
             if (g.split) tmem_st32(a_lane + s * kBAStageCols + 32, lo);
@@ -151,7 +175,9 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       }
       // ---- drain (warps 0-3): G[k,l] = sum_j Gsh[l+j,(k,j)], one shapelet at a time through shared memory
       if (warp < 4) {
+        long long t1 = BP_CLK();
         mbar_wait(accfull, item_no & 1);
+        BP_ADD(6, t1);
         tc_fence_after();
         const int k0 = ic.kblk * g.KG;
         const int et = threadIdx.x;                                  // 0..127
@@ -214,8 +240,15 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       if (++ckb == g.NKB) { ckb = 0; if (++cb == cb1) { ++cw; enter_item(); } }
     };
     enter_item();
+    long long todo = 0;                                              // tiles this CTA builds
+    for (int w2 = wbeg; w2 < wend; ++w2) {
+      const ItemCoord c2 = item_coord(g, w2);
+      todo += (long long)(min(g.B, c2.chunk * kBChunk + kBChunk) - c2.chunk * kBChunk) * g.NKB;
+    }
     auto emit = [&](const float4 (&v)[2][2]) {                       // write one tile from registers, publish it
+      long long t0 = BP_CLK();
       mbar_wait(&emptyB[sb], phb ^ 1);
+      BP_ADD(2, t0);
       uint8_t* st = stage0 + (size_t)sb * stage_bytes;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -236,17 +269,26 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       if (lane == 0) mbar_arrive(&fullB[sb]);
       if (++sb == kBBStages) { sb = 0; phb ^= 1; }
     };
-    // ping-pong register sets, unrolled by two: a register copy between the sets would wait for the loads it copies
-    float4 va[2][2], vb[2][2];
+    // three register sets, unrolled by three: the loads of tiles i+1 and i+2 are in flight while tile i is written
+    // (the coefficients stream from HBM: one tile of prefetch distance left the latency exposed, builders 85 % busy at
+    // L=100), and no register copy between the sets ever waits for a load
+    float4 va[2][2], vb[2][2], vc[2][2];
     fetch(va);
-    while (cw < wend) {
-      advance();
-      fetch(vb);                                                     // next tile's loads in flight
+    advance();
+    fetch(vb);
+    while (true) {
+      if (cw < wend) advance();
+      fetch(vc);
       emit(va);
-      if (cw >= wend) break;
-      advance();
+      if (--todo == 0) break;
+      if (cw < wend) advance();
       fetch(va);
       emit(vb);
+      if (--todo == 0) break;
+      if (cw < wend) advance();
+      fetch(vb);
+      emit(vc);
+      if (--todo == 0) break;
     }
   } else if (warp == kBMmaWarp) {
     // =================================================================== MMA ISSUER
@@ -260,15 +302,21 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       for (int w = wbeg; w < wend; ++w, ++item_no) {
         const ItemCoord ic = item_coord(g, w);
         const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
+        long long t0 = BP_CLK();
         mbar_wait(accempty, (item_no & 1) ^ 1);                      // the previous item's accumulators are drained
+        BP_ADD(5, t0);
         tc_fence_after();
         for (int b = b0; b < b1; ++b) {
           for (int kb = 0; kb < g.NKB; ++kb) {
+            t0 = BP_CLK();
             mbar_wait(&fullB[sb], phb);
+            BP_ADD(3, t0);
             const uint32_t bd_hi = bdesc0 + (uint32_t)sb * bstage16, bd_lo = bd_hi + bimg16;
             const bool first = (b == b0) && (kb == 0);
             for (int mt = 0; mt < g.MT; ++mt) {
+              t0 = BP_CLK();
               mbar_wait(&fullA[sa], pha);
+              BP_ADD(4, t0);
               tc_fence_after();
               const uint32_t d_tmem = tmem_base + (uint32_t)(mt * g.N);
               const uint32_t a_hi = tmem_base + kBACol0 + sa * kBAStageCols, a_lo = a_hi + 32;
@@ -304,7 +352,9 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
       for (int b = b0; b < b1; ++b, ++nrow) {
         const int buf = nrow & 1;
+        long long t0 = BP_CLK();
         if (nrow >= 2) mbar_wait(&rowempty[buf], ((nrow >> 1) - 1) & 1);
+        BP_ADD(7, t0);
         const float* src = a.xn + ((size_t)b * g.M + ic.m) * g.Tp;
         float* dst = xrow + (size_t)buf * g.XR;
         for (int c = lane; c < chunks; c += 32) cp_async16(dst + c * 4, src + c * 4);
@@ -317,6 +367,12 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
     }
   }
 
+  if (lane == 0 || (warp == kBMmaWarp)) {
+    if (warp == 0) { BP_ADD(8, t_entry); BP_FLUSH(); }
+    else if (warp == kBProdWarps && lane == 0) { BP_ADD(9, t_entry); BP_FLUSH(); }
+    else if (warp == kBMmaWarp) { if (bp_any(BP_CLK())) { BP_ADD(10, t_entry); BP_FLUSH(); } }
+    else if (warp == kBRowWarp) { BP_ADD(11, t_entry); BP_FLUSH(); }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kBMmaWarp) tmem_dealloc(tmem_base, 512);
@@ -341,6 +397,18 @@ size_t bwd_tc_smem(const BwdTcGeo& g) {
 }
 
 }  // namespace
+
+int bwd_tc_profile_read(unsigned long long* host16, int reset) {
+#ifdef IGN_TC_PROFILE
+  IGN_CUDA(cudaMemcpyFromSymbol(host16, g_bwd_prof, sizeof(unsigned long long) * 16));
+  if (reset) { unsigned long long z[16] = {0}; IGN_CUDA(cudaMemcpyToSymbol(g_bwd_prof, z, sizeof(z))); }
+  return IGN_OK;
+#else
+  (void)host16; (void)reset;
+  set_error("library built without -DIGN_TC_PROFILE");
+  return IGN_ERR_UNSUPPORTED;
+#endif
+}
 
 // the tensor-core contraction covers: cross-term distances, unit stride, the tcgen05 operand modes, L + 7 <= 512
 bool shapelet_bwd_tc_supported(const ign_shapelet_desc& d) {
