@@ -27,6 +27,18 @@ int max_optin_smem() {
   return cached;
 }
 
+int max_smem_per_sm() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess && v > 0)
+      cached = v;
+    else { cudaGetLastError(); return 228 * 1024; }
+  }
+  return cached;
+}
+
 int sm_count() {
   static int cached = 0;
   if (!cached) {

@@ -78,6 +78,7 @@ int launch_diversity_bwd(const float* W, const float* coef, const float* gout, f
                          cudaStream_t st);
 
 int max_optin_smem();  // per-block opt-in shared memory of the current device (cached)
+int max_smem_per_sm();  // shared memory of one SM (each resident CTA also reserves 1 KB of it)
 int sm_count();
 
 }  // namespace ign

@@ -38,6 +38,12 @@
 #include "ign_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <utility>
 
 namespace ign {
 namespace {
@@ -59,10 +65,18 @@ struct Geo {  // geometry shared by forward and backward
   int KK, KB, nkb;
   int NB;      // series rows resident per pass
   int dbuf;    // forward: series rows double buffered (cp.async one pass ahead)
-  int bpc;     // samples per batch chunk
+  int nchunk, cbase, cextra;   // batch chunks (grid z): chunk c walks cbase (+1 if c < cextra) passes of NB rows
   int dist, pool;
   float eps;
 };
+
+// samples [bbeg, bend) of batch chunk c: balanced chunks, the longer ones first (they are dispatched first)
+__device__ __forceinline__ void chunk_range(const Geo& g, int c, int& bbeg, int& bend) {
+  const int u0 = c * g.cbase + min(c, g.cextra);
+  const int nu = g.cbase + (c < g.cextra ? 1 : 0);
+  bbeg = min(g.B, u0 * g.NB);
+  bend = min(g.B, (u0 + nu) * g.NB);
+}
 
 struct FwdArgs {
   const float* xn; const float* st0; const float* W; const float* thr;   // st0: window statistics [B,M,SP]
@@ -294,7 +308,8 @@ template <int OP, int KK, int TT>
 __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo g, const FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int m = blockIdx.x, k0 = blockIdx.y * g.KB;
-  const int bbeg = blockIdx.z * g.bpc, bend = min(g.B, bbeg + g.bpc);
+  int bbeg, bend;
+  chunk_range(g, blockIdx.z, bbeg, bend);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
 
   const int ntile = g.DP / TT;
@@ -557,6 +572,190 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   }
 }
 
+// Register-resident variant for rows of at most NCH*128 windows (every geometry with T' <= 1024, i.e. all BASELINE
+// configs below T = 2000).  The generic kernel above spends 37 issue slots per element — two passes that each
+// evaluate both exponentials — and is issue-bound at 65 % of HBM peak.  Here each lane owns NCH float4 chunks of the
+// row; pass 1 evaluates the exponentials once and keeps (U_t, V_t) in registers with
+//     c_t = Kc * U_t * (V_t - vbar) + [t == ih] * fix
+//   rbf_max: V = p' = log2(e) p_t,  U = e^{p_t} p' d_t,  vbar = sum(e^p p')/Z,  Kc = -2 eps^2 g / (Z log2(e)^2),  fix = -2 eps^2 g p_ih d_ih
+//   lts_min: V = d_t,  U = e^{dmin - d_t},  vbar = sum(U d)/Z,  Kc = -g/Z,  fix = g
+// so pass 2 is three FP32 instructions per element over registers, all shared-memory and global accesses are
+// 128-bit, and the arg-max is tracked per chunk (3 FMNMX + one compare per four elements, the position inside the
+// chunk is resolved once per row).  Rows are prefetched two ahead (three cp.async stages per warp).
+constexpr int kPoolStages = 3;
+constexpr float kLog2Log2e = 0.5287663729448977f;     // log2(log2(e))
+
+__device__ __forceinline__ float rbf_pprime(float d, float q) {   // log2(e) * exp(-(eps d)^2), q = -eps^2 log2(e)
+  return fast_ex2(__fmaf_rn(__fmul_rn(d, q), d, kLog2Log2e));
+}
+
+// mode factor of one coefficient (the pool-independent part of the generic kernel's inner loop)
+template <int DIST>
+__device__ __forceinline__ float pool_emit(float c, float d, float s0, float s1, float wst, float& sc0, float& sc1) {
+  if (DIST == IGN_DIST_L1 || DIST == IGN_DIST_SQL2) { sc0 += c; return c; }
+  if (DIST == IGN_DIST_COSINE) { sc0 = fmaf(c, 1.f - d, sc0); return c * s0; }
+  const float D = s0 * wst + 1e-8f;                      // s0 = ||x_w-mu||, s1 = mu, wst = ||w-mean||
+  const float coef = __fdividef(c, D);
+  sc0 = fmaf(coef, s1, sc0);
+  sc1 += __fdividef(c * (1.f - d) * s0, wst * D);
+  return coef;
+}
+
+// Lane layout of a row: `nfull` whole 128-window chunks (lane owns the float4 at (j*32+lane)*4), then the remaining
+// < 128 windows in scalar sub-chunks of 32 (lane owns window tail0 + s*32 + lane), kept in the last register slot —
+// a nearly empty float4 chunk would cost the whole warp four element times (T' = 901: 14 % of the row's work).
+template <int POOL, int DIST, int NCH>
+__global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const PoolArgs a, int rows) {
+  extern __shared__ __align__(16) float prow[];          // [warps][kPoolStages][DP]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int wstride = gridDim.x * nwarp;
+  float* slot = prow + (size_t)warp * kPoolStages * g.DP;
+  auto prefetch = [&](int r, int buf) {                  // always commits a group, possibly empty
+    if (r < rows) {
+      const float* src = a.dstore + (size_t)r * g.Ts;
+      float* dstp = slot + (size_t)buf * g.DP;
+      for (int t = lane * 4; t < g.Ts; t += 128) cp_async16_pool(dstp + t, src + t);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const float eps = g.eps;
+  const float q = -eps * eps * kLog2e;
+  const int nfull = g.Tw >> 7, tail0 = nfull << 7, ntail = g.Tw - tail0;   // nfull + (ntail > 0) <= NCH
+  const int tt = tail0 + lane;
+  int row = blockIdx.x * nwarp + warp;
+  prefetch(row, 0);
+  prefetch(row + wstride, 1);
+  int buf = 0;
+  for (; row < rows; row += wstride, buf = buf == kPoolStages - 1 ? 0 : buf + 1) {
+    prefetch(row + 2 * wstride, buf >= 1 ? buf - 1 : kPoolStages - 1);   // stage (buf + 2) % 3
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    const float* dr = slot + (size_t)buf * g.DP;
+    const float4* d4 = reinterpret_cast<const float4*>(dr);
+    const int k = row % g.K, bm = row / g.K;
+    const int m = bm % g.M, b = bm / g.M;
+    const size_t o = ((size_t)b * g.K + k) * g.M + m;
+    const float gk = a.g[o];
+    float sl2 = 0.f;
+    int ih = 0;
+    if (POOL == IGN_POOL_LTS_MIN) { sl2 = a.dmin[o] * kLog2e; ih = a.argmin[o]; }
+
+    // ---- pass 1: exponentials once, (U, V) to registers, soft-max statistics, chunk-wise arg-max
+    float4 U[NCH], V[NCH];
+    float Zs = 0.f, S1s = 0.f, pmx = 0.f;
+    int jmx = -1;
+    auto eval = [&](float d, float& u, float& v) {
+      if (POOL == IGN_POOL_RBF_MAX) {
+        v = rbf_pprime(d, q);
+        const float e = fast_ex2(v);
+        Zs += e; S1s = fmaf(e, v, S1s);
+        u = e * v * d;
+      } else {
+        u = fast_ex2(fmaf(d, -kLog2e, sl2));
+        v = d;
+        Zs += u; S1s = fmaf(u, d, S1s);
+      }
+    };
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      U[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      V[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < nfull) {
+        const float4 d = d4[j * 32 + lane];
+        eval(d.x, U[j].x, V[j].x); eval(d.y, U[j].y, V[j].y); eval(d.z, U[j].z, V[j].z); eval(d.w, U[j].w, V[j].w);
+        if (POOL == IGN_POOL_RBF_MAX) {
+          const float m4 = fmaxf(fmaxf(V[j].x, V[j].y), fmaxf(V[j].z, V[j].w));
+          if (jmx < 0 || m4 > pmx) { pmx = m4; jmx = j; }
+        }
+      }
+    }
+#define IGN_POOL_TAIL1(S, UC, VC)                                                              \
+    if ((S) * 32 < ntail && tt + (S) * 32 < g.Tw) {                                            \
+      eval(dr[tt + (S) * 32], UC, VC);                                                         \
+      if (POOL == IGN_POOL_RBF_MAX) { if (jmx < 0 || VC > pmx) { pmx = VC; jmx = NCH + (S); } } \
+    }
+    IGN_POOL_TAIL1(0, U[NCH - 1].x, V[NCH - 1].x)
+    IGN_POOL_TAIL1(1, U[NCH - 1].y, V[NCH - 1].y)
+    IGN_POOL_TAIL1(2, U[NCH - 1].z, V[NCH - 1].z)
+    IGN_POOL_TAIL1(3, U[NCH - 1].w, V[NCH - 1].w)
+#undef IGN_POOL_TAIL1
+    float fix;
+    if (POOL == IGN_POOL_RBF_MAX) {
+      // first arg-max of p (the reference's hard one-hot, Shapelet.py:79): position inside the lane's best chunk, then
+      // across lanes (largest p, smallest index).  p' >= 0, so its bit pattern orders like the value.
+      int imx = 0x7fffffff;
+      if (jmx >= NCH) {
+        imx = tt + (jmx - NCH) * 32;
+      } else if (jmx >= 0) {
+        const int t0 = (jmx * 32 + lane) * 4;
+        const float4 d = d4[jmx * 32 + lane];
+        if (rbf_pprime(d.w, q) == pmx) imx = t0 + 3;
+        if (rbf_pprime(d.z, q) == pmx) imx = t0 + 2;
+        if (rbf_pprime(d.y, q) == pmx) imx = t0 + 1;
+        if (rbf_pprime(d.x, q) == pmx) imx = t0;
+      }
+      const unsigned bits = __float_as_uint(pmx);
+      const unsigned vmax = __reduce_max_sync(0xffffffffu, bits);
+      ih = (int)__reduce_min_sync(0xffffffffu, bits == vmax ? (unsigned)imx : 0x7fffffffu);
+      const float dh = dr[ih];
+      fix = gk * (-2.f * eps * eps) * (rbf_pprime(dh, q) * (1.f / kLog2e)) * dh;
+    } else {
+      fix = gk;
+    }
+    Zs = warp_sum(Zs); S1s = warp_sum(S1s);
+    const float invZ = 1.f / Zs, vbar = S1s * invZ;
+    const float Kc = POOL == IGN_POOL_RBF_MAX ? gk * (-2.f * eps * eps) * invZ * (1.f / (kLog2e * kLog2e)) : -gk * invZ;
+
+    // ---- pass 2: coefficients from registers, mode factor, 128-bit stores
+    const float wst = (DIST == IGN_DIST_PEARSON) ? a.wstat[(size_t)k * g.M + m] : 0.f;
+    const float* s0r = a.st0 + (size_t)bm * a.SP;          // SP % 16 == 0: float4-aligned rows
+    const float* s1r = a.st1 + (size_t)bm * a.SP;
+    float* dst = a.coef + (size_t)row * g.Ts;
+    float sc0 = 0.f, sc1 = 0.f;
+    constexpr bool kStats = DIST == IGN_DIST_COSINE || DIST == IGN_DIST_PEARSON;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (j < nfull) {
+        const int t0 = (j * 32 + lane) * 4;
+        float c0 = Kc * U[j].x * (V[j].x - vbar), c1 = Kc * U[j].y * (V[j].y - vbar);
+        float c2 = Kc * U[j].z * (V[j].z - vbar), c3 = Kc * U[j].w * (V[j].w - vbar);
+        const int hc = ih - t0;
+        if ((unsigned)hc < 4u) {
+          c0 += hc == 0 ? fix : 0.f; c1 += hc == 1 ? fix : 0.f; c2 += hc == 2 ? fix : 0.f; c3 += hc == 3 ? fix : 0.f;
+        }
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f), s0 = d, s1 = d;
+        if (kStats) { d = d4[j * 32 + lane]; s0 = *reinterpret_cast<const float4*>(s0r + t0); }
+        if (DIST == IGN_DIST_PEARSON) s1 = *reinterpret_cast<const float4*>(s1r + t0);
+        float4 out;
+        out.x = pool_emit<DIST>(c0, d.x, s0.x, s1.x, wst, sc0, sc1);
+        out.y = pool_emit<DIST>(c1, d.y, s0.y, s1.y, wst, sc0, sc1);
+        out.z = pool_emit<DIST>(c2, d.z, s0.z, s1.z, wst, sc0, sc1);
+        out.w = pool_emit<DIST>(c3, d.w, s0.w, s1.w, wst, sc0, sc1);
+        *reinterpret_cast<float4*>(dst + t0) = out;
+      }
+    }
+#define IGN_POOL_TAIL2(S, UC, VC)                                                              \
+    if ((S) * 32 < ntail && tt + (S) * 32 < g.Tw) {                                            \
+      const int t = tt + (S) * 32;                                                             \
+      float c = Kc * UC * (VC - vbar);                                                         \
+      if (t == ih) c += fix;                                                                   \
+      dst[t] = pool_emit<DIST>(c, kStats ? dr[t] : 0.f, kStats ? s0r[t] : 0.f,                 \
+                               DIST == IGN_DIST_PEARSON ? s1r[t] : 0.f, wst, sc0, sc1);        \
+    }
+    IGN_POOL_TAIL2(0, U[NCH - 1].x, V[NCH - 1].x)
+    IGN_POOL_TAIL2(1, U[NCH - 1].y, V[NCH - 1].y)
+    IGN_POOL_TAIL2(2, U[NCH - 1].z, V[NCH - 1].z)
+    IGN_POOL_TAIL2(3, U[NCH - 1].w, V[NCH - 1].w)
+#undef IGN_POOL_TAIL2
+    if (lane < g.Ts - g.Tw) dst[g.Tw + lane] = 0.f;                  // pad windows (at most 3)
+    sc0 = warp_sum(sc0);
+    if (DIST == IGN_DIST_PEARSON) sc1 = warp_sum(sc1);
+    if (lane == 0) { a.rowsc[(size_t)row * 2] = sc0; a.rowsc[(size_t)row * 2 + 1] = sc1; }
+    __syncwarp();                                       // everyone is done with this stage before it is refilled
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ||w - mean|| per (k, m) shapelet row (pearson backward).  One warp per row.
 __global__ void __launch_bounds__(256) shapelet_centred_norm_kernel(const float* __restrict__ W,
                                                                    float* __restrict__ wstat, int rows, int L) {
@@ -638,7 +837,8 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   const int kblk = blockIdx.y / a.nlb, lblk = blockIdx.y - kblk * a.nlb;
   const int k0 = kblk * g.KB;
   const int chunk = blockIdx.z;
-  const int bbeg = chunk * g.bpc, bend = min(g.B, bbeg + g.bpc);
+  int bbeg, bend;
+  chunk_range(g, chunk, bbeg, bend);
   const int nthr = blockDim.x;
 
   const int ntl_all = g.s * g.LQ / LT;                    // l-tiles over all residues
@@ -861,11 +1061,43 @@ bool base_geo(const ign_shapelet_desc& d, Geo& g) {
   return g.Tw > 0;
 }
 
-int plan_bpc(const Geo& g, int ctas_per_bchunk, int NB) {
-  const int target = 24 * sm_count();
-  int nchunk = max(1, ceil_div(target, max(1, ctas_per_bchunk)));
-  nchunk = min(nchunk, ceil_div(g.B, NB));
-  return round_up(ceil_div(g.B, nchunk), NB);
+// Resident CTAs per SM of `kern` at this block size and dynamic shared memory (host API, cached).
+template <typename Kern>
+int occupancy(Kern kern, int threads, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, size_t>, int> cache;
+  const auto key = std::make_tuple(reinterpret_cast<const void*>(kern), threads, smem);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    n = 1;
+  }
+  n = max(n, 1);
+  cache[key] = n;
+  return n;
+}
+
+// Warps are spread over the four schedulers of an SM across CTAs, and the most loaded scheduler paces the SM
+// (tools/ubench_f32x2.cu, block-size sweep: 25 resident warps run at 25/28 of the rate of 24 or 28).
+double sched_balance(int warps_per_sm) { return (double)warps_per_sm / (4.0 * ceil_div(warps_per_sm, 4)); }
+
+// Batch chunking: about kTargetCtasPerSm CTAs per SM, in balanced chunks (sizes differ by at most one pass).
+// Measured on B200 (profiles/r1e_plan_sweep.txt): fewer, longer CTAs sized to an exact number of resident "waves" are
+// SLOWER (L1 backward 11.9 -> 12.6 ms at ~3 waves) — a CTA that is alone on its SM runs several times faster, so a
+// short last wave costs little, while many CTAs in different phases hide each other's pass barriers.
+constexpr int kTargetCtasPerSm = 24;
+void plan_chunks(Geo& g, int ctas_per_chunk, int NB, int wave) {
+  (void)wave;
+  static const int target_env = getenv("IGN_PLAN_CTAS_PER_SM") ? atoi(getenv("IGN_PLAN_CTAS_PER_SM")) : 0;
+  const int target = (target_env > 0 ? target_env : kTargetCtasPerSm) * sm_count();
+  const int units = ceil_div(g.B, NB);
+  int nc = max(1, ceil_div(target, max(1, ctas_per_chunk)));
+  nc = min(nc, units);
+  g.nchunk = nc; g.cbase = units / nc; g.cextra = units % nc;
 }
 
 size_t fwd_smem_floats(const Geo& g, int NB, int KB, int ntile) {
@@ -876,8 +1108,10 @@ size_t fwd_smem_floats(const Geo& g, int NB, int KB, int ntile) {
 }
 
 struct FwdPlan { int threads; size_t smem_bytes; };
+using FwdKernel = void (*)(const Geo, const FwdArgs);
+using BwdKernel = void (*)(const Geo, const BwdArgs);
 
-bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
+bool plan_fwd(Geo& g, int TT, FwdPlan& fp, FwdKernel kern) {
   g.dbuf = 0;
   const size_t cap_soft = 111 * 1024, cap_hard = (size_t)max_optin_smem() - 1024;   // two CTAs per SM
   const int Kpad = round_up(g.K, g.KK);
@@ -910,9 +1144,9 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
     else g.dbuf = 0;
   }
   g.KB = KB; g.nkb = ceil_div(Kpad, KB); g.NB = best;
-  g.bpc = plan_bpc(g, g.M * g.nkb, best);
   fp.threads = bthr;
   fp.smem_bytes = fwd_smem_floats(g, best, KB, ntile) * 4;
+  plan_chunks(g, g.M * g.nkb, best, sm_count() * occupancy(kern, fp.threads, fp.smem_bytes));
   return true;
 }
 
@@ -933,7 +1167,7 @@ size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
   return mult * xs + cbt + (size_t)KB * g.s * g.LQ + KB;
 }
 
-bool plan_bwd(Geo& g, BwdPlan& bp) {
+bool plan_bwd(Geo& g, BwdPlan& bp, BwdKernel kern) {
   const size_t cap = (size_t)max_optin_smem() - 1024;
   const size_t cap_soft = 56 * 1024;     // aim for >= 4 CTAs per SM
   const int ntl_all = g.s * g.LQ / LT;
@@ -946,22 +1180,38 @@ bool plan_bwd(Geo& g, BwdPlan& bp) {
   tlb = ceil_div(ntl_all, nlb);          // balance the lag blocks
   const int per_slot = tlb * KB;
   const int slots = max(1, kMaxThreads / per_slot);
-  int bestNB = 1, bestSeg = 1; double beff = -1.0;
+  // (rows per pass, t-segments, resident CTAs): active lanes per issued warp x scheduler balance of the resident warps
+  // (fewer than 16 warps per SM are discounted: nothing left to hide the pass barriers)
+  const int smem_sm = max_smem_per_sm();
+  int bestNB = 1, bestSeg = 1, bestOcc = 0; double beff = -1.0;
   for (int NB = 1; NB <= min(min(g.B, slots), 16); ++NB) {
-    if (bwd_smem_floats(g, NB, KB) * 4 > (NB == 1 ? cap : cap_soft)) break;
-    int nseg = max(1, slots / NB);
-    nseg = min(nseg, max(1, g.DP / 48));             // keep segments >= 48 windows
-    const int nitem = NB * nseg * per_slot;
-    const double e = (double)nitem / (double)round_up(nitem, 32) + 1e-3 * NB;   // prefer more rows per pass on ties
-    if (e > beff + 0.01) { beff = e; bestNB = NB; bestSeg = nseg; }
+    const size_t bytes = bwd_smem_floats(g, NB, KB) * 4;
+    if (bytes > (NB == 1 ? cap : cap_soft)) break;
+    int nseg_max = max(1, slots / NB);
+    nseg_max = min(nseg_max, max(1, g.DP / 48));     // keep segments >= 48 windows
+    for (int nseg = nseg_max; nseg >= 1; --nseg) {
+      const int nitem = NB * nseg * per_slot;
+      const int thr = round_up(nitem, 32);
+      const double lane = (double)nitem / (double)thr;
+      const int occ_max = occupancy(kern, thr, bytes);
+      for (int occ = occ_max; occ >= 1; --occ) {
+        const int w = occ * thr / 32;
+        const double e = lane * sched_balance(w) * min(1.0, w / 16.0) + 1e-3 * NB;   // prefer more rows per pass on ties
+        if (e > beff + 0.01) { beff = e; bestNB = NB; bestSeg = nseg; bestOcc = occ == occ_max ? 0 : occ; }
+      }
+    }
   }
   g.KB = KB; g.nkb = ceil_div(g.K, KB); g.NB = bestNB;
   bp.nseg = bestSeg; bp.nlb = nlb; bp.tlb = tlb;
   bp.threads = round_up(bestNB * bestSeg * per_slot, 32);
-  g.bpc = plan_bpc(g, g.M * g.nkb * nlb, bestNB);
-  bp.nchunk = ceil_div(g.B, g.bpc);
   bp.hcap = bwd_hash_cap(g, KB);
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
+  if (bestOcc) {   // fewer resident CTAs than would fit: ask for enough shared memory that one more does not
+    const size_t pad = (size_t)smem_sm / (bestOcc + 1) - 1024 + 16;
+    if (pad > bp.smem_bytes && pad <= cap && (pad + 1024) * bestOcc <= (size_t)smem_sm) bp.smem_bytes = pad;
+  }
+  plan_chunks(g, g.M * g.nkb * nlb, bestNB, sm_count() * occupancy(kern, bp.threads, bp.smem_bytes));
+  bp.nchunk = g.nchunk;
   return true;
 }
 
@@ -971,24 +1221,41 @@ int set_smem(Kern kern, size_t bytes) {
   return IGN_OK;
 }
 
-template <int OP, int KK, int TT>
-int run_fwd(const Geo& g, const FwdArgs& a, const FwdPlan& fp, cudaStream_t st) {
-  int rc = set_smem(shapelet_fwd_kernel<OP, KK, TT>, fp.smem_bytes);
+int run_fwd(FwdKernel kern, const Geo& g, const FwdArgs& a, const FwdPlan& fp, cudaStream_t st) {
+  int rc = set_smem(kern, fp.smem_bytes);
   if (rc) return rc;
-  dim3 grid(g.M, g.nkb, ceil_div(g.B, g.bpc));
-  shapelet_fwd_kernel<OP, KK, TT><<<grid, fp.threads, fp.smem_bytes, st>>>(g, a);
+  dim3 grid(g.M, g.nkb, g.nchunk);
+  kern<<<grid, fp.threads, fp.smem_bytes, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }
 
-template <int OP>
-int run_bwd(const Geo& g, const BwdArgs& a, const BwdPlan& bp, cudaStream_t st) {
-  int rc = set_smem(shapelet_bwd_kernel<OP>, bp.smem_bytes);
+int run_bwd(BwdKernel kern, const Geo& g, const BwdArgs& a, const BwdPlan& bp, cudaStream_t st) {
+  int rc = set_smem(kern, bp.smem_bytes);
   if (rc) return rc;
   dim3 grid(g.M, g.nkb * bp.nlb, bp.nchunk);
-  shapelet_bwd_kernel<OP><<<grid, bp.threads, bp.smem_bytes, st>>>(g, a);
+  kern<<<grid, bp.threads, bp.smem_bytes, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
+}
+
+FwdKernel fwd_kernel(bool l1, int KK, int TT) {
+  if (l1) {
+    if (KK == 5) return TT == 8 ? shapelet_fwd_kernel<OP_L1, 5, 8> : shapelet_fwd_kernel<OP_L1, 5, 4>;
+    return TT == 8 ? shapelet_fwd_kernel<OP_L1, 4, 8> : shapelet_fwd_kernel<OP_L1, 4, 4>;
+  }
+  if (KK == 5) return TT == 8 ? shapelet_fwd_kernel<OP_DOT, 5, 8> : shapelet_fwd_kernel<OP_DOT, 5, 4>;
+  return TT == 8 ? shapelet_fwd_kernel<OP_DOT, 4, 8> : shapelet_fwd_kernel<OP_DOT, 4, 4>;
+}
+
+BwdKernel bwd_kernel(int dist) { return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1> : shapelet_bwd_kernel<OP_DOT>; }
+
+void debug_plan(const char* what, const Geo& g, int threads, size_t smem, int occ, int extra0, int extra1) {
+  static const bool on = getenv("IGN_DEBUG_PLAN") != nullptr;
+  if (!on) return;
+  fprintf(stderr, "[ign plan] %s L=%d Tw=%d K=%d: threads=%d smem=%zu occ=%d NB=%d KB=%d nkb=%d nchunk=%d (base %d, +1 x %d) grid=%d waves=%.2f  [%d %d]\n",
+          what, g.L, g.Tw, g.K, threads, smem, occ, g.NB, g.KB, g.nkb, g.nchunk, g.cbase, g.cextra,
+          g.M * g.nkb * g.nchunk * max(1, extra1), (double)g.M * g.nkb * g.nchunk * max(1, extra1) / (sm_count() * occ), extra0, extra1);
 }
 
 }  // namespace
@@ -1000,19 +1267,11 @@ int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   if (!base_geo(d, g)) { set_error("shapelet_forward: T=%d < L=%d (unfold would raise)", d.T, d.L); return IGN_ERR_INVALID; }
   const int TT = g.Tw >= 64 ? 8 : 4;
   FwdPlan fp;
-  if (!plan_fwd(g, TT, fp)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  const FwdKernel kern = fwd_kernel(d.dist == IGN_DIST_L1, g.KK, TT);
+  if (!plan_fwd(g, TT, fp, kern)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  debug_plan("fwd", g, fp.threads, fp.smem_bytes, occupancy(kern, fp.threads, fp.smem_bytes), TT, 1);
   FwdArgs a{xn, st0, W, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, d.stride)};
-  const bool l1 = d.dist == IGN_DIST_L1;
-#define IGN_DISPATCH(OPV, KKV, TTV) return run_fwd<OPV, KKV, TTV>(g, a, fp, st)
-  if (l1) {
-    if (g.KK == 5) { if (TT == 8) IGN_DISPATCH(OP_L1, 5, 8); else IGN_DISPATCH(OP_L1, 5, 4); }
-    else           { if (TT == 8) IGN_DISPATCH(OP_L1, 4, 8); else IGN_DISPATCH(OP_L1, 4, 4); }
-  } else {
-    if (g.KK == 5) { if (TT == 8) IGN_DISPATCH(OP_DOT, 5, 8); else IGN_DISPATCH(OP_DOT, 5, 4); }
-    else           { if (TT == 8) IGN_DISPATCH(OP_DOT, 4, 8); else IGN_DISPATCH(OP_DOT, 4, 4); }
-  }
-#undef IGN_DISPATCH
-  return IGN_OK;
+  return run_fwd(kern, g, a, fp, st);
 }
 
 struct BwdWorkspace { size_t part, coef, rowsc, wstat, tie, total; };   // offsets/size in floats
@@ -1032,7 +1291,7 @@ BwdWorkspace bwd_workspace(const ign_shapelet_desc& d, const Geo& g, const BwdPl
 
 size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
   Geo g; BwdPlan bp;
-  if (!base_geo(d, g) || !plan_bwd(g, bp)) return 0;
+  if (!base_geo(d, g) || !plan_bwd(g, bp, bwd_kernel(d.dist))) return 0;
   return bwd_workspace(d, g, bp).total * sizeof(float);
 }
 
@@ -1042,7 +1301,8 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
                              cudaStream_t st) {
   Geo g; BwdPlan bp;
   if (!base_geo(d, g)) { set_error("shapelet_backward: T=%d < L=%d", d.T, d.L); return IGN_ERR_INVALID; }
-  if (!plan_bwd(g, bp)) { set_error("shapelet_backward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  const BwdKernel kern = bwd_kernel(d.dist);
+  if (!plan_bwd(g, bp, kern)) { set_error("shapelet_backward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
   const BwdWorkspace wo = bwd_workspace(d, g, bp);
   if (ws_bytes < wo.total * sizeof(float)) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, wo.total * sizeof(float)); return IGN_ERR_INVALID; }
   if (((uintptr_t)ws & 15) != 0) { set_error("shapelet_backward: workspace must be 16-byte aligned"); return IGN_ERR_INVALID; }
@@ -1054,16 +1314,25 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   }
   {
     const int rows = d.B * d.M * d.K;
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * 2 * g.DP * sizeof(float) > 72 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * 2 * g.DP * sizeof(float);
-    if (smem > (size_t)max_optin_smem() - 1024) { set_error("shapelet_backward: %d windows per series do not fit shared memory", g.Tw); return IGN_ERR_UNSUPPORTED; }
     PoolArgs pa{gr, dstore, dmin, argmin, st0, st1, stats_pitch(d.T, d.L, d.stride), base + wo.wstat, base + wo.coef, base + wo.rowsc};
-    const int per_sm = max(1, min(2048 / (warps * 32), (int)(((size_t)max_optin_smem()) / (smem + 1024))));
+    const bool in_regs = g.Tw <= 1024;       // rows that fit NCH float4 chunks per lane (pool_bwd_reg_kernel)
+    int warps = 8;
+    const int stages = in_regs ? kPoolStages : 2;
+    while (warps > 1 && (size_t)warps * stages * g.DP * sizeof(float) > (in_regs ? 100 : 72) * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * stages * g.DP * sizeof(float);
+    if (smem > (size_t)max_optin_smem() - 1024) { set_error("shapelet_backward: %d windows per series do not fit shared memory", g.Tw); return IGN_ERR_UNSUPPORTED; }
+    int per_sm = max(1, min(2048 / (warps * 32), (int)(((size_t)max_smem_per_sm()) / (smem + 1024))));
+    if (in_regs) per_sm = min(per_sm, 2);    // __launch_bounds__(256, 2)
     const dim3 pgrid(min(ceil_div(rows, warps), sm_count() * per_sm)), pblock(warps * 32);
-#define IGN_POOL_LAUNCH(PV, DV)                                                        \
-    { int rc = set_smem(pool_bwd_kernel<PV, DV>, smem); if (rc) return rc;              \
-      pool_bwd_kernel<PV, DV><<<pgrid, pblock, smem, st>>>(g, pa, rows); }
+#define IGN_POOL_LAUNCH_K(KERN)                                                         \
+    { int rc = set_smem(KERN, smem); if (rc) return rc;                                 \
+      KERN<<<pgrid, pblock, smem, st>>>(g, pa, rows); }
+#define IGN_POOL_LAUNCH(PV, DV)                                                         \
+    { if (!in_regs) IGN_POOL_LAUNCH_K((pool_bwd_kernel<PV, DV>))                        \
+      else if (g.Tw > 768) IGN_POOL_LAUNCH_K((pool_bwd_reg_kernel<PV, DV, 8>))          \
+      else if (g.Tw > 512) IGN_POOL_LAUNCH_K((pool_bwd_reg_kernel<PV, DV, 6>))          \
+      else if (g.Tw > 256) IGN_POOL_LAUNCH_K((pool_bwd_reg_kernel<PV, DV, 4>))          \
+      else IGN_POOL_LAUNCH_K((pool_bwd_reg_kernel<PV, DV, 2>)) }
     if (d.pool == IGN_POOL_RBF_MAX) {
       switch (d.dist) {
         case IGN_DIST_L1: IGN_POOL_LAUNCH(IGN_POOL_RBF_MAX, IGN_DIST_L1) break;
@@ -1076,6 +1345,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
       else IGN_POOL_LAUNCH(IGN_POOL_LTS_MIN, IGN_DIST_SQL2)
     }
 #undef IGN_POOL_LAUNCH
+#undef IGN_POOL_LAUNCH_K
     IGN_CUDA(cudaGetLastError());
   }
   // 2. contraction with the series into per-chunk partials: tensor pipe for the cross-term modes in the tcgen05
@@ -1101,7 +1371,8 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     tie = tflags;
   }
   BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, tie};
-  int rc = d.dist == IGN_DIST_L1 ? run_bwd<OP_L1>(g, a, bp, st) : run_bwd<OP_DOT>(g, a, bp, st);
+  debug_plan("bwd", g, bp.threads, bp.smem_bytes, occupancy(kern, bp.threads, bp.smem_bytes), bp.nseg, bp.nlb);
+  int rc = run_bwd(kern, g, a, bp, st);
   if (rc) return rc;
   // 3. combine
   shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
