@@ -317,6 +317,9 @@ def main():
     # per-kernel durations for the rooflines: the same steps once more with a CUDA-event pair around every C-ABI
     # call, on the stream the kernels run on (kept out of the timed region above so that it is unperturbed)
     ksteps = min(a.steps, 5)
+    import ctypes
+    from layers import ign_cabi as CABI
+    CABI.check(CABI.lib.ign_debug_bwd_phase_timing(1), "ign_debug_bwd_phase_timing")     # events around the four phases inside ign_shapelet_backward
     STATS.reset(timing=True)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
@@ -328,6 +331,12 @@ def main():
     ms_kernel_region = k0.elapsed_time(k1)
     kern = STATS.summary()
     STATS.reset(timing=False)
+    ph_ms, ph_n = (ctypes.c_float * 4)(), (ctypes.c_int32 * 4)()
+    CABI.check(CABI.lib.ign_debug_bwd_phase_read(ph_ms, ph_n), "ign_debug_bwd_phase_read")
+    CABI.check(CABI.lib.ign_debug_bwd_phase_timing(0), "ign_debug_bwd_phase_timing")
+    for i, name in enumerate(("bwd.pool_bwd", "bwd.tie_check", "bwd.contraction", "bwd.finalize")):
+        if ph_n[i]:
+            kern[name] = (int(ph_n[i]), float(ph_ms[i]))
     value = world * B * a.steps / (ms_total * 1e-3)
 
     # ---------------- end-to-end region: pinned host batch in, loss out, every step ----------------
@@ -377,6 +386,12 @@ def main():
             # so the backward EXECUTES 2E (L1: FSETP + predicated FADD per element; dot modes: one FFMA).
             f["ops"] += n * 2.0 * E[L]
             f["alg"] = f.get("alg", 0.0) + n * 4.0 * E[L]
+        elif fam == "bwd.pool_bwd":
+            # one read of the saved distances + one write of the coefficients per (sample, channel, shapelet, window);
+            # every group is launched once per step, so n launches = n/len(E) steps
+            f["bytes"] += (n / len(E)) * sum(8.0 * B * M * K_PER_LEN * ((T - L_ + 1 + 3) // 4 * 4) for L_ in E)
+        elif fam == "bwd.contraction":
+            f["ops"] += (n / len(E)) * 2.0 * sum(E.values())
         elif fam == "instnorm":
             f["bytes"] += n * (2.0 * B * T * M * 4)
         elif fam == "window_prefix":
@@ -387,7 +402,7 @@ def main():
         r = {"kernel": fam, "launches": f["launches"], "avg_ms": avg_ms, "share_of_step": f["ms"] / ms_kernel_region}
         if f["ops"]:
             ach = f["ops"] / (f["ms"] * 1e-3) / 1e12
-            if fam in ("shapelet_fwd", "shapelet_bwd") and not l1 and a.precision in ("3xtf32", "tf32"):
+            if fam in ("shapelet_fwd", "shapelet_bwd", "bwd.contraction") and not l1 and a.precision in ("3xtf32", "tf32"):
                 # cross term (forward) / coefficient contraction (backward, incl. its HBM-bound pooling pass) on the
                 # tcgen05 pipe: algorithmic 2E flop against the TF32 peak (= half the measured bf16 cuBLAS rate); the
                 # 3xTF32 split executes three MMAs per algorithmic multiply-add
@@ -408,7 +423,13 @@ def main():
             r.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
                      peak_source=peak_src, traffic=traffic_from_profiles(fam))
         rooflines.append(r)
-    dominant = next((r for r in rooflines if "bound" in r), None)
+    # the dominant KERNEL: the backward op as a whole is an aggregate of four kernels (pooling backward, tie pre-check,
+    # contraction, finalize), reported for continuity; its phases are the entries named "bwd.*"
+    have_phases = any(r["kernel"] == "bwd.contraction" for r in rooflines)
+    for r in rooflines:
+        if r["kernel"] == "shapelet_bwd" and have_phases:
+            r["aggregate_of"] = ["bwd.pool_bwd", "bwd.tie_check", "bwd.contraction", "bwd.finalize"]
+    dominant = next((r for r in rooflines if "bound" in r and "aggregate_of" not in r), None)
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:

@@ -74,6 +74,11 @@ const char* ign_last_error(void);
 /* IGN_OK iff `device` (or the current device when < 0) is compute capability 10.x */
 int32_t ign_device_check(int32_t device);
 
+/* debug / measurement: CUDA events around the four phases of ign_shapelet_backward (0 pooling backward, 1 tie
+ * pre-check, 2 contraction, 3 finalize), recorded on the call's stream while enabled.  ign_debug_bwd_phase_read waits
+ * for the recorded events and returns total milliseconds and launch counts per phase since the last read. */
+int32_t ign_debug_bwd_phase_timing(int32_t enable);
+int32_t ign_debug_bwd_phase_read(float* ms4_host, int32_t* count4_host);
 /* debug: role-level cycle counters of the tcgen05 kernel (only in builds with -DIGN_TC_PROFILE) */
 int32_t ign_debug_tc_profile(uint64_t* host16, int32_t reset);
 /* debug: clock64() event trace of CTA 0 of the last tcgen05 launch, [12 roles][32 tiles][4 events] (same builds) */

@@ -83,6 +83,11 @@ int32_t ign_device_check(int32_t device) {
   return IGN_OK;
 }
 
+int32_t ign_debug_bwd_phase_timing(int32_t enable) { return bwd_phase_timing(enable); }
+int32_t ign_debug_bwd_phase_read(float* ms4, int32_t* count4) {
+  IGN_REQUIRE(ms4 != nullptr && count4 != nullptr, "ign_debug_bwd_phase_read: null output");
+  return bwd_phase_read(ms4, count4);
+}
 int32_t ign_debug_tc_trace(int64_t* host, int32_t n) { return tc_trace_read(reinterpret_cast<long long*>(host), n); }
 int32_t ign_debug_tc_profile(uint64_t* host16, int32_t reset) {
   if (reset & 2) return bwd_tc_profile_read(reinterpret_cast<unsigned long long*>(host16), reset & 1);   // backward kernel's counters

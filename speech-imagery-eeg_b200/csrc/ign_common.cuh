@@ -56,6 +56,8 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
                              const float* st1, const float* W, const float* g, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
                              cudaStream_t st);
+int bwd_phase_timing(int enable);
+int bwd_phase_read(float* ms4, int* count4);
 int tc_profile_read(unsigned long long* host16, int reset);
 int tc_trace_read(long long* host, int n);
 int bwd_tc_profile_read(unsigned long long* host16, int reset);

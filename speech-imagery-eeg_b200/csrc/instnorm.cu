@@ -7,12 +7,121 @@
 //                     Shapelet.py:11-19,28,64-66)
 #include "ign_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace ign {
 
 namespace {
 
+#include "tc_ptx.cuh"
+
+namespace cg = cooperative_groups;
+
 constexpr int kNormThreads = 256;
 constexpr int kNormWarps = kNormThreads / 32;
+constexpr int kMaxCluster = 8;          // portable maximum.  16 (opt-in on sm_100) was measured SLOWER: 0.131 ms vs 0.079 ms at
+                                        // config 2 — 16 co-scheduled CTAs leave the GPC's other SMs waiting
+
+// ---- cluster variant (the default whenever it applies): one thread-block cluster per sample, CTA `rank` owns the
+// time rows [rank*R, rank*R + R).  In the [B,T,M] batch layout those rows are ONE contiguous byte range, so the CTA's
+// whole tile is fetched by 1-D bulk TMA copies (fully coalesced DRAM reads, no per-thread address arithmetic, no
+// register staging); per-channel sums are combined across the cluster through distributed shared memory (two-pass
+// mean / squared deviations, as the reference's std), and each warp then writes one channel's R-sample segment with
+// 128-byte stores.  The dense [R][M] tile is read column-wise in the drain, which is bank-conflict free when M is odd
+// (stride M words: CHISCO's 125 channels); layouts with gcd(M, 32) > 2 keep the padded-tile kernel below.
+__global__ void __launch_bounds__(kNormThreads) instnorm_cluster_kernel(const float* __restrict__ x,
+                                                                        float* __restrict__ xn,
+                                                                        float* __restrict__ mean_out,
+                                                                        float* __restrict__ rstd_out, int T, int M,
+                                                                        int Tp, int R) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int Mp = round_up(M, 32);
+  float* tile = reinterpret_cast<float*>(smraw);          // [R][M], byte image of x[b, t_lo : t_lo + rows, :]
+  float* part = tile + (size_t)R * M;                      // [2][warps][Mp] per-warp partial sums / sums of squares
+  float* csum = part + 2 * kNormWarps * Mp;                // [2][Mp] this CTA's partials, read by the cluster peers
+  float* stat = csum + 2 * Mp;                             // [2][Mp] mean, 1 / (std + 1e-8)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stat + 2 * Mp);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t_lo = rank * R, rows = max(0, min(R, T - t_lo));
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async_smem();
+    if (rows > 0) {
+      const uint32_t bytes = (uint32_t)rows * M * sizeof(float);        // multiple of 16: rows % 4 == 0 or T*M % 4 == 0
+      mbar_arrive_expect_tx(bar, bytes);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(x + ((size_t)b * T + t_lo) * M);
+      for (uint32_t off = 0; off < bytes; off += 32768u)
+        tma_bulk_g2s(smraw + off, src + off, min(32768u, bytes - off), bar);
+    }
+  }
+  __syncthreads();
+  if (rows > 0) mbar_wait(bar, 0);
+
+  // One pass over the tile: per-channel sum and sum of squares of (x - x[b,0,c]) — shifting by a sample of the series
+  // keeps the one-pass variance as accurate as the two-pass form (|mean - shift| ~ std) and every CTA of the cluster
+  // can fetch the same shift.  Lanes = consecutive channels (conflict-free), four rows in flight per thread.
+  const float* x0 = x + (size_t)b * T * M;
+  for (int c = lane; c < Mp; c += 32) {
+    float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+    if (c < M) {
+      const float sh = __ldg(x0 + c);
+      int t = warp;
+      for (; t + kNormWarps < rows; t += 2 * kNormWarps) {
+        const float v0 = tile[t * M + c] - sh, v1 = tile[(t + kNormWarps) * M + c] - sh;
+        a0 += v0; q0 = fmaf(v0, v0, q0);
+        a1 += v1; q1 = fmaf(v1, v1, q1);
+      }
+      if (t < rows) { const float v0 = tile[t * M + c] - sh; a0 += v0; q0 = fmaf(v0, v0, q0); }
+    }
+    part[warp * Mp + c] = a0 + a1;
+    part[(kNormWarps + warp) * Mp + c] = q0 + q1;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * Mp; c += kNormThreads) {
+    const int h = c >= Mp ? 1 : 0, cc = c - h * Mp;
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kNormWarps; ++w) sacc += part[(h * kNormWarps + w) * Mp + cc];
+    csum[c] = sacc;                                        // [2][Mp]: sums, sums of squares
+  }
+  cluster.sync();
+  for (int c = threadIdx.x; c < M; c += kNormThreads) {
+    float ps[kMaxCluster], pq[kMaxCluster];
+#pragma unroll
+    for (int r = 0; r < kMaxCluster; ++r) {                // independent remote loads
+      const float* peer = cluster.map_shared_rank(csum, r < CS ? r : 0);
+      ps[r] = r < CS ? peer[c] : 0.f;
+      pq[r] = r < CS ? peer[Mp + c] : 0.f;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < kMaxCluster; ++r) { s1 += ps[r]; s2 += pq[r]; }
+    const float dm = s1 / (float)T;                        // mean - shift
+    const float mu = __ldg(x0 + c) + dm;
+    const float var = fmaxf(s2 - s1 * dm, 0.f) / (float)(T - 1);   // unbiased, as torch.std
+    const float den = sqrtf(var) + 1e-8f;
+    stat[c] = mu; stat[Mp + c] = 1.f / den;
+    if (rank == 0) {
+      if (mean_out) mean_out[(size_t)b * M + c] = mu;
+      if (rstd_out) rstd_out[(size_t)b * M + c] = 1.f / den;
+    }
+  }
+  cluster.sync();                                          // no CTA may exit while a peer still reads its csum
+
+  // drain: one warp per channel, 128 contiguous bytes per store instruction
+  const bool last = rows > 0 && t_lo + rows == T;
+  for (int ch = warp; ch < M; ch += kNormWarps) {
+    const float mu = stat[ch], rden = stat[Mp + ch];       // multiplication by 1/(std+1e-8): <= 1 ulp from the division
+    float* dst = xn + ((size_t)b * M + ch) * Tp + t_lo;
+    for (int i = lane; i < rows; i += 32) dst[i] = (tile[i * M + ch] - mu) * rden;
+    if (last && lane < Tp - T) dst[rows + lane] = 0.f;     // row padding (at most 3 samples)
+  }
+}
 
 // ---- single-read instance norm: the whole (T x CT-channel) tile of one sample is staged in shared memory,
 // so DRAM sees exactly one read of x and one write of xn.  CT = 8 keeps the tile at ~36 KB for T = 1000
@@ -283,9 +392,43 @@ __global__ void __launch_bounds__(256) window_stats_kernel(const float* __restri
 
 }  // namespace
 
+int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
 int launch_instnorm(const float* x, float* xn, float* mean, float* rstd, int B, int T, int M,
                     cudaStream_t st) {
   const int Tp = padded_len(T);
+  // cluster + bulk-TMA kernel: needs 16-byte aligned sample slabs and a conflict-free column read of the dense tile
+  if (((size_t)T * M) % 4 == 0 && gcd_int(M, 32) <= 2 && (((uintptr_t)x) & 15) == 0 && T > 1) {
+    const int Mp = round_up(M, 32);
+    const size_t extra = (size_t)(2 * kNormWarps + 4) * Mp * sizeof(float) + 16;
+    // smallest cluster whose tiles leave room for 3 CTAs per SM: the per-CTA chain TMA -> statistics -> cluster
+    // exchange -> drain is latency-bound, so several CTAs per SM have to overlap it
+    static int max_cluster = kMaxCluster;
+    for (;;) {
+      int CS = 0, R = 0;
+      for (int cs = 1; cs <= max_cluster; cs *= 2) {
+        const int r = round_up(ceil_div(T, cs), 4);
+        const size_t bytes = (size_t)r * M * sizeof(float) + extra;
+        if (bytes <= 74 * 1024 || (cs == max_cluster && bytes <= (size_t)max_optin_smem() - 1024)) { CS = cs; R = r; break; }
+      }
+      if (!CS) break;
+      const size_t smem = (size_t)R * M * sizeof(float) + extra;
+      IGN_CUDA(cudaFuncSetAttribute(instnorm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (CS > 8) IGN_CUDA(cudaFuncSetAttribute(instnorm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(B * CS); cfg.blockDim = dim3(kNormThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, instnorm_cluster_kernel, x, xn, mean, rstd, T, M, Tp, R);
+      if (e == cudaSuccess) return IGN_OK;
+      cudaGetLastError();
+      if (CS > 8 && max_cluster > 8) { max_cluster = 8; continue; }   // this device / partition cannot co-schedule 16 CTAs
+      set_error("instnorm: cluster launch failed: %s", cudaGetErrorString(e));
+      return IGN_ERR_CUDA;
+    }
+  }
 #ifndef IGN_NORM_CT
 #define IGN_NORM_CT 8      // measured on B200 at config 2: CT=4 1.56 TB/s, 8 2.94 TB/s, 16 2.29 TB/s, 32 1.27 TB/s
 #endif

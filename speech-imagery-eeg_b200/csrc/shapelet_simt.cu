@@ -43,6 +43,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 #include <utility>
 
 namespace ign {
@@ -1258,6 +1259,25 @@ void debug_plan(const char* what, const Geo& g, int threads, size_t smem, int oc
           g.M * g.nkb * g.nchunk * max(1, extra1), (double)g.M * g.nkb * g.nchunk * max(1, extra1) / (sm_count() * occ), extra0, extra1);
 }
 
+// ---- optional per-phase CUDA-event timing of the backward (bench.py's per-kernel rooflines) ----
+enum { PH_POOL = 0, PH_TIE, PH_CONTRACT, PH_FINALIZE, PH_COUNT };
+struct PhaseRec { int phase; cudaEvent_t e0, e1; };
+std::mutex g_phase_mu;
+bool g_phase_on = false;
+std::vector<PhaseRec> g_phase;
+struct PhaseScope {
+  cudaStream_t st; cudaEvent_t e1 = nullptr;
+  PhaseScope(int phase, cudaStream_t s) : st(s) {
+    std::lock_guard<std::mutex> lock(g_phase_mu);
+    if (!g_phase_on) return;
+    cudaEvent_t e0;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e1 = nullptr; return; }
+    cudaEventRecord(e0, st);
+    g_phase.push_back({phase, e0, e1});
+  }
+  ~PhaseScope() { if (e1) cudaEventRecord(e1, st); }
+};
+
 }  // namespace
 
 int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
@@ -1313,6 +1333,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     IGN_CUDA(cudaGetLastError());
   }
   {
+    PhaseScope ph(PH_POOL, st);
     const int rows = d.B * d.M * d.K;
     PoolArgs pa{gr, dstore, dmin, argmin, st0, st1, stats_pitch(d.T, d.L, d.stride), base + wo.wstat, base + wo.coef, base + wo.rowsc};
     const bool in_regs = g.Tw <= 1024;       // rows that fit NCH float4 chunks per lane (pool_bwd_reg_kernel)
@@ -1351,8 +1372,10 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   // 2. contraction with the series into per-chunk partials: tensor pipe for the cross-term modes in the tcgen05
   //    precisions (shapelet_tc_bwd.cu), FP32 pipe otherwise
   if (shapelet_bwd_tc_supported(d)) {
-    int rc = launch_shapelet_bwd_tc(d, xn, base + wo.coef, base + wo.part, st);
+    int rc;
+    { PhaseScope ph(PH_CONTRACT, st); rc = launch_shapelet_bwd_tc(d, xn, base + wo.coef, base + wo.part, st); }
     if (rc) return rc;
+    PhaseScope ph(PH_FINALIZE, st);
     shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
                                                                 d.M, d.L, shapelet_bwd_tc_chunks(d), d.dist);
     IGN_CUDA(cudaGetLastError());
@@ -1360,6 +1383,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   }
   const unsigned char* tie = nullptr;
   if (d.dist == IGN_DIST_L1 && bp.hcap) {
+    PhaseScope ph(PH_TIE, st);
     unsigned char* tflags = reinterpret_cast<unsigned char*>(base + wo.tie);
     const int bsplit = max(1, min(d.B, ceil_div(sm_count(), d.M * g.nkb)));
     const size_t hs = ((size_t)bp.hcap + kTieBitmapWords) * sizeof(unsigned);
@@ -1372,12 +1396,35 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   }
   BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, tie};
   debug_plan("bwd", g, bp.threads, bp.smem_bytes, occupancy(kern, bp.threads, bp.smem_bytes), bp.nseg, bp.nlb);
-  int rc = run_bwd(kern, g, a, bp, st);
+  int rc;
+  { PhaseScope ph(PH_CONTRACT, st); rc = run_bwd(kern, g, a, bp, st); }
   if (rc) return rc;
   // 3. combine
+  PhaseScope ph(PH_FINALIZE, st);
   shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
                                                               d.M, d.L, bp.nchunk, d.dist);
   IGN_CUDA(cudaGetLastError());
+  return IGN_OK;
+}
+
+int bwd_phase_timing(int enable) {
+  std::lock_guard<std::mutex> lock(g_phase_mu);
+  g_phase_on = enable != 0;
+  return IGN_OK;
+}
+
+// total milliseconds and launch count per phase since the last read; waits for the recorded events
+int bwd_phase_read(float* ms, int* count) {
+  std::lock_guard<std::mutex> lock(g_phase_mu);
+  for (int i = 0; i < PH_COUNT; ++i) { ms[i] = 0.f; count[i] = 0; }
+  for (auto& r : g_phase) {
+    float t = 0.f;
+    IGN_CUDA(cudaEventSynchronize(r.e1));
+    IGN_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.phase] += t; count[r.phase] += 1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_phase.clear();
   return IGN_OK;
 }
 

@@ -34,6 +34,8 @@ _SIGNATURES = {
     "ign_abi_version": (c_int32, []),
     "ign_last_error": (c_char_p, []),
     "ign_device_check": (c_int32, [c_int32]),
+    "ign_debug_bwd_phase_timing": (c_int32, [c_int32]),
+    "ign_debug_bwd_phase_read": (c_int32, [_P, _P]),
     "ign_debug_tc_profile": (c_int32, [_P, c_int32]),
     "ign_debug_tc_trace": (c_int32, [_P, c_int32]),
     "ign_padded_len": (c_int32, [c_int32]),
