@@ -643,6 +643,17 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
 
     // ---- pass 1: exponentials once, (U, V) to registers, soft-max statistics, chunk-wise arg-max
     float4 U[NCH], V[NCH];
+    // cosine: the row's window-norm factors are fetched now and used in pass 2 (issued per chunk there, each 16-byte
+    // load sat on the critical path: 0.36 ms per group against 0.17 ms for the L1 instantiation)
+    constexpr int NS = DIST == IGN_DIST_COSINE ? NCH : 1;
+    float4 S[NS];
+    const float* s0r = a.st0 + (size_t)bm * a.SP;          // SP % 16 == 0: float4-aligned rows
+    const float* s1r = a.st1 + (size_t)bm * a.SP;
+    if (DIST == IGN_DIST_COSINE) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+        if (j < nfull) S[j] = __ldg(reinterpret_cast<const float4*>(s0r + (j * 32 + lane) * 4));
+    }
     float Zs = 0.f, S1s = 0.f, pmx = 0.f;
     int jmx = -1;
     auto eval = [&](float d, float& u, float& v) {
@@ -709,8 +720,6 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
 
     // ---- pass 2: coefficients from registers, mode factor, 128-bit stores
     const float wst = (DIST == IGN_DIST_PEARSON) ? a.wstat[(size_t)k * g.M + m] : 0.f;
-    const float* s0r = a.st0 + (size_t)bm * a.SP;          // SP % 16 == 0: float4-aligned rows
-    const float* s1r = a.st1 + (size_t)bm * a.SP;
     float* dst = a.coef + (size_t)row * g.Ts;
     float sc0 = 0.f, sc1 = 0.f;
     constexpr bool kStats = DIST == IGN_DIST_COSINE || DIST == IGN_DIST_PEARSON;
@@ -725,7 +734,9 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
           c0 += hc == 0 ? fix : 0.f; c1 += hc == 1 ? fix : 0.f; c2 += hc == 2 ? fix : 0.f; c3 += hc == 3 ? fix : 0.f;
         }
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f), s0 = d, s1 = d;
-        if (kStats) { d = d4[j * 32 + lane]; s0 = *reinterpret_cast<const float4*>(s0r + t0); }
+        if (kStats) d = d4[j * 32 + lane];
+        if (DIST == IGN_DIST_COSINE) s0 = S[j < NS ? j : 0];
+        if (DIST == IGN_DIST_PEARSON) s0 = *reinterpret_cast<const float4*>(s0r + t0);
         if (DIST == IGN_DIST_PEARSON) s1 = *reinterpret_cast<const float4*>(s1r + t0);
         float4 out;
         out.x = pool_emit<DIST>(c0, d.x, s0.x, s1.x, wst, sc0, sc1);
@@ -807,20 +818,29 @@ __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict_
   for (int b = bbeg + warp; b < bend; b += nwarp) {
     const float4* xr = reinterpret_cast<const float4*>(xn + ((size_t)b * M + m) * Tp);   // pad samples are 0: a
     int hit = 0;                                                                          // spurious hit is harmless
-    for (int t4 = lane; t4 < Tp / 4; t4 += 32) {
-      const float4 v = __ldg(xr + t4);
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+    // eight 16-byte loads in flight per lane (a whole row for T <= 1024): with one load per lane the scan was bound by
+    // DRAM latency (1.2 TB/s); indices past the row end are clamped — re-testing a sample is harmless
+    constexpr int UN = 8;
+    const int nv = Tp / 4;
+    for (int t4 = lane; t4 < nv; t4 += 32 * UN) {
+      float4 vq[UN];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned key = hash_key(vv[e]);
-        const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2);
-        if ((bitmap[hb >> 5] >> (hb & 31)) & 1u) {          // rare: confirm in the exact set
-          unsigned h = hash_slot(key, mask);
-          while (true) {
-            const unsigned q = hset[h];
-            if (q == key) { hit = 1; break; }
-            if (q == kHashEmpty) break;
-            h = (h + 1) & mask;
+      for (int u = 0; u < UN; ++u) vq[u] = __ldg(xr + min(t4 + u * 32, nv - 1));
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const float vv[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned key = hash_key(vv[e]);
+          const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2);
+          if ((bitmap[hb >> 5] >> (hb & 31)) & 1u) {          // rare: confirm in the exact set
+            unsigned h = hash_slot(key, mask);
+            while (true) {
+              const unsigned q = hset[h];
+              if (q == key) { hit = 1; break; }
+              if (q == kHashEmpty) break;
+              h = (h + 1) & mask;
+            }
           }
         }
       }
@@ -1082,10 +1102,6 @@ int occupancy(Kern kern, int threads, size_t smem) {
   return n;
 }
 
-// Warps are spread over the four schedulers of an SM across CTAs, and the most loaded scheduler paces the SM
-// (tools/ubench_f32x2.cu, block-size sweep: 25 resident warps run at 25/28 of the rate of 24 or 28).
-double sched_balance(int warps_per_sm) { return (double)warps_per_sm / (4.0 * ceil_div(warps_per_sm, 4)); }
-
 // Batch chunking: about kTargetCtasPerSm CTAs per SM, in balanced chunks (sizes differ by at most one pass).
 // Measured on B200 (profiles/r1e_plan_sweep.txt): fewer, longer CTAs sized to an exact number of resident "waves" are
 // SLOWER (L1 backward 11.9 -> 12.6 ms at ~3 waves) — a CTA that is alone on its SM runs several times faster, so a
@@ -1181,36 +1197,24 @@ bool plan_bwd(Geo& g, BwdPlan& bp, BwdKernel kern) {
   tlb = ceil_div(ntl_all, nlb);          // balance the lag blocks
   const int per_slot = tlb * KB;
   const int slots = max(1, kMaxThreads / per_slot);
-  // (rows per pass, t-segments, resident CTAs): active lanes per issued warp x scheduler balance of the resident warps
-  // (fewer than 16 warps per SM are discounted: nothing left to hide the pass barriers)
-  const int smem_sm = max_smem_per_sm();
-  int bestNB = 1, bestSeg = 1, bestOcc = 0; double beff = -1.0;
+  // rows per pass x t-segments: fill the thread block (idle lanes in the last warp are the waste).  Scoring candidates
+  // by the scheduler balance of the resident warps as well (tools/ubench_f32x2.cu shows the effect in isolation: 21 or
+  // 25 warps per SM run at 7/8 of the rate of 20 or 24) picked 160 threads x 4 CTAs over 224 x 3 at L=100 and measured
+  // 3.5 % SLOWER (1.65 vs 1.59 ms) — the longer t-segments lose more than the balance gains — so it is not used.
+  int bestNB = 1, bestSeg = 1; double beff = -1.0;
   for (int NB = 1; NB <= min(min(g.B, slots), 16); ++NB) {
-    const size_t bytes = bwd_smem_floats(g, NB, KB) * 4;
-    if (bytes > (NB == 1 ? cap : cap_soft)) break;
-    int nseg_max = max(1, slots / NB);
-    nseg_max = min(nseg_max, max(1, g.DP / 48));     // keep segments >= 48 windows
-    for (int nseg = nseg_max; nseg >= 1; --nseg) {
-      const int nitem = NB * nseg * per_slot;
-      const int thr = round_up(nitem, 32);
-      const double lane = (double)nitem / (double)thr;
-      const int occ_max = occupancy(kern, thr, bytes);
-      for (int occ = occ_max; occ >= 1; --occ) {
-        const int w = occ * thr / 32;
-        const double e = lane * sched_balance(w) * min(1.0, w / 16.0) + 1e-3 * NB;   // prefer more rows per pass on ties
-        if (e > beff + 0.01) { beff = e; bestNB = NB; bestSeg = nseg; bestOcc = occ == occ_max ? 0 : occ; }
-      }
-    }
+    if (bwd_smem_floats(g, NB, KB) * 4 > (NB == 1 ? cap : cap_soft)) break;
+    int nseg = max(1, slots / NB);
+    nseg = min(nseg, max(1, g.DP / 48));             // keep segments >= 48 windows
+    const int nitem = NB * nseg * per_slot;
+    const double e = (double)nitem / (double)round_up(nitem, 32) + 1e-3 * NB;   // prefer more rows per pass on ties
+    if (e > beff + 0.01) { beff = e; bestNB = NB; bestSeg = nseg; }
   }
   g.KB = KB; g.nkb = ceil_div(g.K, KB); g.NB = bestNB;
   bp.nseg = bestSeg; bp.nlb = nlb; bp.tlb = tlb;
   bp.threads = round_up(bestNB * bestSeg * per_slot, 32);
   bp.hcap = bwd_hash_cap(g, KB);
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
-  if (bestOcc) {   // fewer resident CTAs than would fit: ask for enough shared memory that one more does not
-    const size_t pad = (size_t)smem_sm / (bestOcc + 1) - 1024 + 16;
-    if (pad > bp.smem_bytes && pad <= cap && (pad + 1024) * bestOcc <= (size_t)smem_sm) bp.smem_bytes = pad;
-  }
   plan_chunks(g, g.M * g.nkb * nlb, bestNB, sm_count() * occupancy(kern, bp.threads, bp.smem_bytes));
   bp.nchunk = g.nchunk;
   return true;

@@ -60,16 +60,20 @@ def full(src, dst, traffic=None):
         agg = {}
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
-            fam = "shapelet_fwd" if "shapelet_fwd" in name else "shapelet_bwd" if "shapelet_bwd_kernel" in name else \
-                "instnorm" if "instnorm" in name else "window_prefix" if "prefix" in name else None
-            if fam is None:
+            fams = ["shapelet_fwd"] if "shapelet_fwd" in name else \
+                ["shapelet_bwd", "bwd.contraction"] if ("shapelet_bwd_kernel" in name or "shapelet_bwd_tc_kernel" in name) else \
+                ["bwd.pool_bwd"] if "pool_bwd" in name else ["bwd.tie_check"] if "tie_check" in name else \
+                ["instnorm"] if "instnorm" in name else ["window_prefix"] if "prefix" in name else \
+                ["window_stats"] if "window_stats" in name else []
+            if not fams:
                 continue
 
             def tobytes(col):
                 v, u = float(r[hdr.index(col)].replace(",", "")), units[hdr.index(col)].lower()
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
-            n, t = agg.get(fam, (0, 0.0))
-            agg[fam] = (n + 1, t + tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"))
+            for fam in fams:
+                n, t = agg.get(fam, (0, 0.0))
+                agg[fam] = (n + 1, t + tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"))
         json.dump({k: t / n for k, (n, t) in agg.items()}, open(traffic, "w"), indent=1)
 
 
