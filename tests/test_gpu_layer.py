@@ -117,6 +117,35 @@ def test_lts_layer_vs_oracle(flag, shape):
     assert_close(dthr, dthr_ref, 1e-4, 1e-5, "lts dthreshold")
 
 
+# Pooling backward (pool_bwd_reg_kernel): the row is split into whole 128-window float4 chunks and a scalar tail of
+# 32-window sub-chunks, with one instantiation per register budget (NCH = 2, 4, 6, 8) and the generic two-pass kernel
+# above 1024 windows — cover every boundary of that split.
+POOL_TW = [1, 31, 32, 33, 127, 128, 129, 256, 300, 512, 517, 768, 769, 1023, 1024, 1025, 1500]
+
+
+@pytest.mark.parametrize("flag", ["euclidean", "sql2", "cosine", "pearson", "lts"])
+@pytest.mark.parametrize("Tw", POOL_TW)
+def test_pool_backward_row_geometries(flag, Tw):
+    B, M, K, L = 2, 2, 3, 5
+    T = Tw + L - 1
+    torch.manual_seed(4000 + Tw)
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    if flag == "lts":
+        mode, dist = MODES["euclidean"]
+        thr = torch.rand(1, K, M)
+        p, dmin, idx, dW, dthr = run_layer(xn, W, 1, 1.0, dist, "lts_min", thr, g)
+        dW_ref, dthr_ref = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 1.0, mode,
+                                                       O.POOL_LTS_MIN, thr.double())
+        assert_close(dthr, dthr_ref, 1e-4, 1e-5, "lts dthreshold Tw=%d" % Tw)
+    else:
+        mode, dist = MODES[flag]
+        ref = O.shapelet_forward(xn, W, 1, 0.9, mode)
+        p, dmin, idx, dW, _ = run_layer(xn, W, 1, 0.9, dist, g=g)
+        assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, f"{flag} p Tw={Tw}")
+        dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 0.9, mode)
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag} dW Tw={Tw}")
+
+
 def test_long_shapelet_needs_lag_blocks():
     """L = 2100 -> more lag tiles than threads: the backward splits the lag axis over CTAs."""
     torch.manual_seed(5)
