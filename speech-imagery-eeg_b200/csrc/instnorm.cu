@@ -320,49 +320,129 @@ __global__ void __launch_bounds__(256) prefix_kernel(const float* __restrict__ x
 // x^2 in shared memory, then for every group g and window t the norm term its distance needs, as fp32:
 //   sql2    st0 = ||x_w||^2            cosine  st0 = 1/max(||x_w||,1e-8)
 //   pearson st0 = sqrt(sum (x_w-mu)^2), st1 = mu
-// Rows are written coalesced with pitch SP_g (windows rounded up to 16, pad = 0).  One warp per row.
-__global__ void __launch_bounds__(256) window_stats_kernel(const float* __restrict__ xn, const StatGroups G,
-                                                           int rows, int T, int Tp, int dist) {
-  extern __shared__ __align__(16) double pbuf[];          // [warps][nseq][T+1]
+// Rows are written with pitch SP_g (windows rounded up to 16; pad slots carry an ignore marker).  One warp per row.
+//
+// Scan: lane l owns the C consecutive samples [l*C, l*C + C) (C = the power of two >= ceil(T/32)): a lane-local running
+// sum, ONE warp scan of the 32 lane totals, then P[j] = base_l + local_j.  (The first version scanned every
+// 128-sample chunk across the warp — eight dependent 64-bit shuffle scans per row, ~1700 instructions per row.)
+// Slot j of a prefix row lives at j + j/C (a shift): the pad double per C slots makes both the lane-strided writes of the scan
+// (stride C+1, odd) and the window-strided reads of the statistics conflict-free.
+// Statistics (unit stride): a lane produces four consecutive windows per step and stores them with one 16-byte
+// store; strides > 1 (seq_len >= 3000) keep the scalar loop.
+// The square root / reciprocal use the MUFU approximations (rsqrt.approx / sqrt.approx: relative error <= 2^-22.9 /
+// 2^-23, i.e. as good as the correctly rounded sequences to the 2e-5 the distances are tested to).  The IEEE forms
+// (sqrtf + 1.f/x, fp64 sqrt and division) compiled to ~25 instructions with three slow-path branches per window and made
+// this HBM-bound kernel issue-bound (52 instructions per output, 0.26 ms for the four groups of config 2).
+// (.ftz: a denormal window energy flushes to 0 and lands on the same 1e8 clamp / 0 as the exact value would)
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int dist>
+__device__ __forceinline__ float stat_value(double sxx, double sx, double invL, float& mean_out) {
+  if (dist == IGN_DIST_SQL2) return (float)sxx;
+  if (dist == IGN_DIST_COSINE) return fminf(rsqrt_approx((float)sxx), 1e8f);     // 1 / max(||x_w||, 1e-8)
+  const double mu = sx * invL;
+  mean_out = (float)mu;
+  return sqrt_approx((float)fmax(sxx - sx * mu, 0.0));
+}
+
+template <int dist>
+__global__ void __launch_bounds__(256, 3) window_stats_kernel(const float* __restrict__ xn, const StatGroups G,
+                                                              int rows, int T, int Tp, int csh, int PS) {
+  constexpr bool need1 = dist == IGN_DIST_PEARSON;
+  extern __shared__ __align__(16) double pbuf[];          // [warps][nseq][PS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int wstride = gridDim.x * (blockDim.x >> 5);       // persistent warps: rows w, w + wstride, ...
+  int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
-  const bool need1 = dist == IGN_DIST_PEARSON;
-  const int nseq = need1 ? 2 : 1;
-  double* P2 = pbuf + (size_t)warp * nseq * (T + 1);
-  double* P1 = P2 + (T + 1);
-  const float* xr = xn + (size_t)row * Tp;
-  if (lane == 0) { P2[0] = 0.0; if (need1) P1[0] = 0.0; }
-  double c1 = 0.0, c2 = 0.0;
-  const int nchunk = (T + 127) / 128;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane * 4 < Tp) v = *reinterpret_cast<const float4*>(xr + lane * 4);
-  for (int ch = 0; ch < nchunk; ++ch) {
-    const int j = ch * 128 + lane * 4;
-    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ch + 1 < nchunk && j + 128 < Tp) nv = *reinterpret_cast<const float4*>(xr + j + 128);
-    const double q0 = (double)v.x * v.x, q1 = q0 + (double)v.y * v.y, q2 = q1 + (double)v.z * v.z,
-                 q3 = q2 + (double)v.w * v.w;
-    const double s2 = warp_incl_scan(q3, lane);
-    const double e2 = c2 + s2 - q3;
-    if (j + 0 < T) P2[j + 1] = e2 + q0;
-    if (j + 1 < T) P2[j + 2] = e2 + q1;
-    if (j + 2 < T) P2[j + 3] = e2 + q2;
-    if (j + 3 < T) P2[j + 4] = e2 + q3;
-    c2 += __shfl_sync(0xffffffffu, s2, 31);
-    if (need1) {
-      const double a0 = v.x, a1 = a0 + (double)v.y, a2 = a1 + (double)v.z, a3 = a2 + (double)v.w;
-      const double s1 = warp_incl_scan(a3, lane);
-      const double e1 = c1 + s1 - a3;
-      if (j + 0 < T) P1[j + 1] = e1 + a0;
-      if (j + 1 < T) P1[j + 2] = e1 + a1;
-      if (j + 2 < T) P1[j + 3] = e1 + a2;
-      if (j + 3 < T) P1[j + 4] = e1 + a3;
-      c1 += __shfl_sync(0xffffffffu, s1, 31);
+  constexpr int nseq = need1 ? 2 : 1;
+  double* P2 = pbuf + (size_t)warp * nseq * PS;
+  double* P1 = P2 + PS;
+  const int C = 1 << csh;                                  // samples per lane, a power of two
+  auto slot = [&](int j) { return j + (j >> csh); };
+  const int i0 = lane * C;
+  constexpr int UN = 8;
+  float4 keep[UN];                                         // the lane's first 32 samples (all of them for T <= 1024)
+  auto fetch = [&](int r) {                                // samples at or beyond Tp read as 0 (Tp - T pads are 0 already)
+    const float* xq = xn + (size_t)r * Tp;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + 4 * u;
+      keep[u] = (4 * u < C && i < Tp) ? __ldg(reinterpret_cast<const float4*>(xq + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    v = nv;
+  };
+  fetch(row);
+  for (; row < rows; row += wstride) {
+  const float* xr = xn + (size_t)row * Tp;
+
+  // pass 1: lane totals
+  double t1 = 0.0, t2 = 0.0;
+  for (int c0 = 0; c0 < C; c0 += 4 * UN) {
+    float4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + c0 + 4 * u;
+      if (c0 == 0) v[u] = keep[u];
+      else v[u] = (c0 + 4 * u < C && i < Tp) ? __ldg(reinterpret_cast<const float4*>(xr + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const double a = v[u].x, b = v[u].y, c = v[u].z, d = v[u].w;
+      t2 += (a * a + b * b) + (c * c + d * d);
+      if (need1) t1 += (a + b) + (c + d);
+    }
+  }
+  const double b2 = warp_incl_scan(t2, lane) - t2;         // exclusive: prefix in front of this lane's samples
+  const double b1 = need1 ? warp_incl_scan(t1, lane) - t1 : 0.0;
+  if (lane == 0) { P2[0] = 0.0; if (need1) P1[0] = 0.0; }
+
+  // pass 2: P[j+1] = base + running local sum.  Two levels keep the fp64 dependency chain short (the kernel is
+  // latency-bound: 24 warps per SM, one row per warp): the prefix inside each float4 (eight independent 3-deep chains),
+  // an 8-step scan of the float4 totals, then four independent adds per float4.
+  double r1 = 0.0, r2 = 0.0;                                // carry across groups of four float4
+  auto group = [&](int c0, const float4 (&v)[4]) {
+    double q2[4][4], q1[need1 ? 4 : 1][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double a = v[u].x, b = v[u].y, c = v[u].z, d = v[u].w;
+      q2[u][0] = a * a; q2[u][1] = q2[u][0] + b * b; q2[u][2] = q2[u][1] + c * c; q2[u][3] = q2[u][2] + d * d;
+      if (need1) { q1[u][0] = a; q1[u][1] = a + b; q1[u][2] = q1[u][1] + c; q1[u][3] = q1[u][2] + d; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + c0 + 4 * u;
+      const double o2 = b2 + r2, o1 = b1 + r1;
+      r2 += q2[u][3];
+      if (need1) r1 += q1[u][3];
+      if (c0 + 4 * u >= C || i >= T) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (i + e < T) {
+          const int sl = slot(i + e + 1);
+          P2[sl] = o2 + q2[u][e];
+          if (need1) P1[sl] = o1 + q1[u][e];
+        }
+      }
+    }
+  };
+  {
+    const float4 g0[4] = {keep[0], keep[1], keep[2], keep[3]};
+    group(0, g0);
+    if (C > 16) { const float4 g1[4] = {keep[4], keep[5], keep[6], keep[7]}; group(16, g1); }
+  }
+  for (int c0 = 32; c0 < C; c0 += 16) {                      // longer series: re-read (L1 / L2 hits)
+    float4 gv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + c0 + 4 * u;
+      gv[u] = i < Tp ? __ldg(reinterpret_cast<const float4*>(xr + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    group(c0, gv);
   }
   __syncwarp();
+  // the next row's samples are fetched now, so that their DRAM latency hides under the statistics stage below (with one
+  // row per warp and nothing in flight during that stage the kernel sat at 2.5 TB/s)
+  if (row + wstride < rows) fetch(row + wstride);
+
   for (int gi = 0; gi < G.n; ++gi) {
     const int L = G.L[gi], st = G.s[gi], Tw = G.Tw[gi], SP = G.SP[gi];
     float* o0 = G.st0[gi] + (size_t)row * SP;
@@ -371,22 +451,45 @@ __global__ void __launch_bounds__(256) window_stats_kernel(const float* __restri
     // no per-window validity logic: +inf for SQL2 (distance +inf), NaN for COSINE / PEARSON (distance NaN, which
     // the min reductions — FMNMX returns the non-NaN operand — skip).
     const float pad = dist == IGN_DIST_SQL2 ? INFINITY : __int_as_float(0x7fc00000);
-    for (int t = lane; t < SP; t += 32) {
-      float a = pad, b = 0.f;
-      if (t < Tw) {
-        const int j0 = t * st;
-        const double sxx = P2[j0 + L] - P2[j0];
-        if (dist == IGN_DIST_SQL2) a = (float)sxx;
-        else if (dist == IGN_DIST_COSINE) a = 1.f / fmaxf(sqrtf((float)sxx), 1e-8f);
-        else {
-          const double sx = P1[j0 + L] - P1[j0];
-          a = (float)sqrt(fmax(sxx - sx * sx / (double)L, 0.0));
-          b = (float)(sx / (double)L);
+    const double invL = 1.0 / (double)L;
+    if (st == 1) {
+#pragma unroll 2
+      for (int t0 = lane * 4; t0 < SP; t0 += 128) {        // SP % 16 == 0: whole float4s, 16-byte aligned rows
+        float av[4] = {pad, pad, pad, pad}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+        // t0 % 4 == 0 and C >= 4 is a power of two: the four low slots share one pad offset; so do the four high ones
+        // unless (t0 + L) sits in the last three slots of a C-block
+        if (t0 + 4 <= Tw && ((t0 + L) & (C - 1)) <= C - 4) {
+          const double* lo2 = P2 + slot(t0), * hi2 = P2 + slot(t0 + L);
+          const double* lo1 = P1 + slot(t0), * hi1 = P1 + slot(t0 + L);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            av[e] = stat_value<dist>(hi2[e] - lo2[e], need1 ? hi1[e] - lo1[e] : 0.0, invL, bv[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int t = t0 + e;
+            if (t < Tw) {
+              const int lo = slot(t), hi = slot(t + L);
+              av[e] = stat_value<dist>(P2[hi] - P2[lo], need1 ? P1[hi] - P1[lo] : 0.0, invL, bv[e]);
+            }
+          }
         }
+        *reinterpret_cast<float4*>(o0 + t0) = make_float4(av[0], av[1], av[2], av[3]);
+        if (o1) *reinterpret_cast<float4*>(o1 + t0) = make_float4(bv[0], bv[1], bv[2], bv[3]);
       }
-      o0[t] = a;
-      if (o1) o1[t] = b;
+    } else {
+      for (int t = lane; t < SP; t += 32) {
+        float a = pad, b = 0.f;
+        if (t < Tw) {
+          const int lo = slot(t * st), hi = slot(t * st + L);
+          a = stat_value<dist>(P2[hi] - P2[lo], need1 ? P1[hi] - P1[lo] : 0.0, invL, b);
+        }
+        o0[t] = a;
+        if (o1) o1[t] = b;
+      }
     }
+  }
+  __syncwarp();                                            // all lanes are done with this row's prefix sums
   }
 }
 
@@ -460,13 +563,23 @@ int launch_prefix(const float* xn, double* pre1, double* pre2, int B, int M, int
 
 int launch_window_stats(const float* xn, const StatGroups& G, int B, int M, int T, int dist, cudaStream_t st) {
   const int rows = B * M;
-  const size_t per_warp = (size_t)(dist == IGN_DIST_PEARSON ? 2 : 1) * (T + 1) * sizeof(double);
+  int csh = 2;                                             // samples per lane: the power of two >= ceil(T / 32), >= 4
+  while ((32 << csh) < T) ++csh;
+  const int PS = round_up(T + 1 + ((T + 1) >> csh) + 1, 2); // prefix row pitch in doubles (one pad slot per 2^csh)
+  const size_t per_warp = (size_t)(dist == IGN_DIST_PEARSON ? 2 : 1) * PS * sizeof(double);
   int warps = 8;
-  while (warps > 1 && warps * per_warp > 64 * 1024) warps >>= 1;
+  while (warps > 1 && warps * per_warp > 72 * 1024) warps >>= 1;
   const size_t smem = warps * per_warp;
   if (smem > (size_t)max_optin_smem() - 1024) { set_error("window_stats: series of %d samples do not fit shared memory", T); return IGN_ERR_UNSUPPORTED; }
-  IGN_CUDA(cudaFuncSetAttribute(window_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  window_stats_kernel<<<ceil_div(rows, warps), warps * 32, smem, st>>>(xn, G, rows, T, padded_len(T), dist);
+  const int per_sm = max(1, min(3, (int)((size_t)max_smem_per_sm() / (smem + 1024))));
+  const int grid = min(ceil_div(rows, warps), sm_count() * per_sm);
+#define IGN_WS_LAUNCH(DV)                                                                                         \
+  { IGN_CUDA(cudaFuncSetAttribute(window_stats_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    window_stats_kernel<DV><<<grid, warps * 32, smem, st>>>(xn, G, rows, T, padded_len(T), csh, PS); }
+  if (dist == IGN_DIST_PEARSON) IGN_WS_LAUNCH(IGN_DIST_PEARSON)
+  else if (dist == IGN_DIST_COSINE) IGN_WS_LAUNCH(IGN_DIST_COSINE)
+  else IGN_WS_LAUNCH(IGN_DIST_SQL2)
+#undef IGN_WS_LAUNCH
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }

@@ -87,6 +87,23 @@ __global__ void __launch_bounds__(256) k(const float* __restrict__ xin, const fl
           acc[i] = fmaf(c4.z, fma_sat(xv[i + 2], BIG, wb[i]), acc[i]);
           acc[i] = fmaf(c4.w, fma_sat(xv[i + 3], BIG, wb[i]), acc[i]);
         }
+      } else if (MODE >= 9) {
+        // mixed: lags i < NF take the FMA-pipe indicator (FFMA.SAT + FFMA), the rest FSETP + predicated FADD
+        constexpr int NF = MODE - 8;
+#pragma unroll
+        for (int i = 0; i < LT; ++i) {
+          if (i < NF) {
+            acc[i] = fmaf(c4.x, fma_sat(xv[i], BIG, wb[i]), acc[i]);
+            acc[i] = fmaf(c4.y, fma_sat(xv[i + 1], BIG, wb[i]), acc[i]);
+            acc[i] = fmaf(c4.z, fma_sat(xv[i + 2], BIG, wb[i]), acc[i]);
+            acc[i] = fmaf(c4.w, fma_sat(xv[i + 3], BIG, wb[i]), acc[i]);
+          } else {
+            if (xv[i] > w[i]) acc[i] += c4.x;
+            if (xv[i + 1] > w[i]) acc[i] += c4.y;
+            if (xv[i + 2] > w[i]) acc[i] += c4.z;
+            if (xv[i + 3] > w[i]) acc[i] += c4.w;
+          }
+        }
       } else if (MODE == 5) {
         const uint64_t c01 = pack2(c4.x, c4.y), c23 = pack2(c4.z, c4.w);
 #pragma unroll
@@ -166,7 +183,7 @@ void run(const char* name, const float* x, const float* c, float* out, int ctas_
   k<MODE><<<grid, 256>>>(x, c, out, iters);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-  const double elems_per_warp = (double)iters * 512 * 32 * (MODE == 5 || MODE == 6 ? 2 : 1);
+  const double elems_per_warp = (double)iters * 512 * 32 * ((MODE == 5 || MODE == 6) ? 2 : 1);
   const double warps_per_smsp = ctas_per_sm * 8 / 4.0;
   const double cycles = ms * 1e-3 * khz * 1e3;
   printf("%-44s %8.3f ms  %.3f cycles/element/warp-slot (SMSP)  [%d CTAs/SM, clock attr %d kHz] %s\n", name, ms,
@@ -191,6 +208,10 @@ int main() {
     run<6>("6 FFMA stream (per fp32 lane-op)", x, c, out, cps);
     run<7>("7 FADD + FADD|.| (current L1 fwd)", x, c, out, cps);
     run<8>("8 FADD2 + 2 FADD|.|", x, c, out, cps);
+    run<9>("9  mixed: 1 of 8 lags on the FMA pipe", x, c, out, cps);
+    run<10>("10 mixed: 2 of 8 lags on the FMA pipe", x, c, out, cps);
+    run<11>("11 mixed: 3 of 8 lags on the FMA pipe", x, c, out, cps);
+    run<12>("12 mixed: 4 of 8 lags on the FMA pipe", x, c, out, cps);
   }
   return 0;
 }
