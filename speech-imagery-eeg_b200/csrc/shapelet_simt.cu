@@ -49,12 +49,9 @@
 namespace ign {
 namespace {
 
-#include "tc_ptx.cuh"
-
 constexpr int OP_L1 = 0;
 constexpr int OP_DOT = 1;
 constexpr int kMaxThreads = 256;
-constexpr int kMaxBwdStages = 4;
 constexpr int LT = 8;   // lags per thread in backward (16 was measured slower: fewer items, lower occupancy)
 
 struct Geo {  // geometry shared by forward and backward
@@ -93,7 +90,6 @@ struct BwdArgs {
   const float* coef;    // [B][M][K][Ts] per-window coefficients a_t written by pool_bwd_kernel
   float* part;          // [nchunk][K][M][L]
   int nseg, nlb, tlb;   // t-segments per row, l-blocks, l-tiles per l-block
-  int nstage;           // unit stride: stages of the bulk-TMA ring the series / coefficient rows stream through
   const unsigned char* tie;   // L1 only: [B][M][nkb] 1 = this row may contain x == w (exact path); NULL = always exact
 };
 
@@ -298,6 +294,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -869,28 +868,19 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   const int nslot = g.NB * a.nseg;
   const int nitem = nslot * ntl * g.KB;                   // <= blockDim.x by construction
 
-  // unit stride: series and coefficient rows stream through an nstage-deep ring filled by 1-D bulk TMA copies (one
-  // elected thread, completion counted on per-stage mbarriers).  Warps wait on the stage they need and release it on
-  // their own, so there is NO CTA-wide barrier per pass: with __syncthreads() + cp.async double buffering a third of
-  // all warp time was spent in barrier stalls (warps of a CTA drift apart under the greedy schedulers).
+  // unit stride: series and coefficient rows are double-buffered and prefetched with cp.async one pass ahead
   const bool dbuf = g.s == 1;
-  const int S = dbuf ? a.nstage : 1;
   const int xs_sz = g.NB * g.s * g.XQ;
   const int cb_sz = max(g.NB * g.KB * g.CP, dbuf ? 0 : kMaxThreads * LT);
   float* xs0 = smem;
-  float* cb0 = xs0 + S * xs_sz;
-  float* ws = cb0 + max(S * cb_sz, kMaxThreads * LT);
+  float* cb0 = xs0 + (dbuf ? 2 : 1) * xs_sz;
+  float* ws = cb0 + max((dbuf ? 2 : 1) * cb_sz, kMaxThreads * LT);
   float* wstat = ws + g.KB * g.s * g.LQ;
-  __shared__ __align__(8) uint64_t bar_full[kMaxBwdStages], bar_empty[kMaxBwdStages];
 
   if (OP == OP_L1) load_shapelets(g, a.W, m, k0, ws, wstat);
-  if (dbuf) {   // zero once: pad columns (series tail, DP - Ts) are never written by the copies
-    for (int i = threadIdx.x; i < S * xs_sz; i += nthr) xs0[i] = 0.f;
-    for (int i = threadIdx.x; i < S * cb_sz; i += nthr) cb0[i] = 0.f;
-    if (threadIdx.x == 0) {
-      for (int st = 0; st < S; ++st) { mbar_init(&bar_full[st], 1); mbar_init(&bar_empty[st], nthr >> 5); }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+  if (dbuf) {   // zero once: pad columns (series tail, DP - Ts) are never written by the prefetch
+    for (int i = threadIdx.x; i < 2 * xs_sz; i += nthr) xs0[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * cb_sz; i += nthr) cb0[i] = 0.f;
   }
 
   // this thread's fixed tile: 8 lags of one shapelet, one (sample slot, t-segment)
@@ -917,42 +907,33 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     for (int i = 0; i < LT; ++i) wreg[i] = ws[((size_t)kl * g.s + r) * g.LQ + q0 + i];
   }
 
-  // producer (thread 0): all copies of pass q into stage q % S, one expect_tx for their total size
-  const int npass = ceil_div(max(bend - bbeg, 0), g.NB);
-  auto issue = [&](int q) {
-    const int stg = q % S, b0 = bbeg + q * g.NB;
+  auto prefetch = [&](int b0, int buf) {
     const int nb = min(g.NB, bend - b0);
+    float* xd = xs0 + buf * xs_sz;
+    float* cd = cb0 + buf * cb_sz;
+    const int xrow = g.Tp / 4;
+    for (int i = threadIdx.x; i < nb * xrow; i += nthr) {
+      const int rbl = i / xrow, c = i - rbl * xrow;
+      cp_async16(xd + rbl * g.XQ + c * 4, a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp + c * 4);
+    }
+    const int crow = g.Ts / 4;
     const int kvalid = min(g.KB, g.K - k0);
-    float* xd = xs0 + stg * xs_sz;
-    float* cd = cb0 + stg * cb_sz;
-    const uint32_t xbytes = (uint32_t)g.Tp * 4u, cbytes = (uint32_t)g.Ts * 4u;
-    mbar_arrive_expect_tx(&bar_full[stg], (uint32_t)nb * (xbytes + (uint32_t)kvalid * cbytes));
-    for (int rbl = 0; rbl < nb; ++rbl) {
-      tma_bulk_g2s(xd + rbl * g.XQ, a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp, xbytes, &bar_full[stg]);
-      for (int rkl = 0; rkl < kvalid; ++rkl)
-        tma_bulk_g2s(cd + ((size_t)rbl * g.KB + rkl) * g.CP,
-                     a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts, cbytes, &bar_full[stg]);
+    for (int i = threadIdx.x; i < nb * kvalid * crow; i += nthr) {
+      const int row = i / crow, c = i - row * crow;
+      const int rbl = row / kvalid, rkl = row - rbl * kvalid;
+      cp_async16(cd + ((size_t)rbl * g.KB + rkl) * g.CP + c * 4,
+                 a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c * 4);
     }
   };
-  if (dbuf && threadIdx.x == 0) {
-    fence_proxy_async_smem();             // the zero fill above (generic proxy) is ordered before the bulk copies
-    for (int q = 0; q < min(S - 1, npass); ++q) issue(q);
-  }
 
   int buf = 0;
-  for (int b0 = bbeg, pass = 0; b0 < bend; b0 += g.NB, ++pass) {
+  if (dbuf && bbeg < bend) prefetch(bbeg, 0);
+  for (int b0 = bbeg; b0 < bend; b0 += g.NB) {
     const int nb = min(g.NB, bend - b0);
     if (dbuf) {
-      buf = pass % S;
-      if (threadIdx.x == 0) {
-        const int q = pass + S - 1;       // refills the stage of pass - 1 once every warp has released it
-        if (q < npass) {
-          if (q >= S) mbar_wait(&bar_empty[q % S], ((q / S) - 1) & 1);
-          issue(q);
-        }
-      }
-      __syncwarp();
-      mbar_wait(&bar_full[buf], (pass / S) & 1);
+      cp_async_commit_wait_all();
+      __syncthreads();                    // pass data visible; everyone is done with the other buffer
+      if (b0 + g.NB < bend) prefetch(b0 + g.NB, buf ^ 1);
     } else {
       __syncthreads();
       load_series(g, a.xn, nullptr, 0, m, b0, nb, xs0, nullptr);
@@ -1009,14 +990,12 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
 #undef IGN_BWD_SWEEP
 #undef IGN_BWD_STEP
     }
-    if (dbuf) {                             // this warp is done with the stage
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(&bar_empty[buf]);
-    }
+    if (dbuf) buf ^= 1;
   }
 
   // ---- fixed-order reduction over (sample slot, t-segment), then one partial per chunk ----
-  __syncthreads();                          // every issued copy has been waited for by every warp
+  if (dbuf) cp_async_commit_wait_all();
+  __syncthreads();
   float* red = cb0;
   if (active) {
     const int slot = bl * a.nseg + seg;
@@ -1188,7 +1167,7 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp, FwdKernel kern) {
   return true;
 }
 
-struct BwdPlan { int nseg, nlb, tlb, nchunk, threads, hcap, nstage; size_t smem_bytes; };
+struct BwdPlan { int nseg, nlb, tlb, nchunk, threads, hcap; size_t smem_bytes; };
 
 int bwd_hash_cap(const Geo& g, int KB) {
   if (g.dist != IGN_DIST_L1) return 0;
@@ -1197,8 +1176,8 @@ int bwd_hash_cap(const Geo& g, int KB) {
   return cap <= 32768 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path (128 KB + 64 KB smem)
 }
 
-size_t bwd_smem_floats(const Geo& g, int NB, int KB, int stages = 2) {
-  const size_t mult = g.s == 1 ? stages : 1;  // unit stride: ring of `stages` passes
+size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
+  const size_t mult = g.s == 1 ? 2 : 1;       // double-buffered for unit stride
   const size_t xs = (size_t)NB * g.s * g.XQ, cb = (size_t)NB * KB * g.CP;
   size_t cbt = mult * cb;
   if (cbt < (size_t)kMaxThreads * LT) cbt = (size_t)kMaxThreads * LT;
@@ -1236,15 +1215,6 @@ bool plan_bwd(Geo& g, BwdPlan& bp, BwdKernel kern) {
   bp.threads = round_up(bestNB * bestSeg * per_slot, 32);
   bp.hcap = bwd_hash_cap(g, KB);
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
-  // ring depth: as deep as costs no resident CTA (the tile shape above is sized for two stages)
-  bp.nstage = 2;
-  if (g.s == 1) {
-    const int occ2 = occupancy(kern, bp.threads, bp.smem_bytes);
-    for (int st = kMaxBwdStages; st > 2; --st) {
-      const size_t bytes = bwd_smem_floats(g, bestNB, KB, st) * 4;
-      if (bytes <= cap && occupancy(kern, bp.threads, bytes) >= occ2) { bp.nstage = st; bp.smem_bytes = bytes; break; }
-    }
-  }
   plan_chunks(g, g.M * g.nkb * nlb, bestNB, sm_count() * occupancy(kern, bp.threads, bp.smem_bytes));
   bp.nchunk = g.nchunk;
   return true;
@@ -1360,7 +1330,6 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   const BwdWorkspace wo = bwd_workspace(d, g, bp);
   if (ws_bytes < wo.total * sizeof(float)) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, wo.total * sizeof(float)); return IGN_ERR_INVALID; }
   if (((uintptr_t)ws & 15) != 0) { set_error("shapelet_backward: workspace must be 16-byte aligned"); return IGN_ERR_INVALID; }
-  if (((uintptr_t)xn & 15) != 0) { set_error("shapelet_backward: xn must be 16-byte aligned (bulk copies)"); return IGN_ERR_INVALID; }
   float* base = reinterpret_cast<float*>(ws);
   // 1. pooling backward (elementwise, HBM-bound): d -> per-window coefficients + per-row scalars
   if (d.dist == IGN_DIST_PEARSON) {
@@ -1429,8 +1398,8 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     IGN_CUDA(cudaGetLastError());
     tie = tflags;
   }
-  BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, bp.nstage, tie};
-  debug_plan("bwd", g, bp.threads, bp.smem_bytes, occupancy(kern, bp.threads, bp.smem_bytes), bp.nseg * 10 + bp.nstage, bp.nlb);
+  BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, tie};
+  debug_plan("bwd", g, bp.threads, bp.smem_bytes, occupancy(kern, bp.threads, bp.smem_bytes), bp.nseg, bp.nlb);
   int rc;
   { PhaseScope ph(PH_CONTRACT, st); rc = run_bwd(kern, g, a, bp, st); }
   if (rc) return rc;
