@@ -1082,7 +1082,7 @@ bool base_geo(const ign_shapelet_desc& d, Geo& g) {
   return g.Tw > 0;
 }
 
-// Resident CTAs per SM of `kern` at this block size and dynamic shared memory (host API, cached).
+// Resident CTAs per SM of `kern` at this block size and dynamic shared memory (host API, cached; IGN_DEBUG_PLAN output).
 template <typename Kern>
 int occupancy(Kern kern, int threads, size_t smem) {
   static std::mutex mu;
@@ -1107,8 +1107,7 @@ int occupancy(Kern kern, int threads, size_t smem) {
 // SLOWER (L1 backward 11.9 -> 12.6 ms at ~3 waves) — a CTA that is alone on its SM runs several times faster, so a
 // short last wave costs little, while many CTAs in different phases hide each other's pass barriers.
 constexpr int kTargetCtasPerSm = 24;
-void plan_chunks(Geo& g, int ctas_per_chunk, int NB, int wave) {
-  (void)wave;
+void plan_chunks(Geo& g, int ctas_per_chunk, int NB) {
   static const int target_env = getenv("IGN_PLAN_CTAS_PER_SM") ? atoi(getenv("IGN_PLAN_CTAS_PER_SM")) : 0;
   const int target = (target_env > 0 ? target_env : kTargetCtasPerSm) * sm_count();
   const int units = ceil_div(g.B, NB);
@@ -1128,7 +1127,7 @@ struct FwdPlan { int threads; size_t smem_bytes; };
 using FwdKernel = void (*)(const Geo, const FwdArgs);
 using BwdKernel = void (*)(const Geo, const BwdArgs);
 
-bool plan_fwd(Geo& g, int TT, FwdPlan& fp, FwdKernel kern) {
+bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
   g.dbuf = 0;
   const size_t cap_soft = 111 * 1024, cap_hard = (size_t)max_optin_smem() - 1024;   // two CTAs per SM
   const int Kpad = round_up(g.K, g.KK);
@@ -1163,7 +1162,7 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp, FwdKernel kern) {
   g.KB = KB; g.nkb = ceil_div(Kpad, KB); g.NB = best;
   fp.threads = bthr;
   fp.smem_bytes = fwd_smem_floats(g, best, KB, ntile) * 4;
-  plan_chunks(g, g.M * g.nkb, best, sm_count() * occupancy(kern, fp.threads, fp.smem_bytes));
+  plan_chunks(g, g.M * g.nkb, best);
   return true;
 }
 
@@ -1184,7 +1183,7 @@ size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
   return mult * xs + cbt + (size_t)KB * g.s * g.LQ + KB;
 }
 
-bool plan_bwd(Geo& g, BwdPlan& bp, BwdKernel kern) {
+bool plan_bwd(Geo& g, BwdPlan& bp) {
   const size_t cap = (size_t)max_optin_smem() - 1024;
   const size_t cap_soft = 56 * 1024;     // aim for >= 4 CTAs per SM
   const int ntl_all = g.s * g.LQ / LT;
@@ -1215,7 +1214,7 @@ bool plan_bwd(Geo& g, BwdPlan& bp, BwdKernel kern) {
   bp.threads = round_up(bestNB * bestSeg * per_slot, 32);
   bp.hcap = bwd_hash_cap(g, KB);
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
-  plan_chunks(g, g.M * g.nkb * nlb, bestNB, sm_count() * occupancy(kern, bp.threads, bp.smem_bytes));
+  plan_chunks(g, g.M * g.nkb * nlb, bestNB);
   bp.nchunk = g.nchunk;
   return true;
 }
@@ -1255,9 +1254,12 @@ FwdKernel fwd_kernel(bool l1, int KK, int TT) {
 
 BwdKernel bwd_kernel(int dist) { return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1> : shapelet_bwd_kernel<OP_DOT>; }
 
-void debug_plan(const char* what, const Geo& g, int threads, size_t smem, int occ, int extra0, int extra1) {
+bool debug_plan_on() {
   static const bool on = getenv("IGN_DEBUG_PLAN") != nullptr;
-  if (!on) return;
+  return on;
+}
+
+void debug_plan(const char* what, const Geo& g, int threads, size_t smem, int occ, int extra0, int extra1) {
   fprintf(stderr, "[ign plan] %s L=%d Tw=%d K=%d: threads=%d smem=%zu occ=%d NB=%d KB=%d nkb=%d nchunk=%d (base %d, +1 x %d) grid=%d waves=%.2f  [%d %d]\n",
           what, g.L, g.Tw, g.K, threads, smem, occ, g.NB, g.KB, g.nkb, g.nchunk, g.cbase, g.cextra,
           g.M * g.nkb * g.nchunk * max(1, extra1), (double)g.M * g.nkb * g.nchunk * max(1, extra1) / (sm_count() * occ), extra0, extra1);
@@ -1292,8 +1294,8 @@ int launch_shapelet_fwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   const int TT = g.Tw >= 64 ? 8 : 4;
   FwdPlan fp;
   const FwdKernel kern = fwd_kernel(d.dist == IGN_DIST_L1, g.KK, TT);
-  if (!plan_fwd(g, TT, fp, kern)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
-  debug_plan("fwd", g, fp.threads, fp.smem_bytes, occupancy(kern, fp.threads, fp.smem_bytes), TT, 1);
+  if (!plan_fwd(g, TT, fp)) { set_error("shapelet_forward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  if (debug_plan_on()) debug_plan("fwd", g, fp.threads, fp.smem_bytes, occupancy(kern, fp.threads, fp.smem_bytes), TT, 1);
   FwdArgs a{xn, st0, W, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, d.stride)};
   return run_fwd(kern, g, a, fp, st);
 }
@@ -1315,7 +1317,7 @@ BwdWorkspace bwd_workspace(const ign_shapelet_desc& d, const Geo& g, const BwdPl
 
 size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
   Geo g; BwdPlan bp;
-  if (!base_geo(d, g) || !plan_bwd(g, bp, bwd_kernel(d.dist))) return 0;
+  if (!base_geo(d, g) || !plan_bwd(g, bp)) return 0;
   return bwd_workspace(d, g, bp).total * sizeof(float);
 }
 
@@ -1326,7 +1328,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   Geo g; BwdPlan bp;
   if (!base_geo(d, g)) { set_error("shapelet_backward: T=%d < L=%d", d.T, d.L); return IGN_ERR_INVALID; }
   const BwdKernel kern = bwd_kernel(d.dist);
-  if (!plan_bwd(g, bp, kern)) { set_error("shapelet_backward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  if (!plan_bwd(g, bp)) { set_error("shapelet_backward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
   const BwdWorkspace wo = bwd_workspace(d, g, bp);
   if (ws_bytes < wo.total * sizeof(float)) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, wo.total * sizeof(float)); return IGN_ERR_INVALID; }
   if (((uintptr_t)ws & 15) != 0) { set_error("shapelet_backward: workspace must be 16-byte aligned"); return IGN_ERR_INVALID; }
@@ -1399,7 +1401,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     tie = tflags;
   }
   BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, tie};
-  debug_plan("bwd", g, bp.threads, bp.smem_bytes, occupancy(kern, bp.threads, bp.smem_bytes), bp.nseg, bp.nlb);
+  if (debug_plan_on()) debug_plan("bwd", g, bp.threads, bp.smem_bytes, occupancy(kern, bp.threads, bp.smem_bytes), bp.nseg, bp.nlb);
   int rc;
   { PhaseScope ph(PH_CONTRACT, st); rc = run_bwd(kern, g, a, bp, st); }
   if (rc) return rc;
