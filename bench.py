@@ -293,7 +293,13 @@ def main():
     sampler = ClockSampler(exp.local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.5)          # let nvidia-smi start up outside the timed region (its launch cost 2-5 ms of step 1)
+    # nvidia-smi needs ~0.5 s to start (its launch cost 2-5 ms of step 1 when it overlapped the timed region).  The GPU
+    # is kept busy with untimed steps meanwhile — an idle half second let the clocks drop and the first timed step
+    # then took up to 39 ms instead of 24.  Same count on every rank (the step contains the gradient all-reduce).
+    for _ in range(20):
+        step_no += 1
+        exp.train_step(x, y, mask, 0, step_no)
+    torch.cuda.synchronize()
     barrier()
     sampler.mark()
     STATS.reset(timing=False)
@@ -444,6 +450,7 @@ def main():
         "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, B, world),
+        "untimed_steps_before_region": max(a.warmup, 3) + 20,   # W warm-up + 20 while the clock sampler starts
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": dominant, "rooflines": rooflines, "cpu_baseline": cpu,
         "shapelet_layer": {"fwd_tflops": fams.get("shapelet_fwd", {}).get("ops", 0) / max(1e-9, fams.get("shapelet_fwd", {}).get("ms", 0) * 1e-3) / 1e12,
