@@ -120,3 +120,29 @@ def test_transformer_expert_matches_reference_golden_on_cpu():
     with torch.no_grad():
         out = m(x, torch.ones(x.shape[0], x.shape[1]), None, None)
     assert torch.allclose(out, torch.as_tensor(g["dnn_preds"]), rtol=1e-4, atol=1e-5)
+
+
+def test_reference_arm_line_contract():
+    """`bench.py --impl reference` (the oracle port timed on the host cores): one JSON line with the bench contract's keys
+    on rank 0, silence and exit 0 on the other ranks of a torchrun launch."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train samples/sec" and line["unit"] == "samples/s"
+    assert line["value"] > 0 and line["steps"] == 1 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["config"]["workload"].startswith("InterpGN(FCN)") and line["data"] == "synthetic"
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    e2e = line["e2e"]
+    assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
