@@ -38,11 +38,12 @@ def test_sbm_transform_host(flag, dist):
 
 
 def test_instnorm_cluster_kernel_geometries():
-    """instnorm_cluster_kernel (odd channel counts, 16-byte aligned sample slabs): cluster sizes 1..8, a last rank with
+    """instnorm_cluster_kernel (channel counts with gcd(M, 32) <= 2, 16-byte aligned sample slabs): cluster sizes 1..8, a last rank with
     fewer rows, ranks with no rows at all, large offsets (one-pass shifted variance) and a constant channel."""
     from layers.shapelet_ops import instance_norm
     torch.manual_seed(11)
-    for (B, T, M) in [(1, 8, 3), (3, 20, 7), (2, 996, 125), (2, 1000, 125), (2, 100, 501), (2, 4100, 5), (3, 1651, 61)]:
+    for (B, T, M) in [(1, 8, 3), (3, 20, 7), (2, 996, 125), (2, 1000, 125), (2, 100, 501), (2, 4100, 5), (3, 1651, 61),
+                      (2, 100, 6), (2, 1000, 122)]:
         assert (T * M) % 4 == 0 or T == 1651
         x = torch.randn(B, T, M) * 2.5 + 40.0          # mean >> std: the two-pass reference must still be matched
         x[:, :, 0] = 3.25                               # a constant channel: std = 0 -> (x - mean) / 1e-8 = 0
