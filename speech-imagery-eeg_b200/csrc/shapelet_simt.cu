@@ -23,18 +23,19 @@
 // shapelet into `stride` residue classes: sum_l f(x[t*s+l], w[l]) = sum_r sum_q f(x_r[t+q], w_r[q]),
 // i.e. `stride` unit-stride correlations, so the same sliding-window code runs for every stride.
 //
-// Backward (stored-d).  One CTA owns a channel, a block of shapelets, a block of lags and a batch chunk.
-//   phase A  the d rows are copied to shared memory cooperatively; one warp per row recomputes the
-//            soft-max statistics (Z, S1, arg-max of p with first-index ties — exactly the reference's
-//            hard one-hot, Shapelet.py:79) and turns d into a_t = dLoss/dd_t (times the mode's norm
-//            factor) in place
-//   phase B  contraction with the series; each thread owns 8 lags of ONE shapelet in registers for the
-//            whole batch chunk and slides along the window axis with the same 12-register ring:
+// Backward (stored-d), four kernels per length group:
+//   pooling backward (pool_bwd_reg_kernel, HBM-bound): one warp per saved distance row recomputes the soft-max
+//            statistics (Z, S1, arg-max of p with first-index ties — exactly the reference's hard one-hot,
+//            Shapelet.py:79) and writes a_t = dLoss/dd_t (times the mode's norm factor) to the coefficient workspace
+//   tie pre-check (L1): which series rows can hold a value equal to one of the CTA's shapelet values
+//   contraction (shapelet_bwd_kernel): one CTA owns a channel, a block of shapelets, a block of lags and a batch
+//            chunk; each thread owns 8 lags of ONE shapelet in registers for the whole chunk and slides along the window
+//            axis with the same 12-register ring:
 //              L1 : dW[l] = -(1/L) sum_t a_t sign(x[t+l]-w[l])     (sign(0)=0, exact)
 //              dot: G[l]  = sum_t a_t x[t+l], then dW from G and two per-shapelet scalars (finalize)
-// ~64 registers per thread, so several CTAs share an SM and one CTA's phase A hides under another's
-// phase B.  Partial sums are combined in a fixed order (shared memory, then a per-chunk workspace, then
-// the finalize kernel) so the result is bit-reproducible run to run — no float atomics.
+//   finalize: per-chunk partials summed in a fixed order, closed-form scalar terms
+// Partial sums are combined in a fixed order (shared memory, then a per-chunk workspace, then the finalize
+// kernel) so the result is bit-reproducible run to run — no float atomics.
 #include "ign_common.cuh"
 
 #include <math.h>
