@@ -1,9 +1,10 @@
 """Batch source with the reference's contract: data_provider(args, flag) -> (Dataset, DataLoader) whose
 batches are (X[B,T,C] float, y[B,1], padding_mask[B,T]) (reference data_factory/uea.py:42, eeg.py:93).
 
-The reference's real loaders (sktime .ts, mne .fif) are outside the hot path and their data is not in this
-environment; `--data synthetic` (also the fallback when a dataset directory is absent) generates seeded
-class-conditional series of the named shape, so run.py / run_uea.sh exercise the full training path.
+Real data: UEA `.ts` archives (data_provider/uea.py) and dumped CHISCO epochs (data_provider/chisco.py) when the
+dataset directory exists.  `--data synthetic` generates seeded class-conditional series of the named shape, so
+run.py / run_uea.sh exercise the full training path without the archives; asking for a real archive whose directory
+is missing raises (unless --allow_synthetic) instead of silently training on synthetic series.
 """
 import math
 import os
@@ -68,6 +69,8 @@ def _shape_for(args):
     if getattr(args, "syn_shape", None):
         c, t, k = (int(v) for v in args.syn_shape.split(","))
         return c, t, k
+    if getattr(args, "dataset", "") in CHISCO_SHAPE:      # --data synthetic --dataset EEG3 | EEG
+        return CHISCO_SHAPE[args.dataset]
     if args.data in CHISCO_SHAPE:
         return CHISCO_SHAPE[args.data]
     return UEA_SHAPES.get(getattr(args, "dataset", ""), (6, 100, 4))
@@ -89,30 +92,66 @@ def loso_dataset(args):
     return ds
 
 
+def equal_shard(n, world, rank):
+    """Indices of rank `rank`'s shard of n samples: every rank gets ceil(n / world) of them (the tail wraps around to
+    the first samples, DistributedSampler-style), so all ranks run the same number of optimisation steps per epoch —
+    the gradient all-reduce is one collective per step and ranks with different step counts would desynchronise."""
+    per = math.ceil(n / world)
+    return [(rank + i * world) % n for i in range(per)]
+
+
+def _require_real_root(args, root):
+    """A real archive was asked for (`--data UEA|EEG|EEG3`) but its directory is missing: refuse, unless the caller
+    explicitly allows synthetic series of that shape (`--allow_synthetic`) — silently training on synthetic data
+    would file its accuracy under the real dataset's name."""
+    if getattr(args, "allow_synthetic", False):
+        print(f"WARNING: --data {args.data}: {root!r} does not exist; using SYNTHETIC series of that shape "
+              f"(--allow_synthetic)", flush=True)
+        args.data_source = "synthetic"
+        return
+    raise FileNotFoundError(
+        f"--data {args.data}: dataset directory {root!r} does not exist. Pass --data_root, or --data synthetic "
+        f"(or --allow_synthetic) to train on synthetic series of the same shape.")
+
+
 def data_provider(args, flag):
     """flag in {'train','val','test'} (reference data_factory.py:29).  Under data-parallel training the
-    train split is sharded by rank (every rank draws a disjoint seeded shard)."""
+    train split is sharded by rank (every rank gets an equally sized shard)."""
     real_root = getattr(args, "root_path", None)
-    if args.data == "UEA" and real_root and os.path.isdir(real_root):
+    world, rank = getattr(args, "world_size", 1), getattr(args, "rank", 0)
+    have_root = bool(real_root) and os.path.isdir(real_root)
+    if args.data != "synthetic" and not have_root:
+        _require_real_root(args, real_root)
+    if args.data == "UEA" and have_root:
         # real archive on disk: the sktime-free .ts reader with the reference's preprocessing (data_provider/uea.py)
         from data_provider import uea
         ds = uea.UEADataset(real_root, flag=flag)
-        world, rank = getattr(args, "world_size", 1), getattr(args, "rank", 0)
-        if flag == "train" and world > 1:                      # data parallel: disjoint shard per rank
-            keep = list(range(rank, len(ds), world))
+        if flag == "train" and world > 1:                      # data parallel: equally sized shard per rank
+            keep = equal_shard(len(ds), world, rank)
             ds.x, ds.y = [ds.x[i] for i in keep], ds.y[keep]
-        max_len = int(getattr(args, "seq_len", 0) or ds.max_seq_len)
+
+        def collate(batch):
+            # the padded length is read when a batch is built, as the reference's collate lambda reads args.seq_len
+            # (data_factory.py:107,136): Experiment sets it once to the longest series over ALL splits, so train,
+            # val and test batches share one length (and the deep expert's Linear(d_model * seq_len) fits them all)
+            return uea.collate_fn(batch, max_len=int(getattr(args, "seq_len", 0) or ds.max_seq_len))
         loader = DataLoader(ds, batch_size=args.batch_size, shuffle=(flag == "train"), num_workers=args.num_workers,
-                            drop_last=False, collate_fn=lambda b: uea.collate_fn(b, max_len=max_len),
-                            pin_memory=torch.cuda.is_available())
+                            drop_last=False, collate_fn=collate, pin_memory=torch.cuda.is_available())
         return ds, loader
-    if args.data in ("EEG", "EEG3") and real_root and os.path.isdir(real_root):
-        raise NotImplementedError(
-            "CHISCO .fif ingestion (mne) is outside the B200 hot path (SURVEY.md §8 f3); use --data synthetic")
+    if args.data in ("EEG", "EEG3") and have_root:
+        # dumped CHISCO epochs with the reference's per-epoch preprocessing and 39 -> 3 map (data_provider/chisco.py)
+        from data_provider import chisco
+        ds = chisco.ChiscoEpochs(real_root, flag=flag, three_class=(args.data == "EEG3"),
+                                 max_files=getattr(args, "max_files", None))
+        if flag == "train" and world > 1:
+            keep = equal_shard(len(ds), world, rank)
+            ds.x, ds.y, ds.subject = ds.x[keep], ds.y[keep], ds.subject[keep]
+        loader = DataLoader(ds, batch_size=args.batch_size, shuffle=(flag == "train"), num_workers=args.num_workers,
+                            drop_last=False, collate_fn=collate_fn, pin_memory=torch.cuda.is_available())
+        return ds, loader
     channels, seq_len, num_class = _shape_for(args)
     n = {"train": getattr(args, "syn_train", 512), "val": getattr(args, "syn_val", 128),
          "test": getattr(args, "syn_test", 128)}[flag]
-    world, rank = getattr(args, "world_size", 1), getattr(args, "rank", 0)
     seed = {"train": 11, "val": 22, "test": 33}[flag] + 1000 * max(0, int(getattr(args, "seed", 0)))
     if flag == "train" and world > 1:
         n = math.ceil(n / world)

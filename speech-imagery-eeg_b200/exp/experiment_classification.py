@@ -79,7 +79,8 @@ class Experiment(object):
         self.grads = FlatGradAllReduce(self.model, 1 if independent else self.world)
         a = self.args
         self.checkpoint_dir = "./checkpoints/{}/{}/dnn-{}_seed-{}_k-{}_div-{}_reg-{}_eps-{}_beta-{}_dfunc-{}_cls-{}".format(
-            a.model, a.dataset, a.dnn_type, a.seed, a.num_shapelet, a.lambda_div, a.lambda_reg, a.epsilon,
+            a.model, a.dataset + ("-synthetic" if getattr(a, "data_source", getattr(a, "data", "")) == "synthetic" else ""),
+            a.dnn_type, a.seed, a.num_shapelet, a.lambda_div, a.lambda_reg, a.epsilon,
             a.beta_schedule, a.distance_func, a.sbm_cls)
         if self.is_main and load_data:
             os.makedirs(self.checkpoint_dir, exist_ok=True)
@@ -93,7 +94,10 @@ class Experiment(object):
     def _get_params_from_data(self):
         """seq_len / enc_in / num_class are injected from the dataset (reference :166-249)."""
         ds = self.train_data
-        self.args.seq_len = int(getattr(ds, "max_seq_len", getattr(ds, "seq_len", 845)))
+        # one padded length for every split: the longest series of train / val / test (variable-length UEA archives
+        # such as JapaneseVowels have longer TEST series; the collate functions read args.seq_len per batch)
+        self.args.seq_len = max(int(getattr(d, "max_seq_len", getattr(d, "seq_len", 845)))
+                                for d in (self.train_data, self.val_data, self.test_data))
         self.args.enc_in = int(getattr(ds, "enc_in", 122))
         self.args.num_class = int(getattr(ds, "num_class", 3))
         self.args.pred_len, self.args.label_len = 0, 0

@@ -12,8 +12,10 @@ import torch
 import torch.distributed as dist
 
 
-def init_distributed():
-    """Reads torchrun's environment.  Returns (rank, local_rank, world_size)."""
+def init_distributed(timeout=None):
+    """Reads torchrun's environment.  Returns (rank, local_rank, world_size).  `timeout` (datetime.timedelta) replaces
+    the process group's default collective timeout (NCCL: 10 minutes) — leave-one-subject-out runs pass days, because
+    their ranks train whole folds independently and only meet at the final gather."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -21,7 +23,8 @@ def init_distributed():
         backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+        kw = {} if timeout is None else {"timeout": timeout}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw,
                                 device_id=torch.device("cuda", local) if backend == "nccl" else None)
     return rank, local, world
 

@@ -33,6 +33,7 @@ FLAGS = [
     ("--shapelet_precision", str, "fp32"), ("--syn_shape", str, None), ("--syn_train", int, 512),
     ("--syn_val", int, 128), ("--syn_test", int, 128), ("--syn_subjects", int, 1),
     ("--loso", "store_true", False),      # leave-one-subject-out: one fold per subject, folds spread over the ranks
+    ("--allow_synthetic", "store_true", False),   # --data UEA|EEG|EEG3 without the archive on disk: synthetic series of its shape
 ]
 
 
@@ -48,8 +49,9 @@ def get_args(argv=None):
     if args.data not in ("synthetic", "EEG", "EEG3", "UEA"):
         parser.error("--data must be one of synthetic, EEG, EEG3, UEA")
     args.root_path = args.data_root if args.data in ('EEG', 'EEG3') else f"{args.data_root}/{args.dataset}"
-    if not os.path.isdir(args.root_path):
-        args.data_source = "synthetic"          # shapes still follow --data / --dataset
+    # where the samples really come from; it is part of the checkpoint directory name and of test_results.pkl.
+    # A real archive whose directory is missing raises in data_provider unless --allow_synthetic is given.
+    args.data_source = "synthetic" if (args.data == "synthetic" or not os.path.isdir(args.root_path)) else args.data
     args.is_training = True
     return args
 
@@ -69,7 +71,11 @@ def run_loso(args):
     from exp import loso
     from exp.experiment_classification import Experiment
     from exp.parallel import init_distributed
-    rank, _, world = init_distributed()
+    import datetime
+    import json
+    # ranks own different numbers of folds and meet only at the final gather: a rank that finishes early (or owns no
+    # fold at all) must be allowed to wait for the slowest one, far beyond NCCL's default 10-minute watchdog
+    rank, _, world = init_distributed(timeout=datetime.timedelta(days=7))
     seed = 0 if args.seed == -1 else args.seed
     set_seed(seed)
     args.seed = seed
@@ -88,6 +94,10 @@ def run_loso(args):
         exp.train()
         loss, res, _ = exp.test(save_csv=False)
         local[f] = (subject, loss, None if res is None else res.accuracy)
+        os.makedirs(exp.checkpoint_dir, exist_ok=True)      # a fold's result survives a later failure of another rank
+        with open(os.path.join(exp.checkpoint_dir, "fold_result.json"), "w") as fh:
+            json.dump({"fold": f, "subject": int(subject), "test_loss": float(loss), "accuracy": local[f][2],
+                       "rank": rank}, fh)
         torch.cuda.empty_cache()
     merged = loso.gather_results(local, world)
     mean_acc, rows = loso.summarize(merged)

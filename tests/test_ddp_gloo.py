@@ -112,7 +112,7 @@ def test_synthetic_provider_contract_and_rank_sharding():
     a.rank = 1
     d1, _ = data_provider(a, "train")
     assert len(d0) == len(d1) == 256 and not torch.equal(d0.x, d1.x)
-    b = run.get_args(["--data", "EEG3"])
+    b = run.get_args(["--data", "synthetic", "--dataset", "EEG3"])     # CHISCO 3-class shape, synthetic series
     b.seed = 0; b.syn_train = 4
     ds3, _ = data_provider(b, "train")
     assert (ds3.enc_in, ds3.max_seq_len, ds3.num_class) == (125, 1000, 3)

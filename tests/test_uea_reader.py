@@ -82,3 +82,65 @@ def test_data_provider_uses_the_archive_when_it_is_on_disk(tmp_path):
     assert X.shape[1:] == (5, 2) and X.shape[0] == 3 and m.shape == (3, 5) and y.shape == (3, 1)
     ds_te, _ = data_provider(args, "test")
     assert len(ds_te) == 3 and ds_te.max_seq_len == 5
+
+
+def test_all_splits_share_one_padded_length_when_test_series_are_longer(tmp_path):
+    """JapaneseVowels-like archives have longer TEST series than TRAIN series.  The collate length is read per batch
+    from args.seq_len (as the reference's collate lambda does, data_factory.py:107,136), which the experiment sets once
+    to the longest series over all splits — so every split pads to the same T and the model built for it fits."""
+    from types import SimpleNamespace
+    from data_provider.data_factory import data_provider
+    d = tmp_path / "Toy2"
+    d.mkdir()
+    (d / "Toy2_TRAIN.ts").write_text(TS.replace("?,1.0,1.0,1.0,1.0:0.0,0.0,0.0,0.0,?:flat\n", "1.0,1.0:0.0,0.0:flat\n"))
+    (d / "Toy2_TEST.ts").write_text(TS)                       # longest series: 5 (train: 4)
+    args = SimpleNamespace(data="UEA", dataset="Toy2", root_path=str(d), batch_size=8, num_workers=0, world_size=1, rank=0)
+    splits = {f: data_provider(args, f) for f in ("train", "val", "test")}
+    assert splits["train"][0].max_seq_len == 4 and splits["test"][0].max_seq_len == 5
+    # what Experiment._get_params_from_data does
+    args.seq_len = max(ds.max_seq_len for ds, _ in splits.values())
+    for f, (_, dl) in splits.items():
+        X, _, m = next(iter(dl))
+        assert X.shape[1] == 5 and m.shape[1] == 5, f
+    # a second seed in the same process rebuilds the loaders with args.seq_len already set: same lengths again
+    X, _, _ = next(iter(data_provider(args, "train")[1]))
+    assert X.shape[1] == 5
+
+
+def test_rank_shards_are_equally_sized_so_every_rank_runs_the_same_number_of_steps(tmp_path):
+    import math
+    from types import SimpleNamespace
+    from data_provider.data_factory import data_provider, equal_shard
+    for n, world in ((129, 2), (5, 4), (7, 8), (64, 2)):
+        shards = [equal_shard(n, world, r) for r in range(world)]
+        assert {len(s) for s in shards} == {math.ceil(n / world)}
+        assert set(i for s in shards for i in s) == set(range(n))          # every sample is seen
+    d = tmp_path / "Toy3"
+    d.mkdir()
+    rows = TS.split("@data\n")[1].strip().split("\n")
+    body = "\n".join(rows[i % 4] for i in range(9)) + "\n"              # 9 cases, world 2, batch 2: 3 steps on both ranks
+    (d / "Toy3_TRAIN.ts").write_text(TS.split("@data\n")[0] + "@data\n" + body)
+    (d / "Toy3_TEST.ts").write_text(TS)
+    steps = []
+    for rank in range(2):
+        args = SimpleNamespace(data="UEA", dataset="Toy3", root_path=str(d), batch_size=2, num_workers=0, world_size=2,
+                               rank=rank, seq_len=0)
+        ds, dl = data_provider(args, "train")
+        steps.append(len(dl))
+    assert steps == [3, 3]
+
+
+def test_missing_archive_raises_instead_of_silently_training_on_synthetic_series(tmp_path):
+    import pytest
+    import run
+    from data_provider.data_factory import data_provider
+    a = run.get_args(["--data", "UEA", "--data_root", str(tmp_path / "nowhere"), "--dataset", "JapaneseVowels"])
+    assert a.data_source == "synthetic"
+    with pytest.raises(FileNotFoundError, match="does not exist"):
+        data_provider(a, "train")
+    b = run.get_args(["--data", "UEA", "--data_root", str(tmp_path / "nowhere"), "--dataset", "JapaneseVowels",
+                      "--allow_synthetic"])
+    b.seed = 0
+    ds, _ = data_provider(b, "train")                       # explicit opt-in: synthetic series of the archive's shape
+    assert (ds.enc_in, ds.max_seq_len, ds.num_class) == (12, 29, 9)
+    assert run.get_args(["--dataset", "JapaneseVowels"]).data_source == "synthetic"        # --data synthetic is the default
