@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--num_class", type=int, default=3)
     ap.add_argument("--cpu_batch", type=int, default=2)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_extras", action="store_true", help="skip the cosine/3xtf32 mode, the same-GPU eager comparator "
+                    "and the config-1 / config-5 lines (they run at N=1 only)")
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the deep expert (reference default is fp32 in its scripts)")
     return ap.parse_args()
 
@@ -154,8 +156,7 @@ class CpuReferenceStep:
     def __init__(self, a):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import ign_oracle as O
-        from models.FullyConvNet import FullyConvNetwork
-        from models.Transformer import Model as TransformerExpert
+        import ign_oracle_experts as OE          # CPU restatement of the deep experts: nothing from the product package
         self.O = O
         cfg = model_args(a)
         torch.manual_seed(0)
@@ -164,7 +165,7 @@ class CpuReferenceStep:
         self.strides = [O.shapelet_stride(T, L) for L in self.lens]
         self.Ws = [torch.normal(0, 1, (K_PER_LEN, M, L)).requires_grad_(True) for L in self.lens]
         self.Wc = (torch.randn(C, K_PER_LEN * M * len(self.lens)) * 0.02).requires_grad_(True)
-        self.fcn = TransformerExpert(cfg) if a.dnn_type == "Transformer" else FullyConvNetwork(cfg)
+        self.fcn = OE.build_expert(a.dnn_type, cfg).train()
         self.mode = O.resolve_mode(a.distance_func, a.memory_efficient)
         self.opt = torch.optim.Adam(self.Ws + [self.Wc] + list(self.fcn.parameters()), lr=5e-3)
         self.cfg = cfg
@@ -172,7 +173,7 @@ class CpuReferenceStep:
     def step(self, x, y):
         O = self.O
         sbm_out, probs, dists = O.sbm_forward(x, self.Ws, self.strides, self.Wc, 1.0, self.mode)
-        deep_out = self.fcn(x, torch.ones(x.shape[0], x.shape[1]), None, None)
+        deep_out = self.fcn(x, torch.ones(x.shape[0], x.shape[1], device=x.device), None, None)
         out, eta = O.gate_forward(sbm_out, deep_out)
         loss = torch.nn.functional.cross_entropy(out, y) + O.sbm_loss(self.Wc, self.Ws, 0.1, 0.1) \
             + torch.nn.functional.cross_entropy(sbm_out, y)
@@ -189,8 +190,11 @@ def time_cpu_reference(a, steps, warmup, batch, budget_s=None):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(batch, ref.cfg.seq_len, ref.cfg.enc_in, generator=g)
     y = torch.randint(0, ref.cfg.num_class, (batch,), generator=g)
-    for _ in range(warmup):
+    tw = time.perf_counter()
+    for i in range(warmup):          # the same warm-up count as the GPU arm, but never more than a minute of it
         ref.step(x, y)
+        if budget_s is not None and time.perf_counter() - tw > 60.0:
+            break
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
@@ -208,15 +212,18 @@ def run_reference_arm(a):
     their outputs by tests/golden).  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    # bounded sample: one CHISCO-shaped sample per step (the reference needs ~4 GB per sample), capped in time
-    sps, ms, done, cores = time_cpu_reference(a, a.steps, min(a.warmup, 1), 1, budget_s=240.0)
+    # bounded sample: a.cpu_batch (2) CHISCO-shaped samples per step (the reference's eager path needs ~4 GB per
+    # sample), the same warm-up count as the GPU arm, timed steps capped at 240 s
+    warm = max(a.warmup, 3)
+    sps, ms, done, cores = time_cpu_reference(a, a.steps, warm, a.cpu_batch, budget_s=240.0)
     line = {
         "impl": "reference", "metric": "train samples/sec", "value": sps, "unit": "samples/s", "n_gpus": a.gpus,
-        "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": done, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, 1, 1),
+        "config": workload_config(a, a.cpu_batch, 1),
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "InterpGN(%s) full train step, batch 1 of the config-2 workload, %d steps" % (a.dnn_type, done)},
+                         "sample": "InterpGN(%s) full train step, batch %d of the config-2 workload, %d timed steps after %d warm-up"
+                                   % (a.dnn_type, a.cpu_batch, done, warm)},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -246,16 +253,10 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-def main():
-    global _REAL_STDOUT
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
-    a = parse()
-    if a.impl == "reference":
-        return run_reference_arm(a)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+def run_ours(a, primary=True):
+    """One measurement of this repo's training step under the contract: W warm-up, K timed steps with inputs resident
+    (CUDA events, max over ranks), per-kernel rooflines from a second instrumented pass, and (primary only) the clock
+    sampler, the end-to-end region with pinned host batches and the CPU baseline.  Returns the JSON line as a dict."""
     import torch.distributed as dist
     from exp.experiment_classification import Experiment
     from layers.shapelet_ops import STATS
@@ -291,7 +292,7 @@ def main():
         exp.train_step(x, y, mask, 0, step_no)
     # ---------------- device-resident timed region ----------------
     sampler = ClockSampler(exp.local_rank)
-    if rank == 0:
+    if rank == 0 and primary:
         sampler.start()
     # nvidia-smi needs ~0.5 s to start (its launch cost 2-5 ms of step 1 when it overlapped the timed region).  The GPU
     # is kept busy with untimed steps meanwhile — an idle half second let the clocks drop and the first timed step
@@ -318,14 +319,15 @@ def main():
         for mk in marks:
             per.append(prev.elapsed_time(mk)); prev = mk
         sys.stderr.write("per-step ms: " + " ".join("%.2f" % v for v in per) + "\n")
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and primary) else None
     launches = STATS.launches
+    engines = STATS.engine_summary()
     # per-kernel durations for the rooflines: the same steps once more with a CUDA-event pair around every C-ABI
     # call, on the stream the kernels run on (kept out of the timed region above so that it is unperturbed)
     ksteps = min(a.steps, 5)
     import ctypes
     from layers import ign_cabi as CABI
-    CABI.check(CABI.lib.ign_debug_bwd_phase_timing(1), "ign_debug_bwd_phase_timing")     # events around the four phases inside ign_shapelet_backward
+    CABI.check(CABI.lib.ign_debug_bwd_phase_timing(1), "ign_debug_bwd_phase_timing")     # events around the phases inside ign_shapelet_backward
     STATS.reset(timing=True)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
@@ -345,33 +347,34 @@ def main():
             kern[name] = (int(ph_n[i]), float(ph_ms[i]))
     value = world * B * a.steps / (ms_total * 1e-3)
 
-    # ---------------- end-to-end region: pinned host batch in, loss out, every step ----------------
-    xh = torch.randn(B, T, M).pin_memory()
-    yh = torch.randint(0, C, (B, 1)).pin_memory()
-    mh = torch.ones(B, T, dtype=torch.bool).pin_memory()
-    from exp.parallel import DevicePrefetcher
-    for xd, yd, md in DevicePrefetcher(((xh, yh, mh) for _ in range(2)), dev):   # warm-up of the same path
-        step_no += 1
-        float(exp.train_step(xd, yd, md, 0, step_no))
-    barrier()
-    t0 = time.perf_counter()
-    # the public training loop's own batch path (Experiment.train): every step's batch is copied from pinned host
-    # memory inside the timed region, one batch ahead on a side stream; the first copy is not overlapped
-    for xd, yd, md in DevicePrefetcher(((xh, yh, mh) for _ in range(a.steps)), dev):
-        step_no += 1
-        loss = exp.train_step(xd, yd, md, 0, step_no)
-        loss_host = float(loss)                    # D2H read of the step's result
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": world * B * a.steps / e2e_s, "unit": "samples/s",
-           "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8 + mh.numel(), "d2h_bytes_per_step": 4,
-           "ms_per_step": e2e_s / a.steps * 1e3, "last_loss": loss_host}
-
+    e2e = None
+    if primary:
+        # ---------------- end-to-end region: pinned host batch in, loss out, every step ----------------
+        xh = torch.randn(B, T, M).pin_memory()
+        yh = torch.randint(0, C, (B, 1)).pin_memory()
+        mh = torch.ones(B, T, dtype=torch.bool).pin_memory()
+        from exp.parallel import DevicePrefetcher
+        for xd, yd, md in DevicePrefetcher(((xh, yh, mh) for _ in range(2)), dev):   # warm-up of the same path
+            step_no += 1
+            float(exp.train_step(xd, yd, md, 0, step_no))
+        barrier()
+        t0 = time.perf_counter()
+        # the public training loop's own batch path (Experiment.train): every step's batch is copied from pinned host
+        # memory inside the timed region, one batch ahead on a side stream; the first copy is not overlapped
+        for xd, yd, md in DevicePrefetcher(((xh, yh, mh) for _ in range(a.steps)), dev):
+            step_no += 1
+            loss = exp.train_step(xd, yd, md, 0, step_no)
+            loss_host = float(loss)                    # D2H read of the step's result
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * B * a.steps / e2e_s, "unit": "samples/s",
+               "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8 + mh.numel(), "d2h_bytes_per_step": 4,
+               "ms_per_step": e2e_s / a.steps * 1e3, "last_loss": loss_host}
+    nbytes_allreduce = exp.grads.nbytes() if world > 1 else 0
+    del exp
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---------------- rooflines from the live per-kernel CUDA-event times ----------------
     hbm_peak, sm_max_mhz, bf16_peak, peak_src = measured_peaks()
@@ -379,6 +382,8 @@ def main():
     alu_peak = sms * FP32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12        # T FP32 instr/s (FADD/FSETP: 1 op each)
     E = algorithmic_elements(B, M, T, K_PER_LEN, LENGTH_FRACS)
     l1 = (a.distance_func not in ("cosine", "pearson")) and not a.memory_efficient
+    tensor_mode = (not l1) and a.precision in ("3xtf32", "tf32", "bf16")
+    mma_passes = {"3xtf32": 3, "tf32": 1, "bf16": 1}.get(a.precision, 1)
     fams = {}
     for tag, (n, ms) in kern.items():
         fam = tag.split("/")[0]
@@ -400,6 +405,10 @@ def main():
             f["ops"] += (n / len(E)) * 2.0 * sum(E.values())
         elif fam == "instnorm":
             f["bytes"] += n * (2.0 * B * T * M * 4)
+        elif fam == "window_stats":
+            # reads the normalised series once, writes one fp32 statistic per window and group (two for pearson)
+            nst = 2 if a.distance_func == "pearson" else 1
+            f["bytes"] += n * (B * M * T * 4.0 + nst * sum(4.0 * B * M * ((T - L_ + 1 + 15) // 16 * 16) for L_ in E))
         elif fam == "window_prefix":
             f["bytes"] += n * (B * M * T * 4 + 2.0 * B * M * (T + 1) * 8)
     rooflines = []
@@ -408,14 +417,16 @@ def main():
         r = {"kernel": fam, "launches": f["launches"], "avg_ms": avg_ms, "share_of_step": f["ms"] / ms_kernel_region}
         if f["ops"]:
             ach = f["ops"] / (f["ms"] * 1e-3) / 1e12
-            if fam in ("shapelet_fwd", "shapelet_bwd", "bwd.contraction") and not l1 and a.precision in ("3xtf32", "tf32"):
+            if fam in ("shapelet_fwd", "shapelet_bwd", "bwd.contraction") and tensor_mode:
                 # cross term (forward) / coefficient contraction (backward, incl. its HBM-bound pooling pass) on the
                 # tcgen05 pipe: algorithmic 2E flop against the TF32 peak (= half the measured bf16 cuBLAS rate); the
                 # 3xTF32 split executes three MMAs per algorithmic multiply-add
-                peak = bf16_peak / 2.0
+                peak = bf16_peak if a.precision == "bf16" else bf16_peak / 2.0
                 r.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
-                         mma_passes=3 if a.precision == "3xtf32" else 1,
-                         peak_source="TF32 dense = bf16_tflops_sustained / 2 (%s)" % peak_src, traffic=None)
+                         mma_passes=mma_passes, frac_executed=mma_passes * ach / peak,
+                         peak_source="%s dense = bf16_tflops_sustained%s (%s)" % (
+                             "bf16" if a.precision == "bf16" else "TF32", "" if a.precision == "bf16" else " / 2", peak_src),
+                         traffic=None)
             else:
                 # executed FP32-pipe work: L1 issues 1 op per flop (no FMA): peak = lanes*clock; dot modes are FFMA
                 peak = alu_peak if l1 else 2.0 * alu_peak
@@ -438,27 +449,143 @@ def main():
     dominant = next((r for r in rooflines if "bound" in r and "aggregate_of" not in r), None)
 
     cpu = None
-    if world == 1 and not a.no_cpu_baseline:
+    if primary and world == 1 and not a.no_cpu_baseline:
         sps, ms, done, cores = time_cpu_reference(a, 1, 0, a.cpu_batch)
         cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": "1 full InterpGN(%s) train step on %d CHISCO-shaped samples (oracle/ign_oracle.py restatement "
                          "of the reference's eager path, fp32, %d threads)" % (a.dnn_type, a.cpu_batch, cores),
                "ms_per_step": ms}
 
-    line = {
+    return {
         "metric": "train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, B, world),
         "untimed_steps_before_region": max(a.warmup, 3) + 20,   # W warm-up + 20 while the clock sampler starts
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": launches, "engines": engines, "clocks": clocks,
         "roofline": dominant, "rooflines": rooflines, "cpu_baseline": cpu,
         "shapelet_layer": {"fwd_tflops": fams.get("shapelet_fwd", {}).get("ops", 0) / max(1e-9, fams.get("shapelet_fwd", {}).get("ms", 0) * 1e-3) / 1e12,
                            "bwd_tflops": fams.get("shapelet_bwd", {}).get("alg", 0) / max(1e-9, fams.get("shapelet_bwd", {}).get("ms", 0) * 1e-3) / 1e12,
                            "share_of_step": sum(f["ms"] for k, f in fams.items() if k.startswith("shapelet")) / ms_kernel_region},
-        "allreduce_bytes_per_step": exp.grads.nbytes() if world > 1 else 0,
+        "allreduce_bytes_per_step": nbytes_allreduce,
     }
-    emit(line)
+
+
+def gpu_eager_reference(a, budget_s=60.0):
+    """Same-box comparator: the reference's EAGER PyTorch path — the oracle port of
+    Shapelet.py:61-84 / InterpGN.py:44-52 with the restated FCN expert, autograd backward, Adam — moved to this B200,
+    at the largest batch that fits (the eager path keeps ~4 GB of 5-D temporaries per sample for backward)."""
+    dev = torch.device("cuda", 0)
+    batch, err = 32, None
+    while batch >= 1:
+        try:
+            ref = CpuReferenceStep(a)
+            ref.fcn.to(dev)
+            ref.Ws = [w.detach().to(dev).requires_grad_(True) for w in ref.Ws]
+            ref.Wc = ref.Wc.detach().to(dev).requires_grad_(True)
+            ref.opt = torch.optim.Adam(ref.Ws + [ref.Wc] + list(ref.fcn.parameters()), lr=5e-3)
+            ref.dev = dev
+            g = torch.Generator(device=dev).manual_seed(0)
+            x = torch.randn(batch, ref.cfg.seq_len, ref.cfg.enc_in, device=dev, generator=g)
+            y = torch.randint(0, ref.cfg.num_class, (batch,), device=dev, generator=g)
+            for _ in range(2):
+                ref.step(x, y)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0, done = time.perf_counter(), 0
+            e0.record()
+            while done < 5 and time.perf_counter() - t0 < budget_s:
+                ref.step(x, y)
+                done += 1
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / done
+            peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+            del ref, x, y
+            torch.cuda.empty_cache()
+            return {"value": batch / (ms * 1e-3), "unit": "samples/s", "batch": batch, "ms_per_step": ms, "steps": done,
+                    "peak_mem_gib": peak,
+                    "what": "reference eager PyTorch path (oracle port, fp32, allow_tf32 off) on the same B200"}
+        except torch.OutOfMemoryError as e:            # halve the batch and retry
+            err = str(e)[:80]
+            ref = x = y = None
+            torch.cuda.empty_cache()
+            batch //= 2
+    return {"unavailable": err}
+
+
+def extra_config_lines(a):
+    """BASELINE.json configs[0] and configs[4] through the same train step (short runs; N=1 only):
+    config 1 = JapaneseVowels-shaped InterpGN(FCN), B=32 — launch-latency-bound, reported as microseconds per step;
+    config 5 = 39-class CHISCO-shaped InterpGN(Transformer d_model 512, 2 layers), per-fold batch 64."""
+    import copy
+    from exp.experiment_classification import Experiment
+    out = {}
+    for name, kw, batch, steps in (
+            ("config1_jv_fcn_b32", dict(enc_in=12, seq_len=29, num_class=9, dnn_type="FCN"), 32, 50),
+            ("config5_chisco39_transformer_b64", dict(enc_in=125, seq_len=1000, num_class=39, dnn_type="Transformer"), 64, 10)):
+        cfg = model_args(a)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        cfg.c_out, cfg.batch_size = cfg.num_class, batch
+        torch.manual_seed(0)
+        exp = Experiment(cfg, load_data=False)
+        exp.model.train()
+        dev = exp.device
+        x = torch.randn(batch, cfg.seq_len, cfg.enc_in, device=dev)
+        y = torch.randint(0, cfg.num_class, (batch,), device=dev)
+        mask = torch.ones(batch, cfg.seq_len, device=dev)
+        exp.grads.zero_grad()
+        for i in range(5):
+            exp.train_step(x, y, mask, 0, i + 1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            exp.train_step(x, y, mask, 0, i + 6)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"samples_per_s": batch / (ms * 1e-3), "step_us": ms * 1e3, "batch": batch, "steps": steps,
+                     "dnn_type": cfg.dnn_type, "num_class": cfg.num_class, "distance_func": cfg.distance_func,
+                     "precision": cfg.shapelet_precision}
+        del exp, x, y, mask
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    import copy
+    import torch.distributed as dist
+    line = run_ours(a, primary=True)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and not a.no_extras:
+        # the tensor-core engine in the same record: cosine distance, 3xTF32 operands (fp32-equivalent), same workload
+        b = copy.copy(a)
+        b.distance_func, b.precision, b.steps = "cosine", "3xtf32", max(10, min(a.steps, 20))
+        m = run_ours(b, primary=False)
+        line["modes"] = {"cosine_3xtf32": {k: m[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config",
+                                                               "gpu_launches", "engines", "roofline", "rooflines",
+                                                               "shapelet_layer")}}
+        try:
+            line["gpu_eager_reference"] = gpu_eager_reference(a)
+        except Exception as e:                     # a comparator must never take the bench line down
+            line["gpu_eager_reference"] = {"unavailable": repr(e)[:200]}
+        try:
+            line["extra_configs"] = extra_config_lines(a)
+        except Exception as e:
+            line["extra_configs"] = {"unavailable": repr(e)[:200]}
+    if line is not None:
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

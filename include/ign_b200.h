@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IGN_ABI_VERSION 1
+#define IGN_ABI_VERSION 2
 
 typedef enum {
   IGN_OK = 0,
@@ -55,9 +55,14 @@ typedef enum {
 typedef enum {
   IGN_PREC_FP32 = 0,    /* CUDA-core FFMA, exact fp32 products                                     */
   IGN_PREC_3XTF32 = 1,  /* tcgen05 kind::tf32, hi*hi + hi*lo + lo*hi split: fp32-equivalent         */
-  IGN_PREC_TF32 = 2,    /* tcgen05 kind::tf32 single pass (own, looser tolerance)                   */
-  IGN_PREC_BF16 = 3     /* tcgen05 kind::f16 bf16 operands (own, looser tolerance)                  */
+  IGN_PREC_TF32 = 2     /* tcgen05 kind::tf32 single pass (own, looser tolerance)                   */
 } ign_precision_t;
+
+/* which kernels a call runs on (ign_shapelet_engine) */
+typedef enum {
+  IGN_ENGINE_FP32 = 0,    /* CUDA-core kernels (shapelet_simt.cu): exact fp32 products, any geometry          */
+  IGN_ENGINE_TCGEN05 = 1  /* tensor-core kernels (shapelet_tc.cu / shapelet_tc_bwd.cu)                        */
+} ign_engine_t;
 
 typedef struct {
   int32_t B, M, T;      /* batch, channels, series length                                          */
@@ -124,6 +129,13 @@ int32_t ign_window_stats(const float* xn_dev, int32_t B, int32_t M, int32_t T, i
                          const int32_t* stride, int32_t dist, float* const* st0_dev, float* const* st1_dev,
                          void* stream);
 
+/* The engine ign_shapelet_forward (backward == 0) or the contraction of ign_shapelet_backward (backward != 0) runs
+ * on for this descriptor.  `precision` is a request: IGN_DIST_L1 has no cross term and always runs on the FP32
+ * engine, and so do the few geometries the tensor-core kernels do not tile (forward: more than 2048 windows per
+ * series).  Callers that report an engine (bench.py, tools/sweep.py) must ask, not assume.
+ * Returns an ign_engine_t, or -1 for an invalid descriptor. */
+int32_t ign_shapelet_engine(const ign_shapelet_desc* desc, int32_t backward);
+
 /* Shapelet.forward / DistThresholdShapelet.forward for one length group.
  *   xn_dev [B,M,Tp]; st0_dev [B,M,SP] window statistics of this group from ign_window_stats (required unless
  *   dist==L1); W_dev [K,M,L]; threshold_dev [K,M] (required for LTS_MIN).
@@ -135,8 +147,8 @@ int32_t ign_window_stats(const float* xn_dev, int32_t B, int32_t M, int32_t T, i
  *               ties of p in fp32; backward re-derives the reference's arg-max-of-p one-hot itself.
  *   dstore_dev  optional [B,M,K,Tw] (Tw = ign_padded_windows) all window distances, kept for backward
  *               (the soft-max statistics are recomputed from it); NULL in inference.
- * Engine: precision FP32 -> CUDA-core kernels; 3XTF32 / TF32 -> tcgen05 kernel (stride 1, T' <= 2048;
- * other geometries run on the FP32 engine).  The tcgen05 engine needs ign_shapelet_forward_workspace(desc)
+ * Engine: precision FP32 -> CUDA-core kernels; 3XTF32 / TF32 -> tcgen05 kernels (any stride; T' <= 2048 —
+ * ign_shapelet_engine tells which one a descriptor gets).  The tcgen05 engine needs ign_shapelet_forward_workspace(desc)
  * bytes of 128-byte-aligned scratch (the pre-swizzled shifted-shapelet tiles); 0 bytes / NULL otherwise. */
 size_t ign_shapelet_forward_workspace(const ign_shapelet_desc* desc);
 int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,
@@ -144,22 +156,35 @@ int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev,
                              int32_t* argmin_dev, float* dstore_dev, void* workspace_dev, size_t workspace_bytes,
                              void* stream);
 
-/* bytes of scratch ign_shapelet_backward needs for this problem */
+/* bytes of scratch ign_shapelet_backward needs for this problem in the stored-distance mode (dstore_dev given) */
 size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* desc);
+
+/* bytes of the saved window distances [B,M,K,Tw] the stored-distance mode keeps between forward and backward */
+size_t ign_shapelet_dstore_bytes(const ign_shapelet_desc* desc);
+
+/* Recompute mode (dstore_dev == NULL in ign_shapelet_backward): nothing is kept from the forward; the backward
+ * walks the K shapelets in chunks and, per chunk, recomputes the window distances into the workspace, turns them
+ * in place into the per-window coefficients and contracts them — so its memory is bounded by the workspace, not by
+ * B*M*K*T' (116 GB + 116 GB at K = 1000, B = 256, L = 100 in the stored mode).  This returns the workspace size for
+ * the largest shapelet chunk that fits `budget_bytes` (at least one shapelet block: the result can exceed a budget
+ * that is too small).  Pass the same number of bytes to ign_shapelet_backward: the chunking is derived from it. */
+size_t ign_shapelet_backward_recompute_workspace(const ign_shapelet_desc* desc, size_t budget_bytes);
 
 /* Gradient of the pooled output w.r.t. the shapelets, through the straight-through soft/hard pooling
  * (Shapelet.py:79-82 | :105-108): every window receives soft_t*(p_t - pbar) (+1 at the hard index).
  *   g_dev [B,K,M] = dLoss/d(max_p)  (rbf_max)   or   dLoss/d(min_d)  (lts_min; the caller folds the
  *   sigmoid: g_min = -g_p * p * (1-p), dthreshold = sum_b g_p * p * (1-p))
  *   st0_dev / st1_dev: window statistics as for forward (st1 only for PEARSON; both NULL for L1).
- *   dstore_dev [B,M,K,Tw] as written by ign_shapelet_forward on the same inputs.
+ *   dstore_dev [B,M,K,Tw] as written by ign_shapelet_forward on the same inputs, or NULL: recompute mode (above;
+   then the threshold of lts_min is needed again: threshold_dev below, NULL otherwise allowed).
  *   dmin_dev / argmin_dev [B,K,M]: the forward's outputs; required for lts_min (its hard index and soft-min
  *   shift), ignored (may be NULL) for rbf_max, whose arg-max-of-p one-hot is re-derived from dstore.
  *   dW_dev [K,M,L] is overwritten (not accumulated).  Deterministic (no float atomics). */
 int32_t ign_shapelet_backward(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,
-                              const float* st1_dev, const float* W_dev, const float* g_dev,
-                              const float* dstore_dev, const float* dmin_dev, const int32_t* argmin_dev,
-                              float* dW_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+                              const float* st1_dev, const float* W_dev, const float* threshold_dev,
+                              const float* g_dev, const float* dstore_dev, const float* dmin_dev,
+                              const int32_t* argmin_dev, float* dW_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream);
 
 /* InterpGN gate + mixture (InterpGN.py:44-52): q=softmax(s), eta=(C*sum q^2-1)/(C-1),
  * if use_gate: eta=1 where eta>gating_value; out=eta*s+(1-eta)*z.  s,z,out [B,C]; eta [B]. */

@@ -60,9 +60,24 @@ static int check_desc(const ign_shapelet_desc* d, const char* who) {
   IGN_REQUIRE(d->T >= d->L, "%s: maximum size for tensor at dimension 2 is %d but size is %d (T < L)", who, d->T, d->L);
   IGN_REQUIRE(d->dist >= IGN_DIST_L1 && d->dist <= IGN_DIST_PEARSON, "%s: bad dist %d", who, d->dist);
   IGN_REQUIRE(d->pool == IGN_POOL_RBF_MAX || d->pool == IGN_POOL_LTS_MIN, "%s: bad pool %d", who, d->pool);
-  IGN_REQUIRE(d->precision >= IGN_PREC_FP32 && d->precision <= IGN_PREC_BF16, "%s: bad precision %d", who, d->precision);
+  IGN_REQUIRE(d->precision >= IGN_PREC_FP32 && d->precision <= IGN_PREC_TF32, "%s: bad precision %d", who, d->precision);
   IGN_REQUIRE(d->B <= 65535 * 64, "%s: batch too large", who);
   return IGN_OK;
+}
+
+size_t shapelet_forward_workspace_bytes(const ign_shapelet_desc& d) {
+  return (d.precision != IGN_PREC_FP32 && shapelet_fwd_tc_supported(d)) ? shapelet_fwd_tc_workspace(d) : 0;
+}
+
+// tcgen05 engine for the cross-term distances in the tensor-core precisions; everything else (L1, IGN_PREC_FP32 and
+// the geometries shapelet_fwd_tc_supported rejects) on the exact-fp32 CUDA-core engine — ign_shapelet_engine reports
+// which one a descriptor gets
+int shapelet_forward_dispatch(const ign_shapelet_desc& d, const float* xn, const float* st0, const float* W,
+                              const float* thr, float* p, float* dmin, int* argmin, float* dstore, void* ws,
+                              size_t ws_bytes, cudaStream_t st) {
+  if (d.precision != IGN_PREC_FP32 && shapelet_fwd_tc_supported(d))
+    return launch_shapelet_fwd_tc(d, xn, st0, W, thr, p, dmin, argmin, dstore, ws, ws_bytes, st);
+  return launch_shapelet_fwd_simt(d, xn, st0, W, thr, p, dmin, argmin, dstore, st);
 }
 
 }  // namespace ign
@@ -131,11 +146,15 @@ int32_t ign_window_stats(const float* xn, int32_t B, int32_t M, int32_t T, int32
   return launch_window_stats(xn, sg, B, M, T, dist, (cudaStream_t)stream);
 }
 
+int32_t ign_shapelet_engine(const ign_shapelet_desc* d, int32_t backward) {
+  if (check_desc(d, "shapelet_engine")) return -1;
+  if (d->precision == IGN_PREC_FP32) return IGN_ENGINE_FP32;
+  return (backward ? shapelet_bwd_tc_supported(*d) : shapelet_fwd_tc_supported(*d)) ? IGN_ENGINE_TCGEN05 : IGN_ENGINE_FP32;
+}
+
 size_t ign_shapelet_forward_workspace(const ign_shapelet_desc* d) {
   if (check_desc(d, "shapelet_forward_workspace")) return 0;
-  if (d->precision != IGN_PREC_FP32 && d->precision != IGN_PREC_BF16 && shapelet_fwd_tc_supported(*d))
-    return shapelet_fwd_tc_workspace(*d);
-  return 0;
+  return shapelet_forward_workspace_bytes(*d);
 }
 
 int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const float* st0, const float* W,
@@ -148,15 +167,7 @@ int32_t ign_shapelet_forward(const ign_shapelet_desc* d, const float* xn, const 
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || thr, "shapelet_forward: LTS pooling needs threshold");
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || d->dist <= IGN_DIST_SQL2,
               "shapelet_forward: DistThresholdShapelet ignores distance_func (Shapelet.py:100-103); use L1 or SQL2");
-  if (d->precision == IGN_PREC_BF16 && d->dist != IGN_DIST_L1) {
-    set_error("shapelet_forward: the bf16 operand mode is not built yet (use fp32, 3xtf32 or tf32)");
-    return IGN_ERR_UNSUPPORTED;
-  }
-  // tcgen05 engine for the cross-term distances; geometries it does not cover (stride > 1, more than 2048
-  // windows per series) run on the exact-fp32 CUDA-core engine instead
-  if (d->precision != IGN_PREC_FP32 && shapelet_fwd_tc_supported(*d))
-    return launch_shapelet_fwd_tc(*d, xn, st0, W, thr, p, dmin, argmin, dstore, ws, ws_bytes, (cudaStream_t)stream);
-  return launch_shapelet_fwd_simt(*d, xn, st0, W, thr, p, dmin, argmin, dstore, (cudaStream_t)stream);
+  return shapelet_forward_dispatch(*d, xn, st0, W, thr, p, dmin, argmin, dstore, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
@@ -164,17 +175,31 @@ size_t ign_shapelet_backward_workspace(const ign_shapelet_desc* d) {
   return shapelet_bwd_workspace_simt(*d);
 }
 
+size_t ign_shapelet_dstore_bytes(const ign_shapelet_desc* d) {
+  if (check_desc(d, "shapelet_dstore_bytes")) return 0;
+  return (size_t)d->B * d->M * d->K * padded_windows(d->T, d->L, d->stride) * sizeof(float);
+}
+
+size_t ign_shapelet_backward_recompute_workspace(const ign_shapelet_desc* d, size_t budget_bytes) {
+  if (check_desc(d, "shapelet_backward_recompute_workspace")) return 0;
+  return shapelet_bwd_recompute_workspace(*d, budget_bytes);
+}
+
 int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const float* st0, const float* st1,
-                              const float* W, const float* g, const float* dstore, const float* dmin,
-                              const int32_t* argmin, float* dW, void* ws, size_t ws_bytes, void* stream) {
+                              const float* W, const float* thr, const float* g, const float* dstore,
+                              const float* dmin, const int32_t* argmin, float* dW, void* ws, size_t ws_bytes,
+                              void* stream) {
   int rc = check_desc(d, "shapelet_backward");
   if (rc) return rc;
   IGN_REQUIRE(xn && W && g && dW && ws, "shapelet_backward: null pointer");
-  IGN_REQUIRE(dstore, "shapelet_backward: dstore (window distances saved by forward) is required");
-  IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || (dmin && argmin), "shapelet_backward: lts_min needs the forward's dmin and argmin");
-  IGN_REQUIRE(d->dist < IGN_DIST_COSINE || st0, "shapelet_backward: dist %d needs the window statistics", d->dist);
+  IGN_REQUIRE(d->dist == IGN_DIST_L1 || st0, "shapelet_backward: dist %d needs the window statistics", d->dist);
   IGN_REQUIRE(d->dist != IGN_DIST_PEARSON || st1, "shapelet_backward: PEARSON needs st1 (window means)");
-  return launch_shapelet_bwd_simt(*d, xn, st0, st1, W, g, dstore, dmin, argmin, dW, ws, ws_bytes, (cudaStream_t)stream);
+  if (!dstore) {   // recompute mode: nothing was kept by the forward
+    IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || thr, "shapelet_backward(recompute): lts_min needs the threshold again");
+    return launch_shapelet_bwd_recompute(*d, xn, st0, st1, W, thr, g, dW, ws, ws_bytes, (cudaStream_t)stream);
+  }
+  IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || (dmin && argmin), "shapelet_backward: lts_min needs the forward's dmin and argmin");
+  return launch_shapelet_bwd_simt(*d, xn, st0, st1, W, g, d->K, 0, dstore, dmin, argmin, dW, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int32_t ign_diversity_partials(int32_t K) { return K <= 0 ? 0 : diversity_blocks(K) * diversity_blocks(K); }

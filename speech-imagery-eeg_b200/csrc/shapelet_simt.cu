@@ -95,7 +95,8 @@ struct BwdArgs {
 };
 
 struct PoolArgs {
-  const float* g; const float* dstore; const float* dmin; const int* argmin;
+  const float* g; int gK, gk0;   // upstream gradient [B,gK,M]; this launch's shapelets are gk0 .. gk0+K-1 of it (recompute chunks)
+  const float* dstore; const float* dmin; const int* argmin;
   const float* st0; const float* st1; int SP; const float* wstat;   // window stats [B,M,SP]; wstat [K][M]: sum (w-mean)^2 (pearson)
   float* coef;          // [B][M][K][Ts]
   float* rowsc;         // [B][M][K][2] per-row scalars for the finalize kernel
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   const int k = row % g.K, bm = row / g.K;
   const int m = bm % g.M, b = bm / g.M;
   const size_t o = ((size_t)b * g.K + k) * g.M + m;
-  const float gk = a.g[o];
+  const float gk = a.g[((size_t)b * a.gK + a.gk0 + k) * g.M + m];
   const float eps = g.eps;
   const float qscale = -eps * eps * kLog2e;              // p = exp(-(eps d)^2) = 2^(qscale d^2)
   float Zs = 0.f, S1s = 0.f, shift = 0.f;
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
     const int k = row % g.K, bm = row / g.K;
     const int m = bm % g.M, b = bm / g.M;
     const size_t o = ((size_t)b * g.K + k) * g.M + m;
-    const float gk = a.g[o];
+    const float gk = a.g[((size_t)b * a.gK + a.gk0 + k) * g.M + m];
     float sl2 = 0.f;
     int ih = 0;
     if (POOL == IGN_POOL_LTS_MIN) { sl2 = a.dmin[o] * kLog2e; ih = a.argmin[o]; }
@@ -1323,7 +1324,7 @@ size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
 }
 
 int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
-                             const float* st1, const float* W, const float* gr, const float* dstore,
+                             const float* st1, const float* W, const float* gr, int gK, int gk0, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
                              cudaStream_t st) {
   Geo g; BwdPlan bp;
@@ -1342,7 +1343,9 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   {
     PhaseScope ph(PH_POOL, st);
     const int rows = d.B * d.M * d.K;
-    PoolArgs pa{gr, dstore, dmin, argmin, st0, st1, stats_pitch(d.T, d.L, d.stride), base + wo.wstat, base + wo.coef, base + wo.rowsc};
+    // recompute mode passes dstore == NULL: the distances were just recomputed INTO the coefficient buffer and are
+    // converted in place (every row is read into shared memory / registers by its own warp before it is rewritten)
+    PoolArgs pa{gr, gK, gk0, dstore ? dstore : base + wo.coef, dmin, argmin, st0, st1, stats_pitch(d.T, d.L, d.stride), base + wo.wstat, base + wo.coef, base + wo.rowsc};
     const bool in_regs = g.Tw <= 1024;       // rows that fit NCH float4 chunks per lane (pool_bwd_reg_kernel)
     int warps = 8;
     const int stages = in_regs ? kPoolStages : 2;
@@ -1411,6 +1414,81 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
                                                               d.M, d.L, bp.nchunk, d.dist);
   IGN_CUDA(cudaGetLastError());
+  return IGN_OK;
+}
+
+// ---- recompute mode: nothing saved by the forward; bounded workspace, shapelets walked in chunks --------------------
+namespace {
+struct RecomputeLayout { int Kc; size_t bwd_bytes, out_off, fws_off, fws_bytes, total; };
+
+size_t align128(size_t v) { return (v + 127) / 128 * 128; }
+
+bool recompute_layout(const ign_shapelet_desc& d, int Kc, RecomputeLayout& r) {
+  ign_shapelet_desc dc = d;
+  dc.K = Kc;
+  Geo g; BwdPlan bp;
+  if (!base_geo(dc, g) || !plan_bwd(g, bp)) return false;
+  r.Kc = Kc;
+  r.bwd_bytes = align128(bwd_workspace(dc, g, bp).total * sizeof(float));
+  r.out_off = r.bwd_bytes;                                            // p | dmin | argmin of the chunk, [B,Kc,M] each
+  r.fws_off = r.out_off + align128((size_t)3 * d.B * Kc * d.M * sizeof(float));
+  r.fws_bytes = shapelet_forward_workspace_bytes(dc);
+  r.total = r.fws_off + align128(r.fws_bytes);
+  return true;
+}
+
+// largest chunk whose workspace fits `bytes` (a whole number of 8-shapelet blocks unless K itself is smaller), then
+// balanced over the resulting number of chunks
+int recompute_chunk(const ign_shapelet_desc& d, size_t bytes) {
+  RecomputeLayout r;
+  int fit = 0;
+  for (int Kc = d.K; Kc >= 1; Kc = (Kc > 8 ? (Kc - 1) / 8 * 8 : Kc - 1)) {
+    if (recompute_layout(d, Kc, r) && r.total <= bytes) { fit = Kc; break; }
+  }
+  if (fit == 0) fit = min(d.K, 8);                                    // budget too small: the minimum chunk
+  const int n = ceil_div(d.K, fit);
+  int bal = ceil_div(d.K, n);
+  if (bal > 8) bal = min(fit, round_up(bal, 8));
+  return bal;
+}
+}  // namespace
+
+size_t shapelet_bwd_recompute_workspace(const ign_shapelet_desc& d, size_t budget) {
+  RecomputeLayout r;
+  if (!recompute_layout(d, recompute_chunk(d, budget), r)) return 0;
+  return r.total;
+}
+
+int launch_shapelet_bwd_recompute(const ign_shapelet_desc& d, const float* xn, const float* st0, const float* st1,
+                                  const float* W, const float* thr, const float* gr, float* dW, void* ws,
+                                  size_t ws_bytes, cudaStream_t st) {
+  if (((uintptr_t)ws & 127) != 0) { set_error("shapelet_backward(recompute): workspace must be 128-byte aligned"); return IGN_ERR_INVALID; }
+  const int Kc = recompute_chunk(d, ws_bytes);
+  RecomputeLayout r;
+  if (!recompute_layout(d, Kc, r)) { set_error("shapelet_backward(recompute): problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  if (r.total > ws_bytes) { set_error("shapelet_backward(recompute): workspace %zu < %zu bytes (ign_shapelet_backward_recompute_workspace)", ws_bytes, r.total); return IGN_ERR_INVALID; }
+  uint8_t* base8 = reinterpret_cast<uint8_t*>(ws);
+  for (int k0 = 0; k0 < d.K; k0 += Kc) {
+    ign_shapelet_desc dc = d;
+    dc.K = min(Kc, d.K - k0);
+    RecomputeLayout rc;
+    if (!recompute_layout(dc, dc.K, rc) || rc.total > ws_bytes) { set_error("shapelet_backward(recompute): internal chunk layout"); return IGN_ERR_INVALID; }
+    Geo g; BwdPlan bp;
+    base_geo(dc, g); plan_bwd(g, bp);
+    const BwdWorkspace wo = bwd_workspace(dc, g, bp);
+    float* dbuf = reinterpret_cast<float*>(base8) + wo.coef;            // distances now, coefficients after the pooling pass
+    float* outp = reinterpret_cast<float*>(base8 + rc.out_off);
+    const size_t no = (size_t)d.B * dc.K * d.M;
+    const size_t wofs = (size_t)k0 * d.M * d.L;
+    // 1. the forward of this chunk again (same kernels, same engine as the real forward): window distances -> dbuf
+    int rc1 = shapelet_forward_dispatch(dc, xn, st0, W + wofs, thr ? thr + (size_t)k0 * d.M : nullptr, outp, outp + no,
+                                        reinterpret_cast<int*>(outp + 2 * no), dbuf, base8 + rc.fws_off, rc.fws_bytes, st);
+    if (rc1) return rc1;
+    // 2. pooling backward in place, contraction, finalize -> dW[k0 .. k0+Kc)
+    rc1 = launch_shapelet_bwd_simt(dc, xn, st0, st1, W + wofs, gr, d.K, k0, nullptr, outp + no,
+                                   reinterpret_cast<const int*>(outp + 2 * no), dW + wofs, ws, rc.bwd_bytes, st);
+    if (rc1) return rc1;
+  }
   return IGN_OK;
 }
 

@@ -85,6 +85,7 @@ class Experiment(object):
         if self.is_main and load_data:
             os.makedirs(self.checkpoint_dir, exist_ok=True)
         self.epoch_stop = 0
+        self.history = []          # (epoch, train_loss, val_loss, val_acc) per finished epoch of train()
 
     def log(self, *a):
         if self.is_main:
@@ -180,6 +181,7 @@ class Experiment(object):
                 nstep += 1
             train_loss = float(run) / max(1, nstep)       # one host sync per epoch
             val_loss, val_acc = self.validation()
+            self.history.append((epoch, train_loss, val_loss, val_acc))
             remain = (time.time() - t0) * (a.train_epochs - epoch) / (epoch + 1)
             if (epoch + 1) % a.log_interval == 0:
                 self.log(f"Epoch {epoch + 1}/{a.train_epochs} | Train Loss {train_loss:.4f} | Val Loss {val_loss:.4f} "

@@ -10,10 +10,11 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_s
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IGN_B200_LIB", os.path.join(_HERE, "..", "lib", "libign_b200.so"))
 
-IGN_ABI_VERSION = 1
+IGN_ABI_VERSION = 2
 DIST = {"l1": 0, "sql2": 1, "cosine": 2, "pearson": 3}
 POOL = {"rbf_max": 0, "lts_min": 1}
-PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16": 3}
+PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+ENGINE = {0: "fp32", 1: "tcgen05"}
 
 
 class ShapeletDesc(Structure):
@@ -49,8 +50,11 @@ _SIGNATURES = {
                                    POINTER(_P), POINTER(_P), _P]),
     "ign_shapelet_forward_workspace": (c_size_t, [POINTER(ShapeletDesc)]),
     "ign_shapelet_forward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 9 + [c_size_t, _P]),
+    "ign_shapelet_engine": (c_int32, [POINTER(ShapeletDesc), c_int32]),
     "ign_shapelet_backward_workspace": (c_size_t, [POINTER(ShapeletDesc)]),
-    "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 10 + [c_size_t, _P]),
+    "ign_shapelet_dstore_bytes": (c_size_t, [POINTER(ShapeletDesc)]),
+    "ign_shapelet_backward_recompute_workspace": (c_size_t, [POINTER(ShapeletDesc), c_size_t]),
+    "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 11 + [c_size_t, _P]),
     "ign_diversity_partials": (c_int32, [c_int32]),
     "ign_diversity_forward": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
     "ign_diversity_backward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),

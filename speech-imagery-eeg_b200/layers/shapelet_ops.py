@@ -8,6 +8,7 @@ Replaces the eager op chains of the reference:
 """
 from __future__ import annotations
 
+import os
 from ctypes import byref, c_int32, c_void_p
 from typing import Optional, Tuple
 
@@ -16,6 +17,13 @@ import torch
 from . import ign_cabi as C
 
 _DIST_OF_FLAG = {"cosine": "cosine", "pearson": "pearson"}
+
+# Memory the backward may spend per length group on the window distances it keeps from the forward plus the
+# coefficient workspace of the same size (stored-distance mode: fastest, 2 x 4*B*M*K*T' bytes).  Above it the layer
+# switches to the recompute backward (nothing saved, shapelets walked in chunks inside a workspace of at most this
+# size): config 2 at B=256 needs 1.2 GB per group and stores; the K = 1000 points of the config-4 sweep would need
+# 232 GB and recompute.
+STORE_BUDGET_BYTES = int(float(os.environ.get("IGN_BWD_STORE_BUDGET_GB", "12")) * 2 ** 30)
 
 
 def resolve_dist(distance_func: str, memory_efficient: bool) -> str:
@@ -52,9 +60,17 @@ class KernelStats:
         self.launches = 0          # kernels launched through the C ABI since the last reset
         self.timing = False
         self.records = []          # (tag, start_event, end_event)
+        self.engines = {}          # tag -> engine the library reported for that call ("fp32" | "tcgen05")
 
     def reset(self, timing=False):
-        self.launches, self.timing, self.records = 0, timing, []
+        self.launches, self.timing, self.records, self.engines = 0, timing, [], {}
+
+    def note_engine(self, tag, desc, backward):
+        """Record which engine the library runs this call on (asked, not assumed: ign_shapelet_engine)."""
+        self.engines[tag] = C.ENGINE.get(int(C.lib.ign_shapelet_engine(byref(desc), int(backward))), "?")
+
+    def engine_summary(self):
+        return dict(sorted(self.engines.items()))
 
     def call(self, tag, nkernels, fn):
         self.launches += nkernels
@@ -212,11 +228,14 @@ class _ShapeletTransform(torch.autograd.Function):
         out = torch.empty((2, B, K, M), dtype=torch.float32, device=dev)     # p, dmin
         idx = torch.empty((B, K, M), dtype=torch.int32, device=dev)         # argmin_t d
         dstore = None
-        if need_grad:
+        # stored-distance backward while distances + coefficients fit the budget, recompute backward beyond it
+        store = need_grad and 2 * int(C.lib.ign_shapelet_dstore_bytes(byref(desc))) <= STORE_BUDGET_BYTES
+        if store:
             Tw = C.padded_windows(T, L, int(stride))
             dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
         fws_bytes = int(C.lib.ign_shapelet_forward_workspace(byref(desc)))
         fws = torch.empty((fws_bytes,), dtype=torch.uint8, device=dev) if fws_bytes else None
+        STATS.note_engine("shapelet_fwd/%s/L%d" % (dist, L), desc, False)
         with torch.cuda.device(dev):
             C.check(STATS.call("shapelet_fwd/%s/L%d" % (dist, L), 2 if fws_bytes else 1, lambda: C.lib.ign_shapelet_forward(
                 byref(desc), _ptr(xn), _ptr(st0), _ptr(Wc), _ptr(thr), _ptr(out[0]), _ptr(out[1]),
@@ -227,14 +246,16 @@ class _ShapeletTransform(torch.autograd.Function):
         ctx.pool = pool
         ctx.pack = pack
         ctx.thr_shape = None if threshold is None else threshold.shape
+        ctx.stored = store
         if need_grad:
-            ctx.save_for_backward(Wc, out, idx, dstore)
+            ctx.save_for_backward(Wc, out, idx, dstore if store else thr)
         ctx.mark_non_differentiable(idx)
         return out[0], out[1], idx
 
     @staticmethod
     def backward(ctx, g_p, g_dmin, _g_idx):
-        Wc, out, idx, dstore = ctx.saved_tensors
+        Wc, out, idx, extra = ctx.saved_tensors
+        dstore, thr = (extra, None) if ctx.stored else (None, extra)
         desc, pack = ctx.desc, ctx.pack
         # d.min() (Shapelet.py:84) feeds reporting only; a gradient arriving there follows the hard argmin
         # and is not produced by any loss of the reference (experiment_classification.py:325-329).
@@ -254,13 +275,18 @@ class _ShapeletTransform(torch.autograd.Function):
         dW = None
         if ctx.needs_input_grad[0]:
             st0, st1 = pack.window_stats(ctx.dist, desc.L, desc.stride)
-            nbytes = C.lib.ign_shapelet_backward_workspace(byref(desc))
+            if ctx.stored:
+                nbytes = C.lib.ign_shapelet_backward_workspace(byref(desc))
+            else:       # recompute mode: the library walks the shapelets in chunks inside this bounded workspace
+                nbytes = C.lib.ign_shapelet_backward_recompute_workspace(byref(desc), STORE_BUDGET_BYTES)
             ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=g.device)
             dW = torch.empty_like(Wc)
+            tag = "shapelet_bwd/%s/L%d" % (ctx.dist, desc.L)
+            STATS.note_engine(tag, desc, True)
             with torch.cuda.device(g.device):
-                C.check(STATS.call("shapelet_bwd/%s/L%d" % (ctx.dist, desc.L), 2, lambda: C.lib.ign_shapelet_backward(
-                    byref(desc), _ptr(pack.xn), _ptr(st0), _ptr(st1), _ptr(Wc), _ptr(g), _ptr(dstore), _ptr(out[1]),
-                    _ptr(idx), _ptr(dW), _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
+                C.check(STATS.call(tag, 2, lambda: C.lib.ign_shapelet_backward(
+                    byref(desc), _ptr(pack.xn), _ptr(st0), _ptr(st1), _ptr(Wc), _ptr(thr), _ptr(g), _ptr(dstore),
+                    _ptr(out[1]), _ptr(idx), _ptr(dW), _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
         return dW, dthr, None, None, None, None, None, None, None
 
 

@@ -17,7 +17,9 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+sys.path.insert(0, os.path.join(HERE, ".."))
 import ref_shim  # noqa: E402
+from helpers import sample_indices, seeded_batch, seeded_fill  # noqa: E402
 
 ns = ref_shim.load_reference()
 torch.set_num_threads(4)
@@ -129,7 +131,69 @@ def model_case(name, cfg_kw, B, seed, gating_value=None, cls="InterpGN"):
     print(name, logits.shape, float(loss.detach()))
 
 
+def full_model_case(name, cfg_kw, B, seed, n_sample=8192):
+    """Whole models at the BASELINE shapes (config 2: 125 ch x T=1000, 3 classes; config 5: 39 classes, Transformer
+    expert d_model 512).  The state dict (4-100 MB) and the batch are NOT stored: both are regenerated from `seed` by
+    tests/helpers.py (seeded_fill / seeded_batch) and the fixture keeps checksums of them, the reference's outputs,
+    and its parameter gradients as (sum, sum|.|, L2) plus the values at `n_sample` seeded positions per tensor
+    (output head in full)."""
+    cfg = SimpleNamespace(epsilon=1., distance_func="euclidean", memory_efficient=False,
+                          sbm_cls="linear", dropout=0., lambda_reg=0.1, lambda_div=0.1, dnn_type="FCN")
+    for k, v in cfg_kw.items():
+        setattr(cfg, k, v)
+    torch.manual_seed(seed)
+    model = ns.InterpGN(cfg)
+    model.train()
+    wsum = seeded_fill(model, seed)
+    x, y = seeded_batch(B, cfg.seq_len, cfg.enc_in, cfg.num_class, seed)
+    mask = torch.ones(B, cfg.seq_len)
+    logits, info = model(x, mask, None, None)
+    loss = torch.nn.functional.cross_entropy(logits, y) + info.loss.mean() \
+        + 1.0 * torch.nn.functional.cross_entropy(info.shapelet_preds, y)
+    loss.backward()
+    out = dict(seed=np.array(seed), B=np.array(B), weight_checksum=np.array(wsum),
+               x_checksum=np.array(float(x.double().abs().sum())), y=np_(y),
+               logits=np_(logits), p=np_(info.p), d=np_(info.d), reg_loss=np_(info.loss), loss=np_(loss),
+               shapelet_preds=np_(info.shapelet_preds), eta=np_(info.eta), dnn_preds=np_(info.dnn_preds),
+               n_sample=np.array(n_sample),
+               cfg_keys=np.array(list(cfg_kw.keys())), cfg_vals=np.array([str(v) for v in cfg_kw.values()]))
+    for k, v in model.named_parameters():
+        if v.grad is None:
+            continue
+        gd = v.grad.double().flatten()
+        out["gradnorm::" + k] = np.array([float(gd.sum()), float(gd.abs().sum()), float(gd.pow(2).sum().sqrt())])
+        if k.startswith("sbm."):
+            if k.endswith("output_layer.weight"):
+                out["grad::" + k] = np_(v.grad)
+            else:
+                idx = sample_indices(gd.numel(), n_sample, seed + 17)
+                out["gradsample::" + k] = np_(v.grad.flatten()[idx])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, logits.shape, float(loss.detach()))
+
+
+TRANSFORMER_KW = dict(dnn_type="Transformer", task_name="classification", pred_len=0, label_len=0, output_attention=False,
+                      d_model=512, embed="timeF", freq="h", factor=1, n_heads=8, d_ff=2048, activation="gelu", e_layers=2,
+                      dec_in=7, c_out=7, d_layers=1)
+
+
+def new_cases():
+    """Round-2 additions (kept separate so the round-1 fixtures are not rewritten)."""
+    jv = dict(enc_in=12, num_class=9, seq_len=29)
+    model_case("model_jv_sbm_bilinear", dict(enc_in=4, num_class=9, seq_len=29, sbm_cls="bilinear"), B=4, seed=3,
+               cls="ShapeBottleneckModel")
+    model_case("model_jv_sbm_attention", dict(jv, sbm_cls="attention"), B=4, seed=4, cls="ShapeBottleneckModel")
+    model_case("model_jv_interpgn_attention", dict(jv, sbm_cls="attention"), B=4, seed=5)
+    chisco = dict(enc_in=125, num_class=3, seq_len=1000)
+    full_model_case("model_chisco_full", chisco, B=2, seed=42)
+    full_model_case("model_chisco_full_cos", dict(chisco, distance_func="cosine"), B=2, seed=42)
+    full_model_case("model_chisco39_transformer", dict(enc_in=125, num_class=39, seq_len=1000, **TRANSFORMER_KW), B=2, seed=7)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "new":
+        new_cases()
+        sys.exit(0)
     kat_cases()
     S, D = ns.Shapelet, ns.DistThresholdShapelet
     layer_case("layer_l1", S, M=4, L=9, K=5, T=40, B=3, stride=1, eps=1.3, dfunc="euclidean", seed=1)
@@ -155,3 +219,4 @@ if __name__ == "__main__":
                task_name="classification", pred_len=0, label_len=0, output_attention=False, d_model=32, embed="timeF",
                freq="h", factor=1, n_heads=4, d_ff=64, activation="gelu", e_layers=2, dec_in=7, c_out=7, d_layers=1),
                B=3, seed=7)
+    new_cases()

@@ -380,3 +380,128 @@ def test_diversity_regulariser_vs_reference_formula(K, M, L):
     assert_close(Wd.grad, Wr.grad.float(), 1e-4, 1e-5 * scale + 1e-12, "diversity dW")
     out2 = shapelet_diversity(Wd.detach())
     assert float(out2) == float(out)          # deterministic
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 4 (layer sweep: K = 10..1000 shapelets per length, L in {.1,.2,.3,.5} T, T up to 4000): ORACLE parity at
+# the sweep's corner geometries, on a channel / batch subset the CPU oracle can afford.  The reference's stride rule
+# (Shapelet.py:162: stride = int(log2 L) once seq_len >= 3000) gives T=4000 the pairs 400/8, 800/9, 1200/10, 2000/10.
+# ---------------------------------------------------------------------------------------------------------------------
+CONFIG4_POINTS = [
+    # B, M, T,    K,    L,   stride
+    (2, 3, 1000, 100, 100, 1),
+    (2, 2, 1000, 100, 500, 1),
+    (1, 2, 1000, 1000, 100, 1),
+    (1, 2, 600, 1000, 500, 1),      # K = 1000 with the long shapelets of the sweep (T shortened: 101 windows)
+    (2, 2, 2000, 10, 1000, 1),      # T = 2000, L = .5 T
+    (1, 2, 2999, 10, 1500, 1),      # the largest unit-stride geometry (seq_len < 3000)
+    (2, 2, 4000, 10, 400, 8),
+    (2, 2, 4000, 10, 800, 9),
+    (1, 2, 4000, 10, 1200, 10),
+    (1, 2, 4000, 10, 2000, 10),
+    (1, 2, 4000, 100, 400, 8),
+]
+
+
+@pytest.mark.parametrize("flag,precision", [("euclidean", "fp32"), ("cosine", "fp32"), ("cosine", "3xtf32"),
+                                            ("sql2", "3xtf32"), ("pearson", "3xtf32")])
+@pytest.mark.parametrize("shape", CONFIG4_POINTS)
+def test_config4_sweep_points_vs_oracle(flag, precision, shape):
+    B, M, T, K, L, stride = shape
+    assert stride == O.shapelet_stride(T, L)
+    mode, dist = MODES[flag]
+    torch.manual_seed(31 + T + K + L)
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    ref = O.shapelet_forward(xn, W, stride, 1.0, mode)
+    p, dmin, idx, dW, _ = run_layer(xn, W, stride, 1.0, dist, g=g, precision=precision)
+    tag = f"{flag}/{precision} {shape}"
+    assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, tag + " p")
+    assert_close(dmin.reshape(B, -1), ref.dmin, RTOL, ATOL, tag + " dmin")
+    index_parity(idx, ref.argmin_d, ref.d, False, L, tag + " argmin")
+    del ref
+    dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), stride, 1.0, mode)
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), tag + " dW")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Recompute backward (nothing saved by the forward; the library walks the shapelets in chunks inside a bounded
+# workspace) against the stored-distance backward and the oracle.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def tiny_store_budget(monkeypatch):
+    from layers import shapelet_ops
+    def set_budget(nbytes):
+        monkeypatch.setattr(shapelet_ops, "STORE_BUDGET_BYTES", int(nbytes))
+    return set_budget
+
+
+@pytest.mark.parametrize("flag,precision,pool", [("euclidean", "fp32", "rbf_max"), ("cosine", "fp32", "rbf_max"),
+                                                 ("pearson", "3xtf32", "rbf_max"), ("sql2", "3xtf32", "rbf_max"),
+                                                 ("euclidean", "fp32", "lts_min"), ("sql2", "fp32", "lts_min")])
+@pytest.mark.parametrize("shape,budget", [((3, 4, 200, 45, 20, 1), 600_000),      # several chunks of 8..16 shapelets
+                                          ((2, 3, 400, 13, 50, 3), 300_000),      # strided windows, ragged last chunk
+                                          ((2, 5, 130, 7, 16, 1), 1)])            # budget too small: minimum chunk
+def test_recompute_backward_matches_stored_backward_and_oracle(tiny_store_budget, flag, precision, pool, shape, budget):
+    B, M, T, K, L, stride = shape
+    mode, dist = MODES[flag]
+    torch.manual_seed(900 + K + L)
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    thr = torch.rand(1, K, M) if pool == "lts_min" else None
+    stored = run_layer(xn, W, stride, 0.9, dist, pool, thr, g, precision)
+    tiny_store_budget(budget)
+    from ctypes import byref
+    from layers import ign_cabi as C
+    desc = C.ShapeletDesc(B, M, T, C.padded_len(T), K, L, stride, 0.9, C.DIST[dist], C.POOL[pool], C.PRECISION[precision])
+    assert 2 * C.lib.ign_shapelet_dstore_bytes(byref(desc)) > budget            # the layer really takes the recompute path
+    rec = run_layer(xn, W, stride, 0.9, dist, pool, thr, g, precision)
+    assert torch.equal(stored[0], rec[0]) and torch.equal(stored[1], rec[1]) and torch.equal(stored[2], rec[2])
+    opool = O.POOL_LTS_MIN if pool == "lts_min" else O.POOL_RBF_MAX
+    dW_ref, dthr_ref = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), stride, 0.9, mode, opool,
+                                                   None if thr is None else thr.double())
+    scale = float(dW_ref.abs().max())
+    assert_close(rec[3], dW_ref, 1e-4, 1e-4 * scale, f"{flag}/{precision}/{pool} recompute dW vs oracle")
+    # the same kernels on the same distances, chunked differently: only the order of the per-chunk sums may differ
+    assert_close(rec[3], stored[3], 1e-5, 1e-6 * scale, "recompute dW vs stored dW")
+    if thr is not None:
+        assert_close(rec[4], dthr_ref, 1e-4, 1e-5, "recompute dthreshold")
+
+
+def test_recompute_backward_at_k1000_bounded_workspace(tiny_store_budget):
+    """Config-4 corner K = 1000, B = 256, L = 100 on a channel subset: the stored mode would keep 2 x 4*B*M*K*T' bytes
+    (7.4 GB here, 232 GB at M = 125); with a 1 GiB budget the backward recomputes in ~8 chunks.  Checked for linearity,
+    determinism and against the oracle on sampled samples."""
+    from ctypes import byref
+    from layers import ign_cabi as C
+    tiny_store_budget(2 ** 30)
+    torch.manual_seed(12)
+    B, M, T, K, L = 256, 4, 1000, 1000, 100
+    xn = torch.randn(B, M, T, device=DEV)
+    W = torch.randn(K, M, L, device=DEV)
+    g = torch.zeros(B, K, M, device=DEV)
+    bs = [5, 131]
+    g[bs] = torch.randn(len(bs), K, M, device=DEV)          # only two samples carry gradient: the oracle can check them
+    desc = C.ShapeletDesc(B, M, T, T, K, L, 1, 1.0, 0, 0, 0)
+    assert 2 * C.lib.ign_shapelet_dstore_bytes(byref(desc)) > 7 * 2 ** 30
+    assert C.lib.ign_shapelet_backward_recompute_workspace(byref(desc), 2 ** 30) <= 2 ** 30
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    p, dmin, idx, dW, _ = run_layer(xn, W, 1, 1.0, "l1", g=g)
+    assert torch.cuda.max_memory_allocated() - base < 1.5 * 2 ** 30          # outputs + the bounded workspace
+    p2, _, _, dW2, _ = run_layer(xn, W, 1, 1.0, "l1", g=g)
+    assert torch.equal(dW, dW2) and torch.equal(p, p2)
+    dW_ref, _ = O.shapelet_backward_formula(xn[bs].cpu().double(), W.cpu().double(), g[bs].cpu().double(), 1, 1.0, O.DIST_L1)
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), "K=1000 recompute dW")
+
+
+def test_engine_report_matches_what_runs():
+    """ign_shapelet_engine is what bench.py / tools/sweep.py label their rows with."""
+    from layers.shapelet_ops import STATS
+    STATS.reset()
+    xn, W = torch.randn(2, 2, 400), torch.randn(4, 2, 50)
+    run_layer(xn, W, 1, 1.0, "cosine", g=torch.randn(2, 4, 2), precision="3xtf32")
+    run_layer(xn, W, 1, 1.0, "l1", g=torch.randn(2, 4, 2), precision="3xtf32")
+    run_layer(xn, torch.randn(4, 2, 60), 1, 1.0, "cosine", g=torch.randn(2, 4, 2), precision="fp32")
+    e = STATS.engine_summary()
+    assert e["shapelet_fwd/cosine/L50"] == "tcgen05" and e["shapelet_bwd/cosine/L50"] == "tcgen05"
+    assert e["shapelet_fwd/l1/L50"] == "fp32" and e["shapelet_bwd/l1/L50"] == "fp32"
+    assert e["shapelet_fwd/cosine/L60"] == "fp32"

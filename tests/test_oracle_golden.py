@@ -140,3 +140,36 @@ def test_shape_rules():
     assert O.shapelet_stride(2999, 1500) == 1
     with pytest.raises(RuntimeError):
         O.num_windows(5, 6, 1)
+
+
+@pytest.mark.parametrize("name", ["model_chisco_full", "model_chisco_full_cos", "model_chisco39_transformer"])
+def test_oracle_at_the_baseline_shapes_matches_live_reference_golden(name):
+    """BASELINE configs 2 and 5 at full width (125 ch x T=1000, default shapelet set, B=2): the fixture holds the live
+    reference's outputs; weights and batch are regenerated from its seed (helpers.seeded_fill / seeded_batch)."""
+    from types import SimpleNamespace
+    from helpers import seeded_batch, seeded_fill
+    from models.InterpGN import InterpGN          # host-side construction only (state-dict layout); no kernels run
+    g = load_golden(name)
+    kw = dict(zip(g["cfg_keys"].tolist(), g["cfg_vals"].tolist()))
+    cfg = SimpleNamespace(epsilon=1., distance_func=kw.get("distance_func", "euclidean"), memory_efficient=False,
+                          sbm_cls="linear", dropout=0., lambda_reg=0.1, lambda_div=0.1, dnn_type="FCN",
+                          enc_in=int(kw["enc_in"]), num_class=int(kw["num_class"]), seq_len=int(kw["seq_len"]))
+    seed, B = int(g["seed"]), int(g["B"])
+    model = InterpGN(cfg).sbm                      # the FCN placeholder expert is not used: only sbm.* names matter
+    # seeded_fill derives every tensor's stream from (seed, parameter name): fill under the InterpGN names
+    holder = torch.nn.Module()
+    holder.sbm = model
+    seeded_fill(holder, seed)
+    x, y = seeded_batch(B, cfg.seq_len, cfg.enc_in, cfg.num_class, seed)
+    assert abs(float(x.double().abs().sum()) - float(g["x_checksum"])) <= 1e-9 * float(g["x_checksum"])
+    Ws = [s.weights.detach() for s in model.shapelets]
+    Wc = model.output_layer.weight.detach()
+    mode = MODES[cfg.distance_func][0]
+    logits, probs, dists = O.sbm_forward(x, Ws, [1, 1, 1, 1], Wc, 1.0, mode)
+    assert_close(probs, t(g["p"]), 1e-6, 1e-7, name + " p")
+    assert_close(dists, t(g["d"]), 1e-6, 1e-7, name + " d")
+    assert_close(logits, t(g["shapelet_preds"]), 1e-5, 1e-6, name + " shapelet logits")
+    out, eta = O.gate_forward(t(g["shapelet_preds"]), t(g["dnn_preds"]))
+    assert_close(out, t(g["logits"]), 1e-6, 1e-7, name + " gated logits")
+    assert_close(eta, t(g["eta"]), 1e-6, 1e-7, name + " eta")
+    assert_close(O.sbm_loss(Wc, Ws, 0.1, 0.1).reshape(1), t(g["reg_loss"]), 1e-6, 1e-8, name + " regulariser")

@@ -1,6 +1,8 @@
 """BASELINE config 4: shapelet-distance layer sweep (K shapelets per length, L in {.1,.2,.3,.5}*T, T up to 4000,
-batch 256, 125 channels).  Forward always; forward+backward where the saved distances fit (K*T' small enough).
-Writes a JSON list and a markdown table.   python tools/sweep.py --out profiles/r1_sweep"""
+batch 256, 125 channels).  Forward and backward for every point: the backward keeps the window distances while they
+fit the store budget (layers/shapelet_ops.STORE_BUDGET_BYTES) and recomputes them chunk by chunk beyond it (K = 1000).
+Every row is labelled with the engine the library reports for it (ign_shapelet_engine), not with the one asked for.
+Writes a JSON list and a markdown table.   python tools/sweep.py --out profiles/r2_sweep"""
 import argparse
 import json
 import math
@@ -10,6 +12,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "speech-imagery-eeg_b200"))
 import torch  # noqa: E402
+from ctypes import byref  # noqa: E402
+from layers import ign_cabi as C  # noqa: E402
+from layers import shapelet_ops  # noqa: E402
 from layers.shapelet_ops import instance_norm, shapelet_transform  # noqa: E402
 
 
@@ -55,10 +60,14 @@ def main():
                         W = torch.randn(K, a.M, L, device="cuda", requires_grad=True)
                         with torch.no_grad():
                             t_f = timed(lambda: shapelet_transform(pack, W, stride, 1.0, dist, precision=prec))
+                        desc = C.ShapeletDesc(a.B, a.M, T, C.padded_len(T), K, L, stride, 1.0, C.DIST[dist], 0,
+                                              C.PRECISION[prec])
+                        eng = [C.ENGINE[C.lib.ign_shapelet_engine(byref(desc), b)] for b in (0, 1)]
+                        stored = 2 * C.lib.ign_shapelet_dstore_bytes(byref(desc)) <= shapelet_ops.STORE_BUDGET_BYTES
                         row = dict(T=T, L=L, stride=stride, windows=Tw, K=K, dist=dist, precision=prec, E=E,
+                                   fwd_engine=eng[0], bwd_engine=eng[1], bwd_mode="stored" if stored else "recompute",
                                    fwd_ms=t_f, fwd_tflops=2 * E / t_f / 1e9)
-                        dstore_gb = a.B * a.M * K * Tw * 4 / 1e9
-                        if dstore_gb < 20 and 3 * est_ms < a.max_ms:
+                        if 4 * est_ms < a.max_ms:
                             p, _, _ = shapelet_transform(pack, W, stride, 1.0, dist, precision=prec)
                             g = torch.randn_like(p)
 
@@ -77,10 +86,12 @@ def main():
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     json.dump(rows, open(a.out + ".json", "w"), indent=1)
     with open(a.out + ".md", "w") as f:
-        f.write("| T | L | stride | T' | K | dist | engine | fwd ms | fwd TFLOP/s | bwd ms | bwd TFLOP/s (4E) |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+        f.write("| T | L | stride | T' | K | dist | precision asked | engine fwd / bwd | bwd mode | fwd ms | fwd TFLOP/s | bwd ms | bwd TFLOP/s (4E) |\n"
+                "|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         for r in rows:
-            f.write("| %d | %d | %d | %d | %d | %s | %s | %.3f | %.1f | %s | %s |\n" % (
-                r["T"], r["L"], r["stride"], r["windows"], r["K"], r["dist"], r["precision"], r["fwd_ms"], r["fwd_tflops"],
+            f.write("| %d | %d | %d | %d | %d | %s | %s | %s / %s | %s | %.3f | %.1f | %s | %s |\n" % (
+                r["T"], r["L"], r["stride"], r["windows"], r["K"], r["dist"], r["precision"], r["fwd_engine"], r["bwd_engine"],
+                r["bwd_mode"], r["fwd_ms"], r["fwd_tflops"],
                 "%.3f" % r["bwd_ms"] if "bwd_ms" in r else "-", "%.1f" % r["bwd_tflops"] if "bwd_tflops" in r else "-"))
 
 
