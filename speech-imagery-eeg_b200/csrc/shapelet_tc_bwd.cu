@@ -4,9 +4,11 @@
 //
 // is the transpose problem of the forward (shapelet_tc.cu).  With P = 8 shifts, window t = 8 r + j:
 //   Gsh[u,(k,j)] = sum_{(b,r)} x[b, 8 r + u] * a[b,k,8 r + j],   u in [0, L+7),       G[k,l] = sum_j Gsh[l+j,(k,j)]
-// i.e. a GEMM with  M' = u (the TMEM lanes; ceil((L+7)/128) <= 4 tiles),  N' = 8 K (padded to 16),  and the
+// i.e. a GEMM with  M' = u (the TMEM lanes; up to 4 tiles of 128 per item),  N' = 8 K (padded to 16),  and the
 // contraction over the window-group rows (b, r) — the whole batch chunk accumulates into ONE resident set of
 // accumulators, so there is no epilogue per tile: only one small drain per (channel, shapelet block, batch chunk).
+// Shapelets longer than 505 lags split the lag axis into blocks of 504 lags (512 lanes u, the 8 extra ones feed the
+// shift sum of the block's last lags); each (lag block) is its own item with its own accumulators.
 //   A'[u][(b,r)]     = x[b, 8 r + u]   transposed Hankel rows: gathered by the producer warps (one LDS.32 per element,
 //                      conflict-free: consecutive lanes = consecutive u) straight into tensor memory (tcgen05.st), hi and
 //                      lo = x - trunc_tf32(x) columns, exactly as in the forward
@@ -40,6 +42,8 @@ constexpr int kBAStages = 4, kBBStages = 4;
 constexpr int kBAStageCols = 64;       // 32 hi + 32 lo
 constexpr int kBACol0 = 256;           // accumulators live in columns [0,256), A' stages behind them
 constexpr int kBChunk = 32;            // samples per item
+constexpr int kBMaxMT = 4;             // M' tiles (of 128 lanes u) per item: 4 accumulators of N' <= 64 columns
+constexpr int kBLagStep = kBMaxMT * kBRows - kBShifts;   // 504 lags per lag block
 
 // role-level wait accounting (debug builds only: -DIGN_TC_PROFILE); slots: 0 prod wait row, 1 prod wait emptyA,
 // 2 build wait emptyB, 3 mma wait fullB, 4 mma wait fullA, 5 mma wait accempty, 6 drain wait accfull, 7 loader wait
@@ -63,7 +67,8 @@ struct BwdTcGeo {
   int B, M, T, Tp, K, L;
   int Tw, Ts;          // windows, coefficient row pitch
   int RI, NKB;         // window groups (of 8) per sample, 32-row k-blocks per sample
-  int MT;              // 128-lane tiles over u = l + j
+  int MT;              // 128-lane tiles over u = l + j of ONE lag block (<= kBMaxMT; the last block may use fewer)
+  int nlb;             // lag blocks: ceil(L / 504)
   int KG, nkb, N;      // shapelets per N' tile, shapelet blocks, N' = 8*KG rounded up to 16
   int XR;              // floats per series row in shared memory (zero padded)
   int nchunk, nitems;
@@ -74,13 +79,17 @@ struct BwdTcArgs {
   const float* xn; const float* coef; float* part;
 };
 
-struct ItemCoord { int m, kblk, chunk; };
+struct ItemCoord { int m, kblk, chunk, lb, mt; };   // mt: M' tiles of this item's lag block
 __device__ __forceinline__ ItemCoord item_coord(const BwdTcGeo& g, int w) {
   ItemCoord c;
-  const int mk = w / g.nchunk;
+  int mk = w / g.nchunk;
   c.chunk = w - mk * g.nchunk;
+  const int mkl = mk;
+  mk = mkl / g.nlb;
+  c.lb = mkl - mk * g.nlb;
   c.m = mk / g.nkb;
   c.kblk = mk - c.m * g.nkb;
+  c.mt = min(g.MT, (g.L + kBShifts - 1 - c.lb * kBLagStep + kBRows - 1) / kBRows);
   return c;
 }
 
@@ -144,13 +153,13 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
         BP_ADD(0, t0);
         const float* xs = xrow + (size_t)buf * g.XR;
         for (int kb = 0; kb < g.NKB; ++kb) {
-          for (int mt = 0; mt < g.MT; ++mt, ++ia) {
+          for (int mt = 0; mt < ic.mt; ++mt, ++ia) {
             const int s = sidx;
             const uint32_t ph = sph;
             if (++sidx == kBAStages) { sidx = 0; sph ^= 1; }
             if ((int)(ia & 1) != grp) continue;
             // this lane's row of A': x[8 (32 kb + c) + 128 mt + up], c = 0..31 (zero beyond the series)
-            const float* src = xs + 8 * (kBKBlock * kb) + kBRows * mt + up;
+            const float* src = xs + 8 * (kBKBlock * kb) + kBRows * mt + up + ic.lb * kBLagStep;
             uint32_t hi[32], lo[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
         for (int kl = 0; kl < g.KG; ++kl) {
           const int k = k0 + kl;
           if (k >= g.K) break;                                       // uniform
-          for (int mt = 0; mt < g.MT; ++mt) {
+          for (int mt = 0; mt < ic.mt; ++mt) {
             uint32_t v[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -195,11 +204,12 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
             for (int j = 0; j < kBShifts; ++j) tk[j * TU + kBRows * mt + up] = __uint_as_float(v[j]);
           }
           bar_sync(3, 128);
-          for (int l = et; l < g.L; l += 128) {
+          const int l0 = ic.lb * kBLagStep, nl = min(kBLagStep, g.L - l0);            // this block's lags [l0, l0 + nl)
+          for (int l = et; l < nl; l += 128) {
             float s = 0.f;
 #pragma unroll
             for (int j = 0; j < kBShifts; ++j) s += tk[j * TU + l + j];                // fixed order
-            a.part[(((size_t)ic.chunk * g.K + k) * g.M + ic.m) * g.L + l] = s;
+            a.part[(((size_t)ic.chunk * g.K + k) * g.M + ic.m) * g.L + l0 + l] = s;
           }
           bar_sync(3, 128);
         }
@@ -313,7 +323,7 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
             BP_ADD(3, t0);
             const uint32_t bd_hi = bdesc0 + (uint32_t)sb * bstage16, bd_lo = bd_hi + bimg16;
             const bool first = (b == b0) && (kb == 0);
-            for (int mt = 0; mt < g.MT; ++mt) {
+            for (int mt = 0; mt < ic.mt; ++mt) {
               t0 = BP_CLK();
               mbar_wait(&fullA[sa], pha);
               BP_ADD(4, t0);
@@ -382,11 +392,12 @@ void bwd_tc_geo(const ign_shapelet_desc& d, BwdTcGeo& g) {
   g.B = d.B; g.M = d.M; g.T = d.T; g.Tp = d.Tp; g.K = d.K; g.L = d.L;
   g.Tw = num_windows(d.T, d.L, 1); g.Ts = round_up(g.Tw, 4);
   g.RI = ceil_div(g.Tw, kBShifts); g.NKB = ceil_div(g.RI, kBKBlock);
-  g.MT = ceil_div(d.L + kBShifts - 1, kBRows);
+  g.nlb = ceil_div(d.L, kBLagStep);
+  g.MT = min(kBMaxMT, ceil_div(d.L + kBShifts - 1, kBRows));
   g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb); g.N = round_up(kBShifts * g.KG, 16);
-  g.XR = round_up(max(d.Tp, kBShifts * kBKBlock * g.NKB + kBRows * g.MT) + 8, 4);
+  g.XR = round_up(max(d.Tp, kBShifts * kBKBlock * g.NKB + (g.nlb - 1) * kBLagStep + kBRows * g.MT) + 8, 4);
   g.nchunk = ceil_div(d.B, kBChunk);
-  g.nitems = d.M * g.nkb * g.nchunk;
+  g.nitems = d.M * g.nkb * g.nlb * g.nchunk;
   g.split = d.precision == IGN_PREC_3XTF32 ? 1 : 0;
 }
 
@@ -410,14 +421,15 @@ int bwd_tc_profile_read(unsigned long long* host16, int reset) {
 #endif
 }
 
-// the tensor-core contraction covers: cross-term distances, unit stride, the tcgen05 operand modes, L + 7 <= 512
+// the tensor-core contraction covers: cross-term distances, unit stride, the tcgen05 operand modes; any shapelet
+// length (lag blocks of 504) as long as one series row and its zero padding fit shared memory twice
 bool shapelet_bwd_tc_supported(const ign_shapelet_desc& d) {
   if (d.dist == IGN_DIST_L1 || d.stride != 1) return false;
   if (d.precision != IGN_PREC_3XTF32 && d.precision != IGN_PREC_TF32) return false;
   if (num_windows(d.T, d.L, 1) <= 0) return false;
   BwdTcGeo g;
   bwd_tc_geo(d, g);
-  if (g.MT * g.N > kBACol0 || g.MT > 4) return false;
+  if (g.MT * g.N > kBACol0) return false;
   return bwd_tc_smem(g) <= (size_t)max_optin_smem();
 }
 

@@ -439,7 +439,7 @@ def tiny_store_budget(monkeypatch):
                                                  ("pearson", "3xtf32", "rbf_max"), ("sql2", "3xtf32", "rbf_max"),
                                                  ("euclidean", "fp32", "lts_min"), ("sql2", "fp32", "lts_min")])
 @pytest.mark.parametrize("shape,budget", [((3, 4, 200, 45, 20, 1), 600_000),      # several chunks of 8..16 shapelets
-                                          ((2, 3, 400, 13, 50, 3), 300_000),      # strided windows, ragged last chunk
+                                          ((2, 3, 400, 13, 50, 3), 40_000),       # strided windows, ragged last chunk
                                           ((2, 5, 130, 7, 16, 1), 1)])            # budget too small: minimum chunk
 def test_recompute_backward_matches_stored_backward_and_oracle(tiny_store_budget, flag, precision, pool, shape, budget):
     B, M, T, K, L, stride = shape
