@@ -2,13 +2,15 @@
 //
 //   G[k,l] = sum_b sum_t a[b,k,t] * x[b,m,t+l]        (a = the per-window coefficients written by pool_bwd_kernel)
 //
-// is the transpose problem of the forward (shapelet_tc.cu).  With P = 8 shifts, window t = 8 r + j:
-//   Gsh[u,(k,j)] = sum_{(b,r)} x[b, 8 r + u] * a[b,k,8 r + j],   u in [0, L+7),       G[k,l] = sum_j Gsh[l+j,(k,j)]
-// i.e. a GEMM with  M' = u (the TMEM lanes; up to 4 tiles of 128 per item),  N' = 8 K (padded to 16),  and the
+// is the transpose problem of the forward (shapelet_tc.cu).  With P shifts (template: 16 or 8), window t = P r + j:
+//   Gsh[u,(k,j)] = sum_{(b,r)} x[b, P r + u] * a[b,k,P r + j],   u in [0, L+P-1),     G[k,l] = sum_j Gsh[l+j,(k,j)]
+// i.e. a GEMM with  M' = u (the TMEM lanes; up to 256/N' tiles of 128 per item),  N' = P K (padded to 16),  and the
 // contraction over the window-group rows (b, r) — the whole batch chunk accumulates into ONE resident set of
 // accumulators, so there is no epilogue per tile: only one small drain per (channel, shapelet block, batch chunk).
-// Shapelets longer than 505 lags split the lag axis into blocks of 504 lags (512 lanes u, the 8 extra ones feed the
-// shift sum of the block's last lags); each (lag block) is its own item with its own accumulators.
+// Longer shapelets split the lag axis into blocks of (128 MT - P) lags (the P extra lanes u feed the shift sum of the
+// block's last lags); each lag block is its own item with its own accumulators.
+// P = 16 halves the A' tiles, B' stages and MMA issue slots per sample (N' = 80 instead of 48 for K = 5) and is taken
+// whenever the shapelet fits ONE lag block that way (L + 15 <= 128 * (256 / N')); otherwise P = 8 (N' = 48, 4 tiles).
 //   A'[u][(b,r)]     = x[b, 8 r + u]   transposed Hankel rows: gathered by the producer warps (one LDS.32 per element,
 //                      conflict-free: consecutive lanes = consecutive u) straight into tensor memory (tcgen05.st), hi and
 //                      lo = x - trunc_tf32(x) columns, exactly as in the forward
@@ -18,9 +20,14 @@
 //
 // Roles (448 threads, one persistent CTA per SM walking a contiguous range of (channel, shapelet block, chunk) items):
 //   warps 0-7   A' producers (two per TMEM lane quarter, alternating stages); warps 0-3 also drain the accumulators
-//   warps 8-11  B' builders
+//   warps 8-15  B' builders: two groups of four warps that build ALTERNATE stages — a stage is a short latency chain
+//               (wait for the slot, 16-32 scattered stores, proxy fence, arrive), so two of them have to be in flight for
+//               the MMA thread not to wait for B' (it waited 45 % of the time at L = 100 with all eight warps on one stage)
 //   warp 12     one elected thread issues tcgen05.mma / tcgen05.commit
-//   warp 13     series-row loader (cp.async, double buffered, mbarrier hand-off)
+//   warp 17     series-row loader: one elected thread streams the rows with 1-D bulk TMA copies into a ring of four
+//               row buffers (completion counted on the row's mbarrier), so the DRAM latency of up to three rows is in
+//               flight while one is consumed (a cp.async + wait per row exposed ~1 us per sample: more than the 960 MMA
+//               cycles a sample needs at L = 100)
 // The drain writes per-chunk partial sums part[chunk][k][m][l] in a fixed order; shapelet_bwd_finalize (shapelet_simt.cu)
 // combines them exactly as for the FP32 engine: bit-reproducible, no float atomics.
 #include "ign_common.cuh"
@@ -32,18 +39,18 @@ namespace {
 
 #include "tc_ptx.cuh"
 
-constexpr int kBShifts = 8;            // P
 constexpr int kBRows = 128;            // UMMA M
 constexpr int kBKBlock = 32;           // window-group rows per stage (one 128-byte swizzle row of fp32)
-constexpr int kBProdWarps = 8, kBBuildWarps = 8;
+constexpr int kBProdWarps = 8, kBBuildWarps = 8, kBBuildGroups = 2;
+constexpr int kBGroupThreads = kBBuildWarps / kBBuildGroups * 32;   // 128 builder threads per stage
 constexpr int kBMmaWarp = kBProdWarps + kBBuildWarps, kBRowWarp = kBMmaWarp + 1;
 constexpr int kBThreads = (kBRowWarp + 1) * 32;
 constexpr int kBAStages = 4, kBBStages = 4;
 constexpr int kBAStageCols = 64;       // 32 hi + 32 lo
 constexpr int kBACol0 = 256;           // accumulators live in columns [0,256), A' stages behind them
 constexpr int kBChunk = 32;            // samples per item
-constexpr int kBMaxMT = 4;             // M' tiles (of 128 lanes u) per item: 4 accumulators of N' <= 64 columns
-constexpr int kBLagStep = kBMaxMT * kBRows - kBShifts;   // 504 lags per lag block
+constexpr int kBRowBufs = 4;           // series-row ring
+constexpr int kBMaxMT = 4;             // M' tiles (of 128 lanes u) per item, at most; MT * N' <= 256 accumulator columns
 
 // role-level wait accounting (debug builds only: -DIGN_TC_PROFILE); slots: 0 prod wait row, 1 prod wait emptyA,
 // 2 build wait emptyB, 3 mma wait fullB, 4 mma wait fullA, 5 mma wait accempty, 6 drain wait accfull, 7 loader wait
@@ -67,8 +74,9 @@ struct BwdTcGeo {
   int B, M, T, Tp, K, L;
   int Tw, Ts;          // windows, coefficient row pitch
   int RI, NKB;         // window groups (of 8) per sample, 32-row k-blocks per sample
-  int MT;              // 128-lane tiles over u = l + j of ONE lag block (<= kBMaxMT; the last block may use fewer)
-  int nlb;             // lag blocks: ceil(L / 504)
+  int P;               // shifts: 16 or 8
+  int MT;              // 128-lane tiles over u = l + j of ONE lag block (the last block may use fewer)
+  int nlb, lagstep;    // lag blocks and their step in lags: 128 MT - P
   int KG, nkb, N;      // shapelets per N' tile, shapelet blocks, N' = 8*KG rounded up to 16
   int XR;              // floats per series row in shared memory (zero padded)
   int nchunk, nitems;
@@ -89,10 +97,13 @@ __device__ __forceinline__ ItemCoord item_coord(const BwdTcGeo& g, int w) {
   c.lb = mkl - mk * g.nlb;
   c.m = mk / g.nkb;
   c.kblk = mk - c.m * g.nkb;
-  c.mt = min(g.MT, (g.L + kBShifts - 1 - c.lb * kBLagStep + kBRows - 1) / kBRows);
+  c.mt = min(g.MT, (g.L + g.P - 1 - c.lb * g.lagstep + kBRows - 1) / kBRows);
   return c;
 }
 
+// KQ: shapelets per block the builder threads hold in registers (5 covers the reference's default K = 5 without the
+// register pressure of the general 8)
+template <int kBShifts, int KQ>
 __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const BwdTcGeo g, const BwdTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,22 +116,22 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
   const int stage_bytes = b_bytes * (g.split ? 2 : 1);
   uint8_t* stage0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ptr = stage0 + (size_t)kBBStages * stage_bytes;
-  float* xrow = reinterpret_cast<float*>(ptr);                      // [2][XR]
-  ptr += (size_t)2 * g.XR * sizeof(float);
+  float* xrow = reinterpret_cast<float*>(ptr);                      // [kBRowBufs][XR]
+  ptr += (size_t)kBRowBufs * g.XR * sizeof(float);
   const int TU = kBRows * g.MT + 8;                                 // pitch of one drained shift row
   float* tk = reinterpret_cast<float*>(ptr);                        // [8][TU] one shapelet's Gsh, transposed
   ptr += (size_t)kBShifts * TU * sizeof(float);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ptr);
   uint64_t* fullA = bars; uint64_t* emptyA = fullA + kBAStages;
   uint64_t* fullB = emptyA + kBAStages; uint64_t* emptyB = fullB + kBBStages;
-  uint64_t* rowfull = emptyB + kBBStages; uint64_t* rowempty = rowfull + 2;
-  uint64_t* accfull = rowempty + 2; uint64_t* accempty = accfull + 1;
+  uint64_t* rowfull = emptyB + kBBStages; uint64_t* rowempty = rowfull + kBRowBufs;
+  uint64_t* accfull = rowempty + kBRowBufs; uint64_t* accempty = accfull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBAStages; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < kBBStages; ++s) { mbar_init(&fullB[s], kBBuildWarps); mbar_init(&emptyB[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&rowfull[i], 1); mbar_init(&rowempty[i], kBProdWarps); }
+    for (int s = 0; s < kBBStages; ++s) { mbar_init(&fullB[s], kBBuildWarps / kBBuildGroups); mbar_init(&emptyB[s], 1); }
+    for (int i = 0; i < kBRowBufs; ++i) { mbar_init(&rowfull[i], 1); mbar_init(&rowempty[i], kBProdWarps); }
     mbar_init(accfull, 1); mbar_init(accempty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -147,9 +158,9 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       const ItemCoord ic = item_coord(g, w);
       const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
       for (int b = b0; b < b1; ++b, ++nrow) {
-        const int buf = nrow & 1;
+        const int buf = nrow % kBRowBufs;
         long long t0 = BP_CLK();
-        mbar_wait(&rowfull[buf], (nrow >> 1) & 1);
+        mbar_wait(&rowfull[buf], (nrow / kBRowBufs) & 1);
         BP_ADD(0, t0);
         const float* xs = xrow + (size_t)buf * g.XR;
         for (int kb = 0; kb < g.NKB; ++kb) {
@@ -158,12 +169,12 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
             const uint32_t ph = sph;
             if (++sidx == kBAStages) { sidx = 0; sph ^= 1; }
             if ((int)(ia & 1) != grp) continue;
-            // this lane's row of A': x[8 (32 kb + c) + 128 mt + up], c = 0..31 (zero beyond the series)
-            const float* src = xs + 8 * (kBKBlock * kb) + kBRows * mt + up + ic.lb * kBLagStep;
+            // this lane's row of A': x[P (32 kb + c) + 128 mt + up], c = 0..31 (zero beyond the series)
+            const float* src = xs + kBShifts * (kBKBlock * kb) + kBRows * mt + up + ic.lb * g.lagstep;
             uint32_t hi[32], lo[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const float v = src[8 * c];
+              const float v = src[kBShifts * c];
               hi[c] = __float_as_uint(v);
               lo[c] = __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u));
             }
@@ -194,17 +205,20 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
           const int k = k0 + kl;
           if (k >= g.K) break;                                       // uniform
           for (int mt = 0; mt < ic.mt; ++mt) {
-            uint32_t v[8];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                         : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * g.N + kl * kBShifts))
-                         : "memory");
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < kBShifts; ++j) tk[j * TU + kBRows * mt + up] = __uint_as_float(v[j]);
+            for (int h = 0; h < kBShifts / 8; ++h) {
+              uint32_t v[8];
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                           : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * g.N + kl * kBShifts + 8 * h))
+                           : "memory");
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tk[(8 * h + j) * TU + kBRows * mt + up] = __uint_as_float(v[j]);
+            }
           }
           bar_sync(3, 128);
-          const int l0 = ic.lb * kBLagStep, nl = min(kBLagStep, g.L - l0);            // this block's lags [l0, l0 + nl)
+          const int l0 = ic.lb * g.lagstep, nl = min(g.lagstep, g.L - l0);            // this block's lags [l0, l0 + nl)
           for (int l = et; l < nl; l += 128) {
             float s = 0.f;
 #pragma unroll
@@ -220,85 +234,104 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
     }
   } else if (warp < kBMmaWarp) {
     // =================================================================== B' BUILDERS
-    // Coefficient rows come straight from global memory (L2 / HBM latency): the loads of tile i+1 are issued before
-    // tile i is written, and before waiting for its stage to be free.
-    const int bt = threadIdx.x - kBProdWarps * 32;                   // 0..127
-    int sb = 0; uint32_t phb = 0;
-    // flat walk over (item, sample, k-block)
-    int cw = wbeg, cb = 0, ckb = 0, cb1 = 0;
-    ItemCoord cic{0, 0, 0};
-    auto enter_item = [&]() {
-      if (cw < wend) { cic = item_coord(g, cw); cb = cic.chunk * kBChunk; cb1 = min(g.B, cb + kBChunk); ckb = 0; }
-    };
-    auto fetch = [&](float4 (&v)[2][2]) {                            // this thread's (up to) two tasks of the current tile
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        v[q][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[q][1] = v[q][0];
-        const int task = bt + q * kBBuildWarps * 32;
-        if (cw >= wend || task >= g.KG * kBKBlock) continue;
-        const int kl = task >> 5, r = task & 31;
-        const int k = cic.kblk * g.KG + kl;
-        const int t = kBShifts * (kBKBlock * ckb + r);
-        if (k < g.K) {
-          const float* src = a.coef + (((size_t)cb * g.M + cic.m) * g.K + k) * g.Ts + t;
-          if (t < g.Ts) v[q][0] = __ldg(reinterpret_cast<const float4*>(src));
-          if (t + 4 < g.Ts) v[q][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        }
+    // Group `bgrp` (four warps) builds the tiles with (tile number & 1) == bgrp.  Work split inside a tile: thread
+    // (quad = warp in group, r = lane) owns, for EVERY shapelet kl of the block, the four shifts j = 4 quad .. 4 quad + 3
+    // of window group r — one 16-byte load and four (hi, lo) pairs of scattered 4-byte stores per shapelet, the same
+    // count for every thread (a (shapelet, window group) task per thread left a quarter of the threads with twice the
+    // work of the others at K = 5: 160 tasks on 128 threads).
+    // The coefficients stream from HBM: the loads of the group's next tile are in flight (registers) while the current
+    // one is written, and the tile after that is pulled into L2 (prefetch.global.L2) at the same time.
+    const int bgrp = (warp - kBProdWarps) / (kBBuildWarps / kBBuildGroups);
+    const int quad = (warp - kBProdWarps) % (kBBuildWarps / kBBuildGroups);
+    static_assert(kBShifts / 4 == kBBuildWarps / kBBuildGroups || kBShifts == 8, "one quad of shifts per builder warp");
+    constexpr int QN = kBShifts / 4;                                  // quads per task: 4 (16 shifts) or 2 (8 shifts)
+    // 8 shifts: two quads only, so warps (quad >> 1) split the shapelets instead: warp handles kl = (quad >> 1), +2, ..
+    const int jq = kBShifts == 16 ? quad : (quad & 1);                // which quad of shifts
+    const int kl0 = kBShifts == 16 ? 0 : (quad >> 1), klstep = kBShifts == 16 ? 1 : 2;
+    struct Cursor { int cw, cb, cb1, ckb, m, kblk; };
+    Cursor cur{wbeg, 0, 0, 0, 0, 0};
+    auto enter_item = [&](Cursor& c) {
+      if (c.cw < wend) {
+        const ItemCoord ic = item_coord(g, c.cw);
+        c.cb = ic.chunk * kBChunk; c.cb1 = min(g.B, c.cb + kBChunk); c.ckb = 0; c.m = ic.m; c.kblk = ic.kblk;
       }
     };
-    auto advance = [&]() {
-      if (++ckb == g.NKB) { ckb = 0; if (++cb == cb1) { ++cw; enter_item(); } }
+    auto advance1 = [&](Cursor& c) {
+      if (c.cw >= wend) return;
+      if (++c.ckb == g.NKB) { c.ckb = 0; if (++c.cb == c.cb1) { ++c.cw; enter_item(c); } }
     };
-    enter_item();
-    long long todo = 0;                                              // tiles this CTA builds
+    auto src_of = [&](const Cursor& c, int kl) -> const float* {     // nullptr: nothing to load (past the end / pad shapelet / pad windows)
+      const int k = c.kblk * g.KG + kl;
+      const int t = kBShifts * (kBKBlock * c.ckb + lane) + 4 * jq;
+      if (c.cw >= wend || k >= g.K || t >= g.Ts) return nullptr;
+      return a.coef + (((size_t)c.cb * g.M + c.m) * g.K + k) * g.Ts + t;
+    };
+    auto fetch = [&](const Cursor& c, float4 (&v)[KQ]) {
+#pragma unroll
+      for (int q = 0; q < KQ; ++q) {
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int kl = kl0 + q * klstep;
+        if (kl < g.KG) { const float* src = src_of(c, kl); if (src) v[q] = __ldg(reinterpret_cast<const float4*>(src)); }
+      }
+    };
+    auto prefetch_l2 = [&](const Cursor& c) {
+#pragma unroll
+      for (int q = 0; q < KQ; ++q) {
+        const int kl = kl0 + q * klstep;
+        if (kl < g.KG) { const float* src = src_of(c, kl); if (src) asm volatile("prefetch.global.L2 [%0];" ::"l"(src)); }
+      }
+    };
+    enter_item(cur);
+    long long total = 0;                                             // tiles this CTA builds
     for (int w2 = wbeg; w2 < wend; ++w2) {
       const ItemCoord c2 = item_coord(g, w2);
-      todo += (long long)(min(g.B, c2.chunk * kBChunk + kBChunk) - c2.chunk * kBChunk) * g.NKB;
+      total += (long long)(min(g.B, c2.chunk * kBChunk + kBChunk) - c2.chunk * kBChunk) * g.NKB;
     }
-    auto emit = [&](const float4 (&v)[2][2]) {                       // write one tile from registers, publish it
+    long long todo = (total - bgrp + 1) / 2;                         // tiles bgrp, bgrp + 2, ...
+    int sb = bgrp; uint32_t phb = 0;                                 // kBBStages is even: the group's stages keep its parity
+    static_assert(kBBStages % kBBuildGroups == 0, "a builder group must keep its stage parity");
+    auto emit = [&](const float4 (&v)[KQ]) {                         // write this thread's share of one tile, publish it
       long long t0 = BP_CLK();
       mbar_wait(&emptyB[sb], phb ^ 1);
       BP_ADD(2, t0);
       uint8_t* st = stage0 + (size_t)sb * stage_bytes;
+      const uint32_t colb = (uint32_t)((lane & 3) * 4);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int task = bt + q * kBBuildWarps * 32;
-        if (task >= g.KG * kBKBlock) continue;
-        const int kl = task >> 5, r = task & 31;
-        const float vv[8] = {v[q][0].x, v[q][0].y, v[q][0].z, v[q][0].w, v[q][1].x, v[q][1].y, v[q][1].z, v[q][1].w};
+      for (int q = 0; q < KQ; ++q) {
+        const int kl = kl0 + q * klstep;
+        if (kl >= g.KG) continue;
+        const float vv[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
-        for (int j = 0; j < kBShifts; ++j) {
-          const int n = kl * kBShifts + j;
-          const uint32_t off = sw128_off(n, r >> 2) + (uint32_t)((r & 3) * 4);
-          *reinterpret_cast<float*>(st + off) = vv[j];
-          if (g.split) *reinterpret_cast<float*>(st + b_bytes + off) = vv[j] - __uint_as_float(__float_as_uint(vv[j]) & 0xffffe000u);
+        for (int jj = 0; jj < 4; ++jj) {
+          const int n = kl * kBShifts + 4 * jq + jj;
+          const uint32_t off = sw128_off(n, lane >> 2) + colb;
+          *reinterpret_cast<float*>(st + off) = vv[jj];
+          if (g.split) *reinterpret_cast<float*>(st + b_bytes + off) = vv[jj] - __uint_as_float(__float_as_uint(vv[jj]) & 0xffffe000u);
         }
       }
       fence_proxy_async_smem();                                      // generic-proxy writes -> visible to the MMA's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&fullB[sb]);
-      if (++sb == kBBStages) { sb = 0; phb ^= 1; }
+      sb += kBBuildGroups;
+      if (sb >= kBBStages) { sb -= kBBStages; phb ^= 1; }
     };
-    // three register sets, unrolled by three: the loads of tiles i+1 and i+2 are in flight while tile i is written
-    // (the coefficients stream from HBM: one tile of prefetch distance left the latency exposed, builders 85 % busy at
-    // L=100), and no register copy between the sets ever waits for a load
-    float4 va[2][2], vb[2][2], vc[2][2];
-    fetch(va);
-    advance();
-    fetch(vb);
-    while (true) {
-      if (cw < wend) advance();
-      fetch(vc);
-      emit(va);
-      if (--todo == 0) break;
-      if (cw < wend) advance();
-      fetch(va);
-      emit(vb);
-      if (--todo == 0) break;
-      if (cw < wend) advance();
-      fetch(vb);
-      emit(vc);
-      if (--todo == 0) break;
+    if (todo > 0) {
+      if (bgrp) advance1(cur);                                       // group 1 starts at tile 1
+      float4 va[KQ], vb[KQ];
+      fetch(cur, va);
+      advance1(cur); advance1(cur);
+      while (true) {
+        fetch(cur, vb);                                              // the group's next tile -> registers
+        { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }   // the one after -> L2
+        emit(va);
+        if (--todo == 0) break;
+        advance1(cur); advance1(cur);
+        fetch(cur, va);
+        { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }
+        emit(vb);
+        if (--todo == 0) break;
+        advance1(cur); advance1(cur);
+      }
     }
   } else if (warp == kBMmaWarp) {
     // =================================================================== MMA ISSUER
@@ -353,28 +386,26 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
     __syncwarp();
   } else {
     // =================================================================== SERIES-ROW LOADER
-    for (int i = lane; i < 2 * g.XR; i += 32) xrow[i] = 0.f;          // pads behind Tp stay zero for ever
+    for (int i = lane; i < kBRowBufs * g.XR; i += 32) xrow[i] = 0.f;  // pads behind Tp stay zero for ever
+    fence_proxy_async_smem();                                        // generic zero fill before the async-proxy row copies
     __syncwarp();
-    const int chunks = g.Tp / 4;
-    int nrow = 0;
-    for (int w = wbeg; w < wend; ++w) {
-      const ItemCoord ic = item_coord(g, w);
-      const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
-      for (int b = b0; b < b1; ++b, ++nrow) {
-        const int buf = nrow & 1;
-        long long t0 = BP_CLK();
-        if (nrow >= 2) mbar_wait(&rowempty[buf], ((nrow >> 1) - 1) & 1);
-        BP_ADD(7, t0);
-        const float* src = a.xn + ((size_t)b * g.M + ic.m) * g.Tp;
-        float* dst = xrow + (size_t)buf * g.XR;
-        for (int c = lane; c < chunks; c += 32) cp_async16(dst + c * 4, src + c * 4);
-        cp_async_commit();
-        cp_async_wait_all();
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&rowfull[buf]);
+    if (elect_one()) {
+      const uint32_t row_bytes = (uint32_t)g.Tp * sizeof(float);     // Tp % 4 == 0: a multiple of 16, rows 16-byte aligned
+      int nrow = 0;
+      for (int w = wbeg; w < wend; ++w) {
+        const ItemCoord ic = item_coord(g, w);
+        const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
+        for (int b = b0; b < b1; ++b, ++nrow) {
+          const int buf = nrow % kBRowBufs;
+          long long t0 = BP_CLK();
+          if (nrow >= kBRowBufs) mbar_wait(&rowempty[buf], ((nrow / kBRowBufs) - 1) & 1);   // row nrow - kBRowBufs is consumed
+          BP_ADD(7, t0);
+          mbar_arrive_expect_tx(&rowfull[buf], row_bytes);
+          tma_bulk_g2s(xrow + (size_t)buf * g.XR, a.xn + ((size_t)b * g.M + ic.m) * g.Tp, row_bytes, &rowfull[buf]);
+        }
       }
     }
+    __syncwarp();
   }
 
   if (lane == 0 || (warp == kBMmaWarp)) {
@@ -391,11 +422,21 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
 void bwd_tc_geo(const ign_shapelet_desc& d, BwdTcGeo& g) {
   g.B = d.B; g.M = d.M; g.T = d.T; g.Tp = d.Tp; g.K = d.K; g.L = d.L;
   g.Tw = num_windows(d.T, d.L, 1); g.Ts = round_up(g.Tw, 4);
-  g.RI = ceil_div(g.Tw, kBShifts); g.NKB = ceil_div(g.RI, kBKBlock);
-  g.nlb = ceil_div(d.L, kBLagStep);
-  g.MT = min(kBMaxMT, ceil_div(d.L + kBShifts - 1, kBRows));
-  g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb); g.N = round_up(kBShifts * g.KG, 16);
-  g.XR = round_up(max(d.Tp, kBShifts * kBKBlock * g.NKB + (g.nlb - 1) * kBLagStep + kBRows * g.MT) + 8, 4);
+  g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb);
+  // 16 shifts when the whole shapelet then fits one lag block (half the A' tiles, B' stages and MMA issue slots per
+  // sample), else 8 shifts with up to four 128-lane tiles per block
+  g.P = 16;
+  g.N = 16 * g.KG;
+  // (measured at config 2, K = 5: L = 500 as two lag blocks of 16 shifts needs 10 A' tiles per sample, as one block of
+  //  8 shifts 16 — the A' producers pace that case; 8 shifts remain as the fallback for N' > 256, which K <= 8 per block
+  //  never reaches)
+  if (g.N > kBACol0) { g.P = 8; g.N = round_up(8 * g.KG, 16); }
+  const int mtmax = max(1, min(kBMaxMT, kBACol0 / g.N));
+  g.RI = ceil_div(g.Tw, g.P); g.NKB = ceil_div(g.RI, kBKBlock);
+  g.lagstep = mtmax * kBRows - g.P;
+  g.nlb = ceil_div(d.L, g.lagstep);
+  g.MT = min(mtmax, ceil_div(d.L + g.P - 1, kBRows));
+  g.XR = round_up(max(d.Tp, g.P * kBKBlock * g.NKB + (g.nlb - 1) * g.lagstep + kBRows * g.MT) + 8, 4);
   g.nchunk = ceil_div(d.B, kBChunk);
   g.nitems = d.M * g.nkb * g.nlb * g.nchunk;
   g.split = d.precision == IGN_PREC_3XTF32 ? 1 : 0;
@@ -403,8 +444,8 @@ void bwd_tc_geo(const ign_shapelet_desc& d, BwdTcGeo& g) {
 
 size_t bwd_tc_smem(const BwdTcGeo& g) {
   const size_t stage = (size_t)(g.N * 128) * (g.split ? 2 : 1);
-  return kBBStages * stage + (size_t)2 * g.XR * 4 + (size_t)kBShifts * (kBRows * g.MT + 8) * 4 +
-         (2 * kBAStages + 2 * kBBStages + 6) * 8 + 16 + 1024;
+  return kBBStages * stage + (size_t)kBRowBufs * g.XR * 4 + (size_t)g.P * (kBRows * g.MT + 8) * 4 +
+         (2 * kBAStages + 2 * kBBStages + 2 * kBRowBufs + 2) * 8 + 16 + 1024;
 }
 
 }  // namespace
@@ -440,10 +481,12 @@ int launch_shapelet_bwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   BwdTcGeo g;
   bwd_tc_geo(d, g);
   const size_t smem = max(bwd_tc_smem(g), (size_t)118 * 1024);       // > half the SM: one CTA per SM (it owns all of TMEM)
-  IGN_CUDA(cudaFuncSetAttribute(shapelet_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = g.P == 16 ? (g.KG <= 5 ? shapelet_bwd_tc_kernel<16, 5> : shapelet_bwd_tc_kernel<16, 8>)
+                        : shapelet_bwd_tc_kernel<8, 8>;
+  IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BwdTcArgs a{xn, coef, part};
   const int grid = min(sm_count(), g.nitems);
-  shapelet_bwd_tc_kernel<<<grid, kBThreads, smem, st>>>(g, a);
+  kern<<<grid, kBThreads, smem, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;
 }

@@ -481,7 +481,7 @@ def test_recompute_backward_at_k1000_bounded_workspace(tiny_store_budget):
     bs = [5, 131]
     g[bs] = torch.randn(len(bs), K, M, device=DEV)          # only two samples carry gradient: the oracle can check them
     desc = C.ShapeletDesc(B, M, T, T, K, L, 1, 1.0, 0, 0, 0)
-    assert 2 * C.lib.ign_shapelet_dstore_bytes(byref(desc)) > 7 * 2 ** 30
+    assert 2 * C.lib.ign_shapelet_dstore_bytes(byref(desc)) > 6 * 2 ** 30
     assert C.lib.ign_shapelet_backward_recompute_workspace(byref(desc), 2 ** 30) <= 2 ** 30
     torch.cuda.reset_peak_memory_stats()
     base = torch.cuda.memory_allocated()

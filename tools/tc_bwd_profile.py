@@ -9,7 +9,7 @@ NAMES = ["prod wait row", "prod wait emptyA", "build wait emptyB", "mma wait ful
          "drain wait accfull", "loader wait rowempty", "prod warp0 total", "builder warp0 total", "mma total", "loader total"]
 B, M, T, K = 256, 125, 1000, 5
 x = torch.randn(B, T, M, device="cuda"); pack = instance_norm(x)
-for L in (100, 500):
+for L in (100, 200, 500):
     W = torch.randn(K, M, L, device="cuda", requires_grad=True)
     p, _, _ = shapelet_transform(pack, W, 1, 1.0, "cosine", precision="3xtf32"); g = torch.randn_like(p)
     p.backward(g, retain_graph=True); torch.cuda.synchronize()
