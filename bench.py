@@ -521,13 +521,15 @@ def extra_config_lines(a):
     import copy
     from exp.experiment_classification import Experiment
     out = {}
-    for name, kw, batch, steps in (
-            ("config1_jv_fcn_b32", dict(enc_in=12, seq_len=29, num_class=9, dnn_type="FCN"), 32, 50),
-            ("config5_chisco39_transformer_b64", dict(enc_in=125, seq_len=1000, num_class=39, dnn_type="Transformer"), 64, 10)):
+    for name, kw, batch, steps, graph in (
+            ("config1_jv_fcn_b32", dict(enc_in=12, seq_len=29, num_class=9, dnn_type="FCN"), 32, 50, False),
+            # the same step replayed from one captured CUDA graph (run.py --cuda_graph): config 1 is launch-latency-bound
+            ("config1_jv_fcn_b32_cuda_graph", dict(enc_in=12, seq_len=29, num_class=9, dnn_type="FCN"), 32, 200, True),
+            ("config5_chisco39_transformer_b64", dict(enc_in=125, seq_len=1000, num_class=39, dnn_type="Transformer"), 64, 10, False)):
         cfg = model_args(a)
         for k, v in kw.items():
             setattr(cfg, k, v)
-        cfg.c_out, cfg.batch_size = cfg.num_class, batch
+        cfg.c_out, cfg.batch_size, cfg.cuda_graph = cfg.num_class, batch, graph
         torch.manual_seed(0)
         exp = Experiment(cfg, load_data=False)
         exp.model.train()
@@ -548,7 +550,7 @@ def extra_config_lines(a):
         ms = e0.elapsed_time(e1) / steps
         out[name] = {"samples_per_s": batch / (ms * 1e-3), "step_us": ms * 1e3, "batch": batch, "steps": steps,
                      "dnn_type": cfg.dnn_type, "num_class": cfg.num_class, "distance_func": cfg.distance_func,
-                     "precision": cfg.shapelet_precision}
+                     "precision": cfg.shapelet_precision, "cuda_graph": graph}
         del exp, x, y, mask
         torch.cuda.empty_cache()
     return out

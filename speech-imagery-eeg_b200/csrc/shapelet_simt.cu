@@ -605,8 +605,10 @@ __device__ __forceinline__ float pool_emit(float c, float d, float s0, float s1,
 }
 
 // Lane layout of a row: `nfull` whole 128-window chunks (lane owns the float4 at (j*32+lane)*4), then the remaining
-// < 128 windows in scalar sub-chunks of 32 (lane owns window tail0 + s*32 + lane), kept in the last register slot —
-// a nearly empty float4 chunk would cost the whole warp four element times (T' = 901: 14 % of the row's work).
+// < 128 windows, kept in the last register slot, either as ONE more float4 chunk with per-element validity (64 or more
+// tail windows: T' = 501 has 117, and four scalar sub-chunks with their scalar loads cost it a third of the row's time)
+// or in scalar sub-chunks of 32 (lane owns window tail0 + s*32 + lane) — a nearly empty float4 chunk would cost the
+// whole warp four element times (T' = 901, 5 tail windows: 14 % of the row's work).
 template <int POOL, int DIST, int NCH>
 __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const PoolArgs a, int rows) {
   extern __shared__ __align__(16) float prow[];          // [warps][kPoolStages][DP]
@@ -623,8 +625,11 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
   };
   const float eps = g.eps;
   const float q = -eps * eps * kLog2e;
-  const int nfull = g.Tw >> 7, tail0 = nfull << 7, ntail = g.Tw - tail0;   // nfull + (ntail > 0) <= NCH
+  const int nfull = g.Tw >> 7, tail0 = nfull << 7;                          // nfull + (tail > 0) <= NCH
+  const bool vtail = g.Tw - tail0 >= 64;                                    // the tail as one masked float4 chunk
+  const int ntail = vtail ? 0 : g.Tw - tail0;                               // windows handled by the scalar sub-chunks
   const int tt = tail0 + lane;
+  const int tv0 = tail0 + 4 * lane;                                         // this lane's first window of the masked chunk
   int row = blockIdx.x * nwarp + warp;
   prefetch(row, 0);
   prefetch(row + wstride, 1);
@@ -655,6 +660,7 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
 #pragma unroll
       for (int j = 0; j < NCH; ++j)
         if (j < nfull) S[j] = __ldg(reinterpret_cast<const float4*>(s0r + (j * 32 + lane) * 4));
+      if (vtail && tv0 < g.Ts) S[NS - 1] = __ldg(reinterpret_cast<const float4*>(s0r + tv0));   // Ts <= SP
     }
     float Zs = 0.f, S1s = 0.f, pmx = 0.f;
     int jmx = -1;
@@ -693,12 +699,27 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
     IGN_POOL_TAIL1(2, U[NCH - 1].z, V[NCH - 1].z)
     IGN_POOL_TAIL1(3, U[NCH - 1].w, V[NCH - 1].w)
 #undef IGN_POOL_TAIL1
+    if (vtail && tv0 < g.Tw) {                             // masked float4 tail chunk -> the last register slot
+      const float4 d = d4[nfull * 32 + lane];
+      float m4;
+      eval(d.x, U[NCH - 1].x, V[NCH - 1].x); m4 = V[NCH - 1].x;
+      if (tv0 + 1 < g.Tw) { eval(d.y, U[NCH - 1].y, V[NCH - 1].y); m4 = fmaxf(m4, V[NCH - 1].y); }
+      if (tv0 + 2 < g.Tw) { eval(d.z, U[NCH - 1].z, V[NCH - 1].z); m4 = fmaxf(m4, V[NCH - 1].z); }
+      if (tv0 + 3 < g.Tw) { eval(d.w, U[NCH - 1].w, V[NCH - 1].w); m4 = fmaxf(m4, V[NCH - 1].w); }
+      if (POOL == IGN_POOL_RBF_MAX) { if (jmx < 0 || m4 > pmx) { pmx = m4; jmx = 2 * NCH; } }
+    }
     float fix;
     if (POOL == IGN_POOL_RBF_MAX) {
       // first arg-max of p (the reference's hard one-hot, Shapelet.py:79): position inside the lane's best chunk, then
       // across lanes (largest p, smallest index).  p' >= 0, so its bit pattern orders like the value.
       int imx = 0x7fffffff;
-      if (jmx >= NCH) {
+      if (jmx == 2 * NCH) {                                // inside the masked tail chunk
+        const float4 d = d4[nfull * 32 + lane];
+        if (tv0 + 3 < g.Tw && rbf_pprime(d.w, q) == pmx) imx = tv0 + 3;
+        if (tv0 + 2 < g.Tw && rbf_pprime(d.z, q) == pmx) imx = tv0 + 2;
+        if (tv0 + 1 < g.Tw && rbf_pprime(d.y, q) == pmx) imx = tv0 + 1;
+        if (rbf_pprime(d.x, q) == pmx) imx = tv0;
+      } else if (jmx >= NCH) {
         imx = tt + (jmx - NCH) * 32;
       } else if (jmx >= 0) {
         const int t0 = (jmx * 32 + lane) * 4;
@@ -761,7 +782,25 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_reg_kernel(const Geo g, const
     IGN_POOL_TAIL2(2, U[NCH - 1].z, V[NCH - 1].z)
     IGN_POOL_TAIL2(3, U[NCH - 1].w, V[NCH - 1].w)
 #undef IGN_POOL_TAIL2
-    if (lane < g.Ts - g.Tw) dst[g.Tw + lane] = 0.f;                  // pad windows (at most 3)
+    if (vtail && tv0 < g.Ts) {                             // masked float4 tail chunk: pad windows (t >= T') get 0
+      const float4 uu = U[NCH - 1], vv = V[NCH - 1];
+      float cc[4] = {Kc * uu.x * (vv.x - vbar), Kc * uu.y * (vv.y - vbar), Kc * uu.z * (vv.z - vbar), Kc * uu.w * (vv.w - vbar)};
+      const int hc = ih - tv0;
+      if ((unsigned)hc < 4u) {
+        cc[0] += hc == 0 ? fix : 0.f; cc[1] += hc == 1 ? fix : 0.f; cc[2] += hc == 2 ? fix : 0.f; cc[3] += hc == 3 ? fix : 0.f;
+      }
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f), s0 = d, s1 = d;
+      if (kStats) d = d4[nfull * 32 + lane];
+      if (DIST == IGN_DIST_COSINE) s0 = S[NS - 1];
+      if (DIST == IGN_DIST_PEARSON) { s0 = *reinterpret_cast<const float4*>(s0r + tv0); s1 = *reinterpret_cast<const float4*>(s1r + tv0); }
+      float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tv0 < g.Tw) out.x = pool_emit<DIST>(cc[0], d.x, s0.x, s1.x, wst, sc0, sc1);
+      if (tv0 + 1 < g.Tw) out.y = pool_emit<DIST>(cc[1], d.y, s0.y, s1.y, wst, sc0, sc1);
+      if (tv0 + 2 < g.Tw) out.z = pool_emit<DIST>(cc[2], d.z, s0.z, s1.z, wst, sc0, sc1);
+      if (tv0 + 3 < g.Tw) out.w = pool_emit<DIST>(cc[3], d.w, s0.w, s1.w, wst, sc0, sc1);
+      *reinterpret_cast<float4*>(dst + tv0) = out;
+    }
+    if (!vtail && lane < g.Ts - g.Tw) dst[g.Tw + lane] = 0.f;        // pad windows (at most 3)
     sc0 = warp_sum(sc0);
     if (DIST == IGN_DIST_PEARSON) sc1 = warp_sum(sc1);
     if (lane == 0) { a.rowsc[(size_t)row * 2] = sc0; a.rowsc[(size_t)row * 2 + 1] = sc1; }

@@ -33,6 +33,7 @@ FLAGS = [
     ("--shapelet_precision", str, "fp32"), ("--syn_shape", str, None), ("--syn_train", int, 512),
     ("--syn_val", int, 128), ("--syn_test", int, 128), ("--syn_subjects", int, 1),
     ("--loso", "store_true", False),      # leave-one-subject-out: one fold per subject, folds spread over the ranks
+    ("--cuda_graph", "store_true", False),        # replay each full-batch training step from one captured CUDA graph
     ("--allow_synthetic", "store_true", False),   # --data UEA|EEG|EEG3 without the archive on disk: synthetic series of its shape
 ]
 

@@ -27,7 +27,7 @@ def test_run_py_trains_tests_and_checkpoints_with_reference_keys(tmp_path, monke
     argv = ["--model", "InterpGN", "--dnn_type", "FCN", "--dataset", "JapaneseVowels", "--train_epochs", "6",
             "--batch_size", "32", "--lr", "5e-3", "--dropout", "0.", "--num_shapelet", "10", "--lambda_div", "0.1",
             "--lambda_reg", "0.1", "--epsilon", "1", "--beta_schedule", "constant", "--seed", "0", "--gating_value", "1",
-            "--amp", "--log_interval", "1", "--syn_train", "256", "--syn_val", "64", "--syn_test", "64"]
+            "--amp", "--log_interval", "1", "--syn_train", "256", "--syn_val", "64", "--syn_test", "64", "--cuda_graph"]
     run, results = _run_main(argv, tmp_path, monkeypatch)
     assert len(results) == 1
     loss, acc = results[0]
@@ -153,3 +153,40 @@ def test_nccl_two_rank_gradients_equal_full_batch_gradients(tmp_path):
     worst = float(line.split("worst_rel=")[1].split()[0])
     assert worst < 2e-4, line
     assert "identical_across_ranks=True" in line
+
+
+def test_cuda_graph_replay_is_the_same_training_as_the_eager_step(tmp_path, monkeypatch):
+    """--cuda_graph replays forward + backward + Adam (+ clamp, gradient reset) of a full batch from one captured graph.
+    Same kernels, same order: the parameters after N steps equal those of the eager loop (which here repeats the
+    capture's three warm-up steps on the first batch, as the graphed path does; the capture pass itself only records)."""
+    import copy
+    import run
+    from exp.experiment_classification import Experiment
+    monkeypatch.chdir(tmp_path)
+    base = run.get_args(["--dataset", "JapaneseVowels", "--dnn_type", "FCN", "--batch_size", "32", "--seed", "0", "--amp",
+                         "--syn_train", "64", "--syn_val", "32", "--syn_test", "32", "--pos_weight"])
+    torch.backends.cudnn.deterministic = True
+    gen = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(32, 29, 12, generator=gen).cuda(), torch.randint(0, 9, (32,), generator=gen).cuda(),
+                torch.ones(32, 29).cuda()) for _ in range(5)]
+    params = {}
+    for mode in ("eager", "graph"):
+        args = copy.copy(base)
+        args.cuda_graph = mode == "graph"
+        run.set_seed(0)
+        exp = Experiment(args)
+        exp.model.train()
+        exp.grads.zero_grad()
+        losses = []
+        for i, (x, y, m) in enumerate(batches):
+            if mode == "eager" and i == 0:
+                for _ in range(3):                           # the 3 warm-up steps of the graphed path
+                    exp.train_step(x, y, m, 0, 1)
+            losses.append(float(exp.train_step(x, y, m, 0, i + 1)))
+        if mode == "graph":
+            assert exp._graph is not None
+            # a ragged batch falls back to the eager step and keeps training the same parameters
+            exp.train_step(batches[0][0][:7], batches[0][1][:7], batches[0][2][:7], 0, 9)
+        params[mode] = ([p.detach().clone() for p in exp.model.parameters()], losses)
+    for le, lg in zip(params["eager"][1], params["graph"][1]):
+        assert abs(le - lg) <= 1e-4 * abs(le) + 1e-6, (params["eager"][1], params["graph"][1])
