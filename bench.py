@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--num_class", type=int, default=3)
     ap.add_argument("--cpu_batch", type=int, default=2)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--cuda_graph", action="store_true", help="replay each step from one captured CUDA graph (N=1)")
     ap.add_argument("--no_extras", action="store_true", help="skip the cosine/3xtf32 mode, the same-GPU eager comparator "
                     "and the config-1 / config-5 lines (they run at N=1 only)")
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the deep expert (reference default is fp32 in its scripts)")
@@ -67,7 +68,7 @@ def model_args(a):
         num_workers=0, log_interval=20, min_epochs=0, lr_decay=False,
         # Transformer expert (run.py defaults)
         task_name="classification", pred_len=0, label_len=0, output_attention=False, d_model=512, embed="timeF",
-        freq="h", factor=1, n_heads=8, d_ff=2048, activation="gelu", e_layers=2)
+        freq="h", factor=1, n_heads=8, d_ff=2048, activation="gelu", e_layers=2, cuda_graph=getattr(a, "cuda_graph", False))
 
 
 def algorithmic_elements(B, M, T, K, fracs):
