@@ -12,6 +12,31 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPU cores NVML reports as local to its GPU, so that the pinned host batches it allocates
+    afterwards (first touch) and the copy engine's reads sit on the GPU's own NUMA node.  With eight ranks on one box all
+    128 MB/step batches otherwise tend to land on node 0 and the far GPUs' H2D copies cross the socket link (the 8-GPU
+    end-to-end efficiency was 0.981 against 0.993 with resident inputs).  Best effort: silently skipped when NVML or
+    the affinity call is unavailable.  IGN_NO_NUMA_BIND=1 disables it."""
+    if os.environ.get("IGN_NO_NUMA_BIND") == "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def init_distributed(timeout=None):
     """Reads torchrun's environment.  Returns (rank, local_rank, world_size).  `timeout` (datetime.timedelta) replaces
     the process group's default collective timeout (NCCL: 10 minutes) — leave-one-subject-out runs pass days, because
@@ -22,6 +47,7 @@ def init_distributed(timeout=None):
     if world > 1 and not dist.is_initialized():
         backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            bind_to_gpu_numa(local)
             torch.cuda.set_device(local)
         kw = {} if timeout is None else {"timeout": timeout}
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw,
