@@ -186,6 +186,19 @@ int32_t ign_shapelet_backward(const ign_shapelet_desc* desc, const float* xn_dev
                               const int32_t* argmin_dev, float* dW_dev, void* workspace_dev,
                               size_t workspace_bytes, void* stream);
 
+/* The same call split in two, for callers that own several length groups (ShapeBottleneckModel has four): the
+ * PREPARE phase (pooling backward, L1 tie pre-check: HBM / L2-bound, a few hundred microseconds) of the next groups
+ * can be issued on a second stream under the compute-bound CONTRACT phase (contraction + finalize -> dW) of the current
+ * one.  Both phases take the same arguments and the same workspace; CONTRACT must be ordered after PREPARE of its own
+ * group (stream order or an event).  Stored-distance mode only (dstore_dev != NULL). */
+#define IGN_BWD_PREPARE 1
+#define IGN_BWD_CONTRACT 2
+int32_t ign_shapelet_backward_phases(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,
+                                     const float* st1_dev, const float* W_dev, const float* threshold_dev,
+                                     const float* g_dev, const float* dstore_dev, const float* dmin_dev,
+                                     const int32_t* argmin_dev, float* dW_dev, void* workspace_dev,
+                                     size_t workspace_bytes, int32_t phases, void* stream);
+
 /* InterpGN gate + mixture (InterpGN.py:44-52): q=softmax(s), eta=(C*sum q^2-1)/(C-1),
  * if use_gate: eta=1 where eta>gating_value; out=eta*s+(1-eta)*z.  s,z,out [B,C]; eta [B]. */
 int32_t ign_gate_forward(const float* sbm_out_dev, const float* deep_out_dev, float* out_dev,

@@ -189,17 +189,28 @@ int32_t ign_shapelet_backward(const ign_shapelet_desc* d, const float* xn, const
                               const float* W, const float* thr, const float* g, const float* dstore,
                               const float* dmin, const int32_t* argmin, float* dW, void* ws, size_t ws_bytes,
                               void* stream) {
+  return ign_shapelet_backward_phases(d, xn, st0, st1, W, thr, g, dstore, dmin, argmin, dW, ws, ws_bytes,
+                                      IGN_BWD_PREPARE | IGN_BWD_CONTRACT, stream);
+}
+
+int32_t ign_shapelet_backward_phases(const ign_shapelet_desc* d, const float* xn, const float* st0, const float* st1,
+                                     const float* W, const float* thr, const float* g, const float* dstore,
+                                     const float* dmin, const int32_t* argmin, float* dW, void* ws, size_t ws_bytes,
+                                     int32_t phases, void* stream) {
   int rc = check_desc(d, "shapelet_backward");
   if (rc) return rc;
   IGN_REQUIRE(xn && W && g && dW && ws, "shapelet_backward: null pointer");
   IGN_REQUIRE(d->dist == IGN_DIST_L1 || st0, "shapelet_backward: dist %d needs the window statistics", d->dist);
   IGN_REQUIRE(d->dist != IGN_DIST_PEARSON || st1, "shapelet_backward: PEARSON needs st1 (window means)");
+  IGN_REQUIRE(phases >= 1 && phases <= 3, "shapelet_backward: phases must be IGN_BWD_PREPARE, IGN_BWD_CONTRACT or both");
   if (!dstore) {   // recompute mode: nothing was kept by the forward
+    IGN_REQUIRE(phases == 3, "shapelet_backward(recompute): the phases cannot be split (the workspace is reused per chunk)");
     IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || thr, "shapelet_backward(recompute): lts_min needs the threshold again");
     return launch_shapelet_bwd_recompute(*d, xn, st0, st1, W, thr, g, dW, ws, ws_bytes, (cudaStream_t)stream);
   }
   IGN_REQUIRE(d->pool != IGN_POOL_LTS_MIN || (dmin && argmin), "shapelet_backward: lts_min needs the forward's dmin and argmin");
-  return launch_shapelet_bwd_simt(*d, xn, st0, st1, W, g, d->K, 0, dstore, dmin, argmin, dW, ws, ws_bytes, (cudaStream_t)stream);
+  return launch_shapelet_bwd_simt(*d, xn, st0, st1, W, g, d->K, 0, dstore, dmin, argmin, dW, ws, ws_bytes, phases,
+                                  (cudaStream_t)stream);
 }
 
 int32_t ign_diversity_partials(int32_t K) { return K <= 0 ? 0 : diversity_blocks(K) * diversity_blocks(K); }

@@ -57,7 +57,7 @@ size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d);
 int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
                              const float* st1, const float* W, const float* g, int gK, int gk0, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
-                             cudaStream_t st);
+                             int phases, cudaStream_t st);
 size_t shapelet_bwd_recompute_workspace(const ign_shapelet_desc& d, size_t budget);
 int launch_shapelet_bwd_recompute(const ign_shapelet_desc& d, const float* xn, const float* st0, const float* st1,
                                   const float* W, const float* thr, const float* g, float* dW, void* ws,

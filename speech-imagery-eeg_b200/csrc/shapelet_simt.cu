@@ -1365,7 +1365,11 @@ size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
 int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const float* st0,
                              const float* st1, const float* W, const float* gr, int gK, int gk0, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
-                             cudaStream_t st) {
+                             int phases, cudaStream_t st) {
+  // phases: bit 0 = preparation (pooling backward, pearson shapelet norms, L1 tie pre-check: HBM / L2-bound, needs
+  // only the forward's saved tensors and g), bit 1 = contraction + finalize (compute-bound).  A caller that owns
+  // several length groups issues the preparation of the next groups on a second stream under the contraction of the
+  // current one (layers/shapelet_ops.py).
   Geo g; BwdPlan bp;
   if (!base_geo(d, g)) { set_error("shapelet_backward: T=%d < L=%d", d.T, d.L); return IGN_ERR_INVALID; }
   const BwdKernel kern = bwd_kernel(d.dist);
@@ -1374,6 +1378,10 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   if (ws_bytes < wo.total * sizeof(float)) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, wo.total * sizeof(float)); return IGN_ERR_INVALID; }
   if (((uintptr_t)ws & 15) != 0) { set_error("shapelet_backward: workspace must be 16-byte aligned"); return IGN_ERR_INVALID; }
   float* base = reinterpret_cast<float*>(ws);
+  const bool use_tc = shapelet_bwd_tc_supported(d);
+  const bool use_tie = !use_tc && d.dist == IGN_DIST_L1 && bp.hcap;
+  unsigned char* tflags = reinterpret_cast<unsigned char*>(base + wo.tie);
+  if (phases & 1) {
   // 1. pooling backward (elementwise, HBM-bound): d -> per-window coefficients + per-row scalars
   if (d.dist == IGN_DIST_PEARSON) {
     shapelet_centred_norm_kernel<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.wstat, d.K * d.M, d.L);
@@ -1418,9 +1426,21 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
 #undef IGN_POOL_LAUNCH_K
     IGN_CUDA(cudaGetLastError());
   }
+  if (use_tie) {     // L1: which series rows can hold a value equal to one of their shapelet block's values
+    PhaseScope ph(PH_TIE, st);
+    const int bsplit = max(1, min(d.B, ceil_div(sm_count(), d.M * g.nkb)));
+    const size_t hs = ((size_t)bp.hcap + kTieBitmapWords) * sizeof(unsigned);
+    int rc0 = set_smem(tie_check_kernel, hs);
+    if (rc0) return rc0;
+    tie_check_kernel<<<dim3(d.M, g.nkb, bsplit), 256, hs, st>>>(xn, W, tflags, d.B, d.M, d.T, d.Tp, d.K, d.L, g.KB,
+                                                               g.nkb, bp.hcap, bsplit);
+    IGN_CUDA(cudaGetLastError());
+  }
+  }   // phases & 1
+  if (!(phases & 2)) return IGN_OK;
   // 2. contraction with the series into per-chunk partials: tensor pipe for the cross-term modes in the tcgen05
   //    precisions (shapelet_tc_bwd.cu), FP32 pipe otherwise
-  if (shapelet_bwd_tc_supported(d)) {
+  if (use_tc) {
     int rc;
     { PhaseScope ph(PH_CONTRACT, st); rc = launch_shapelet_bwd_tc(d, xn, base + wo.coef, base + wo.part, st); }
     if (rc) return rc;
@@ -1430,19 +1450,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     IGN_CUDA(cudaGetLastError());
     return IGN_OK;
   }
-  const unsigned char* tie = nullptr;
-  if (d.dist == IGN_DIST_L1 && bp.hcap) {
-    PhaseScope ph(PH_TIE, st);
-    unsigned char* tflags = reinterpret_cast<unsigned char*>(base + wo.tie);
-    const int bsplit = max(1, min(d.B, ceil_div(sm_count(), d.M * g.nkb)));
-    const size_t hs = ((size_t)bp.hcap + kTieBitmapWords) * sizeof(unsigned);
-    int rc0 = set_smem(tie_check_kernel, hs);
-    if (rc0) return rc0;
-    tie_check_kernel<<<dim3(d.M, g.nkb, bsplit), 256, hs, st>>>(xn, W, tflags, d.B, d.M, d.T, d.Tp, d.K, d.L, g.KB,
-                                                               g.nkb, bp.hcap, bsplit);
-    IGN_CUDA(cudaGetLastError());
-    tie = tflags;
-  }
+  const unsigned char* tie = use_tie ? tflags : nullptr;
   BwdArgs a{xn, W, base + wo.coef, base + wo.part, bp.nseg, bp.nlb, bp.tlb, tie};
   if (debug_plan_on()) debug_plan("bwd", g, bp.threads, bp.smem_bytes, occupancy(kern, bp.threads, bp.smem_bytes), bp.nseg, bp.nlb);
   int rc;
@@ -1525,7 +1533,7 @@ int launch_shapelet_bwd_recompute(const ign_shapelet_desc& d, const float* xn, c
     if (rc1) return rc1;
     // 2. pooling backward in place, contraction, finalize -> dW[k0 .. k0+Kc)
     rc1 = launch_shapelet_bwd_simt(dc, xn, st0, st1, W + wofs, gr, d.K, k0, nullptr, outp + no,
-                                   reinterpret_cast<const int*>(outp + 2 * no), dW + wofs, ws, rc.bwd_bytes, st);
+                                   reinterpret_cast<const int*>(outp + 2 * no), dW + wofs, ws, rc.bwd_bytes, 3, st);
     if (rc1) return rc1;
   }
   return IGN_OK;

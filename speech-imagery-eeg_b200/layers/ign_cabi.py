@@ -15,6 +15,7 @@ DIST = {"l1": 0, "sql2": 1, "cosine": 2, "pearson": 3}
 POOL = {"rbf_max": 0, "lts_min": 1}
 PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2}
 ENGINE = {0: "fp32", 1: "tcgen05"}
+BWD_PREPARE, BWD_CONTRACT = 1, 2
 
 
 class ShapeletDesc(Structure):
@@ -55,6 +56,7 @@ _SIGNATURES = {
     "ign_shapelet_dstore_bytes": (c_size_t, [POINTER(ShapeletDesc)]),
     "ign_shapelet_backward_recompute_workspace": (c_size_t, [POINTER(ShapeletDesc), c_size_t]),
     "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 11 + [c_size_t, _P]),
+    "ign_shapelet_backward_phases": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 11 + [c_size_t, c_int32, _P]),
     "ign_diversity_partials": (c_int32, [c_int32]),
     "ign_diversity_forward": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
     "ign_diversity_backward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),

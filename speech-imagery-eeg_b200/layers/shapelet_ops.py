@@ -203,60 +203,121 @@ def instance_norm(x: torch.Tensor) -> SeriesPack:
     return SeriesPack(xn, T)
 
 
+# When a model owns several length groups (ShapeBottleneckModel: four), the memory-bound preparation phase of every
+# group's backward (pooling backward, tie pre-check) CAN be issued on a side stream with only the compute-bound
+# contractions on the main stream, each waiting for its own group's event.  MEASURED ON B200 AND OFF BY DEFAULT: at
+# config 2 it changes nothing for the L1 engine (22.57 vs 22.55 ms per step: the contraction's three CTAs per SM leave
+# no shared memory for a pooling CTA to co-reside) and costs the tcgen05 engine 4 % (8.6 -> 8.95 ms: the persistent
+# one-CTA-per-SM contraction and the pooling kernel time-slice the SMs instead of overlapping).  IGN_OVERLAP_BWD_PREPARE=1
+# enables it for experiments; the deep expert's side stream (models/InterpGN.py) is the overlap that pays.
+OVERLAP_BWD_PREPARE = os.environ.get("IGN_OVERLAP_BWD_PREPARE", "0") == "1"
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+class _Group:
+    """One length group's forward state (what the backward needs)."""
+    __slots__ = ("desc", "dist", "pool", "stored", "thr_shape", "n_saved", "needs")
+
+
+def _forward_group(pack: SeriesPack, W, threshold, stride, eps, dist, pool, precision, need_grad):
+    """Launch one group's forward.  Returns (group record, outputs (p, dmin, idx), tensors to save for backward)."""
+    xn = pack.xn
+    B, M, T, Tp = pack.B, pack.M, pack.T, pack.Tp
+    K, M2, L = W.shape
+    if M2 != M:
+        raise RuntimeError("shapelet channels %d != series channels %d" % (M2, M))
+    Wc = W.detach().to(torch.float32).contiguous()
+    thr = None
+    if pool == "lts_min":
+        thr = threshold.detach().to(torch.float32).reshape(K, M).contiguous()
+    desc = C.ShapeletDesc(B, M, T, Tp, K, L, int(stride), float(eps), C.DIST[dist], C.POOL[pool], C.PRECISION[precision])
+    st0, _ = pack.window_stats(dist, L, stride)
+    dev = xn.device
+    out = torch.empty((2, B, K, M), dtype=torch.float32, device=dev)     # p, dmin
+    idx = torch.empty((B, K, M), dtype=torch.int32, device=dev)         # argmin_t d
+    dstore = None
+    # stored-distance backward while distances + coefficients fit the budget, recompute backward beyond it
+    store = need_grad and 2 * int(C.lib.ign_shapelet_dstore_bytes(byref(desc))) <= STORE_BUDGET_BYTES
+    if store:
+        Tw = C.padded_windows(T, L, int(stride))
+        dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
+    fws_bytes = int(C.lib.ign_shapelet_forward_workspace(byref(desc)))
+    fws = torch.empty((fws_bytes,), dtype=torch.uint8, device=dev) if fws_bytes else None
+    tag = "shapelet_fwd/%s/L%d" % (dist, L)
+    STATS.note_engine(tag, desc, False)
+    with torch.cuda.device(dev):
+        C.check(STATS.call(tag, 2 if fws_bytes else 1, lambda: C.lib.ign_shapelet_forward(
+            byref(desc), _ptr(xn), _ptr(st0), _ptr(Wc), _ptr(thr), _ptr(out[0]), _ptr(out[1]),
+            _ptr(idx), _ptr(dstore), _ptr(fws), fws_bytes, _stream())), "ign_shapelet_forward")
+    rec = _Group()
+    rec.desc, rec.dist, rec.pool, rec.stored = desc, dist, pool, bool(store)
+    rec.thr_shape = None if threshold is None else threshold.shape
+    saved = (Wc, out, idx, dstore if store else thr) if need_grad else ()
+    rec.n_saved = len(saved)
+    return rec, (out[0], out[1], idx), saved
+
+
+def _backward_group_args(rec: _Group, pack: SeriesPack, saved, g_p, need_dthr):
+    """Host-side preparation of one group's backward: (g, dthr, call) where call(phases) launches the library."""
+    Wc, out, idx, extra = saved
+    dstore, thr = (extra, None) if rec.stored else (None, extra)
+    desc = rec.desc
+    g = g_p.to(torch.float32).contiguous()
+    dthr = None
+    if rec.pool == "lts_min":
+        p = out[0]
+        sig = p * (1.0 - p)                         # d sigmoid(thr - min_d)
+        if need_dthr:
+            dthr = (g * sig).sum(dim=0).reshape(rec.thr_shape)
+        g = (-g * sig).contiguous()                 # dLoss/d(min_d)
+    st0, st1 = pack.window_stats(rec.dist, desc.L, desc.stride)
+    if rec.stored:
+        nbytes = C.lib.ign_shapelet_backward_workspace(byref(desc))
+    else:       # recompute mode: the library walks the shapelets in chunks inside this bounded workspace
+        nbytes = C.lib.ign_shapelet_backward_recompute_workspace(byref(desc), STORE_BUDGET_BYTES)
+    ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=g.device)
+    dW = torch.empty_like(Wc)
+    tag = "shapelet_bwd/%s/L%d" % (rec.dist, desc.L)
+    STATS.note_engine(tag, desc, True)
+
+    def call(phases):
+        with torch.cuda.device(g.device):
+            launch = lambda: C.lib.ign_shapelet_backward_phases(
+                byref(desc), _ptr(pack.xn), _ptr(st0), _ptr(st1), _ptr(Wc), _ptr(thr), _ptr(g), _ptr(dstore),
+                _ptr(out[1]), _ptr(idx), _ptr(dW), _ptr(ws), int(nbytes), int(phases), _stream())
+            if phases == C.BWD_PREPARE:            # counted and timed with the contraction call of the same group
+                C.check(launch(), "ign_shapelet_backward_phases")
+            else:
+                C.check(STATS.call(tag, 2, launch), "ign_shapelet_backward")
+    return dW, dthr, call, (g, ws, st0, st1)
+
+
 class _ShapeletTransform(torch.autograd.Function):
     """One length group: window distance + pooling over time, with the saved-statistics backward."""
 
     @staticmethod
     def forward(ctx, W, threshold, pack: SeriesPack, stride, eps, dist, pool, precision, track):
-        xn = pack.xn
-        B, M, T, Tp = pack.B, pack.M, pack.T, pack.Tp
-        K, M2, L = W.shape
-        if M2 != M:
-            raise RuntimeError("shapelet channels %d != series channels %d" % (M2, M))
-        Wc = W.detach().to(torch.float32).contiguous()
-        thr = None
-        if pool == "lts_min":
-            thr = threshold.detach().to(torch.float32).reshape(K, M).contiguous()
-        desc = C.ShapeletDesc(B, M, T, Tp, K, L, int(stride), float(eps), C.DIST[dist], C.POOL[pool],
-                              C.PRECISION[precision])
-        st0, _ = pack.window_stats(dist, L, stride)
         # Grad mode is always off inside Function.forward and needs_input_grad mirrors requires_grad even under
         # torch.no_grad(), so the caller's grad mode is passed in: evaluation loops must not pay for the 1.9 GB of
         # saved window distances.
         need_grad = bool(track and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]))
-        dev = xn.device
-        out = torch.empty((2, B, K, M), dtype=torch.float32, device=dev)     # p, dmin
-        idx = torch.empty((B, K, M), dtype=torch.int32, device=dev)         # argmin_t d
-        dstore = None
-        # stored-distance backward while distances + coefficients fit the budget, recompute backward beyond it
-        store = need_grad and 2 * int(C.lib.ign_shapelet_dstore_bytes(byref(desc))) <= STORE_BUDGET_BYTES
-        if store:
-            Tw = C.padded_windows(T, L, int(stride))
-            dstore = torch.empty((B, M, K, Tw), dtype=torch.float32, device=dev)
-        fws_bytes = int(C.lib.ign_shapelet_forward_workspace(byref(desc)))
-        fws = torch.empty((fws_bytes,), dtype=torch.uint8, device=dev) if fws_bytes else None
-        STATS.note_engine("shapelet_fwd/%s/L%d" % (dist, L), desc, False)
-        with torch.cuda.device(dev):
-            C.check(STATS.call("shapelet_fwd/%s/L%d" % (dist, L), 2 if fws_bytes else 1, lambda: C.lib.ign_shapelet_forward(
-                byref(desc), _ptr(xn), _ptr(st0), _ptr(Wc), _ptr(thr), _ptr(out[0]), _ptr(out[1]),
-                _ptr(idx), _ptr(dstore), _ptr(fws), fws_bytes, _stream())), "ign_shapelet_forward")
+        rec, outs, saved = _forward_group(pack, W, threshold, stride, eps, dist, pool, precision, need_grad)
         ctx.set_materialize_grads(False)
-        ctx.desc = desc
-        ctx.dist = dist
-        ctx.pool = pool
-        ctx.pack = pack
-        ctx.thr_shape = None if threshold is None else threshold.shape
-        ctx.stored = store
+        ctx.rec, ctx.pack = rec, pack
         if need_grad:
-            ctx.save_for_backward(Wc, out, idx, dstore if store else thr)
-        ctx.mark_non_differentiable(idx)
-        return out[0], out[1], idx
+            ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable(outs[2])
+        return outs
 
     @staticmethod
     def backward(ctx, g_p, g_dmin, _g_idx):
-        Wc, out, idx, extra = ctx.saved_tensors
-        dstore, thr = (extra, None) if ctx.stored else (None, extra)
-        desc, pack = ctx.desc, ctx.pack
         # d.min() (Shapelet.py:84) feeds reporting only; a gradient arriving there follows the hard argmin
         # and is not produced by any loss of the reference (experiment_classification.py:325-329).
         # (grads are not materialised, so None here means "unused" and costs no host sync.)
@@ -264,29 +325,11 @@ class _ShapeletTransform(torch.autograd.Function):
             raise NotImplementedError("ign_b200: gradient through the reported min distance is not implemented")
         if g_p is None:
             return (None,) * 9
-        g = g_p.to(torch.float32).contiguous()
-        dthr = None
-        if ctx.pool == "lts_min":
-            p = out[0]
-            sig = p * (1.0 - p)                         # d sigmoid(thr - min_d)
-            if ctx.needs_input_grad[1]:
-                dthr = (g * sig).sum(dim=0).reshape(ctx.thr_shape)
-            g = (-g * sig).contiguous()                 # dLoss/d(min_d)
-        dW = None
+        dW, dthr, call, _keep = _backward_group_args(ctx.rec, ctx.pack, ctx.saved_tensors, g_p, ctx.needs_input_grad[1])
         if ctx.needs_input_grad[0]:
-            st0, st1 = pack.window_stats(ctx.dist, desc.L, desc.stride)
-            if ctx.stored:
-                nbytes = C.lib.ign_shapelet_backward_workspace(byref(desc))
-            else:       # recompute mode: the library walks the shapelets in chunks inside this bounded workspace
-                nbytes = C.lib.ign_shapelet_backward_recompute_workspace(byref(desc), STORE_BUDGET_BYTES)
-            ws = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=g.device)
-            dW = torch.empty_like(Wc)
-            tag = "shapelet_bwd/%s/L%d" % (ctx.dist, desc.L)
-            STATS.note_engine(tag, desc, True)
-            with torch.cuda.device(g.device):
-                C.check(STATS.call(tag, 2, lambda: C.lib.ign_shapelet_backward(
-                    byref(desc), _ptr(pack.xn), _ptr(st0), _ptr(st1), _ptr(Wc), _ptr(thr), _ptr(g), _ptr(dstore),
-                    _ptr(out[1]), _ptr(idx), _ptr(dW), _ptr(ws), int(nbytes), _stream())), "ign_shapelet_backward")
+            call(C.BWD_PREPARE | C.BWD_CONTRACT)
+        else:
+            dW = None
         return dW, dthr, None, None, None, None, None, None, None
 
 
@@ -302,6 +345,84 @@ def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: 
     # autocast as well.
     with torch.autocast(device_type="cuda", enabled=False):
         return _ShapeletTransform.apply(W, threshold, pack, stride, eps, dist, pool, precision, track)
+
+
+class _SbmTransform(torch.autograd.Function):
+    """All length groups of a ShapeBottleneckModel as ONE autograd node (the python loop of Shapelet.py:191-194): same
+    kernels as _ShapeletTransform per group, but the backward sees every group's upstream gradient at once and can
+    pipeline the groups' preparation phases against the contractions (see OVERLAP_BWD_PREPARE)."""
+
+    @staticmethod
+    def forward(ctx, pack: SeriesPack, cfgs, track, *params):      # params = W_0, thr_0, W_1, thr_1, ...
+        recs, outs, saved_all = [], [], []
+        for gi, (stride, eps, dist, pool, precision) in enumerate(cfgs):
+            W, thr = params[2 * gi], params[2 * gi + 1]
+            need = bool(track and (ctx.needs_input_grad[3 + 2 * gi] or ctx.needs_input_grad[4 + 2 * gi]))
+            rec, o, saved = _forward_group(pack, W, thr, stride, eps, dist, pool, precision, need)
+            rec.needs = (need, bool(ctx.needs_input_grad[3 + 2 * gi]), bool(ctx.needs_input_grad[4 + 2 * gi]))
+            recs.append(rec); outs.extend(o); saved_all.extend(saved)
+        ctx.set_materialize_grads(False)
+        ctx.recs, ctx.pack = recs, pack
+        ctx.save_for_backward(*saved_all)
+        ctx.mark_non_differentiable(*outs[2::3])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        recs, pack = ctx.recs, ctx.pack
+        saved = ctx.saved_tensors
+        grads = [None] * (2 * len(recs))
+        jobs, keep, off = [], [], 0
+        for gi, rec in enumerate(recs):
+            sv = saved[off:off + rec.n_saved]
+            off += rec.n_saved
+            g_p, g_dmin = gs[3 * gi], gs[3 * gi + 1]
+            if g_dmin is not None:
+                raise NotImplementedError("ign_b200: gradient through the reported min distance is not implemented")
+            if g_p is None or not rec.needs[0]:
+                continue
+            dW, dthr, call, k = _backward_group_args(rec, pack, sv, g_p, rec.needs[2])
+            keep.append(k)
+            grads[2 * gi + 1] = dthr
+            if rec.needs[1]:
+                grads[2 * gi] = dW
+                jobs.append((rec, call))
+        split = OVERLAP_BWD_PREPARE and len(jobs) > 1 and all(rec.stored for rec, _ in jobs)
+        if not split:
+            for _, call in jobs:
+                call(C.BWD_PREPARE | C.BWD_CONTRACT)
+        else:
+            dev = pack.xn.device
+            cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(cur)                          # upstream gradients and workspaces are ready
+            events = []
+            with torch.cuda.stream(side):
+                for _, call in jobs:
+                    call(C.BWD_PREPARE)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+            for (_, call), ev in zip(jobs, events):
+                cur.wait_event(ev)                         # this group's coefficients (and tie flags) are written
+                call(C.BWD_CONTRACT)
+            # every side-stream kernel precedes one of the waits above: the main stream is ordered after all of them
+        return (None, None, None) + tuple(grads)
+
+
+def sbm_transform(pack: SeriesPack, layers):
+    """[(p, dmin, idx)] for the Shapelet layers of one bottleneck model, as one autograd node."""
+    cfgs, params = [], []
+    for layer in layers:
+        _require_cuda(layer.weights, "shapelet weights")
+        if pack.T < layer.length:   # what x.unfold raises in Shapelet.py:61
+            raise RuntimeError(f"maximum size for tensor at dimension 2 is {pack.T} but size is {layer.length}")
+        cfgs.append((layer.stride, layer.eps, layer._dist(), layer.pool, layer.precision))
+        params.extend((layer.weights, layer._threshold()))
+    _check_device(pack.xn.device)
+    track = torch.is_grad_enabled()
+    with torch.autocast(device_type="cuda", enabled=False):
+        outs = _SbmTransform.apply(pack, tuple(cfgs), track, *params)
+    return [(outs[3 * i], outs[3 * i + 1], outs[3 * i + 2]) for i in range(len(layers))]
 
 
 class _Diversity(torch.autograd.Function):

@@ -11,7 +11,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from layers.shapelet_ops import SeriesPack, instance_norm, resolve_dist, shapelet_diversity, shapelet_transform
+from layers.shapelet_ops import (SeriesPack, instance_norm, resolve_dist, sbm_transform, shapelet_diversity,
+                                 shapelet_transform)
 from utils.shapelet_util import ModelInfo
 
 
@@ -138,9 +139,8 @@ class ShapeBottleneckModel(nn.Module):
         first = self.shapelets[0]                           # norm terms of all length groups in one pass
         pack.prepare_stats(first._dist(), [(s.length, s.stride) for s in self.shapelets])
         probs, dists, idxs = [], [], []
-        for layer in self.shapelets:                        # Shapelet.py:191-194
-            p, d, idx = layer.transform(pack)
-            probs.append(p); dists.append(d); idxs.append(idx)
+        for p, d, idx in sbm_transform(pack, self.shapelets):   # Shapelet.py:191-194, all groups as one autograd node
+            probs.append(p.flatten(start_dim=1)); dists.append(d.flatten(start_dim=1)); idxs.append(idx)
         self.last_indices = idxs
         shapelet_probs = torch.cat(probs, dim=-1)
         shapelet_dists = torch.cat(dists, dim=-1)
