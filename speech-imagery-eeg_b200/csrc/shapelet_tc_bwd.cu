@@ -42,7 +42,6 @@ namespace {
 constexpr int kBRows = 128;            // UMMA M
 constexpr int kBKBlock = 32;           // window-group rows per stage (one 128-byte swizzle row of fp32)
 constexpr int kBProdWarps = 8, kBBuildWarps = 8, kBBuildGroups = 2;
-constexpr int kBGroupThreads = kBBuildWarps / kBBuildGroups * 32;   // 128 builder threads per stage
 constexpr int kBMmaWarp = kBProdWarps + kBBuildWarps, kBRowWarp = kBMmaWarp + 1;
 constexpr int kBThreads = (kBRowWarp + 1) * 32;
 constexpr int kBAStages = 4, kBBStages = 4;
@@ -244,7 +243,6 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
     const int bgrp = (warp - kBProdWarps) / (kBBuildWarps / kBBuildGroups);
     const int quad = (warp - kBProdWarps) % (kBBuildWarps / kBBuildGroups);
     static_assert(kBShifts / 4 == kBBuildWarps / kBBuildGroups || kBShifts == 8, "one quad of shifts per builder warp");
-    constexpr int QN = kBShifts / 4;                                  // quads per task: 4 (16 shifts) or 2 (8 shifts)
     // 8 shifts: two quads only, so warps (quad >> 1) split the shapelets instead: warp handles kl = (quad >> 1), +2, ..
     const int jq = kBShifts == 16 ? quad : (quad & 1);                // which quad of shifts
     const int kl0 = kBShifts == 16 ? 0 : (quad >> 1), klstep = kBShifts == 16 ? 1 : 2;

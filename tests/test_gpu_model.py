@@ -196,3 +196,27 @@ def test_full_size_model_matches_live_reference_golden(name, precision, rtol, at
                 assert int(bad.sum()) <= 0.01 * bad.numel(), tag + " sampled grad %s: %d outliers" % (k, int(bad.sum()))
             else:
                 assert_close(got, ref, 10 * gtol, gtol * float(ref.abs().max()), tag + " sampled grad " + k)
+
+
+def test_pipelined_backward_phases_give_identical_gradients(monkeypatch):
+    """ign_shapelet_backward_phases (PREPARE on a side stream, CONTRACT on the main stream, per-group events) is the same
+    arithmetic in a different launch order: bit-identical gradients, with and without the deep expert's side stream."""
+    from layers import shapelet_ops
+    model, g = build("model_small_chisco")
+    x, y = t(g["x"], DEV), torch.as_tensor(g["y"]).to(DEV)
+
+    def grads():
+        model.zero_grad(set_to_none=True)
+        logits, info = model(x, None, None, None)
+        (torch.nn.functional.cross_entropy(logits, y) + info.loss.mean()
+         + torch.nn.functional.cross_entropy(info.shapelet_preds, y)).backward()
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in model.sbm.parameters()]
+
+    base = grads()
+    monkeypatch.setattr(shapelet_ops, "OVERLAP_BWD_PREPARE", True)
+    piped = grads()
+    model.overlap_experts = False
+    serial = grads()
+    for a, b, c in zip(base, piped, serial):
+        assert torch.equal(a, b) and torch.equal(a, c)
