@@ -2,15 +2,14 @@
 //
 //   G[k,l] = sum_b sum_t a[b,k,t] * x[b,m,t+l]        (a = the per-window coefficients written by pool_bwd_kernel)
 //
-// is the transpose problem of the forward (shapelet_tc.cu).  With P shifts (template: 16 or 8), window t = P r + j:
+// is the transpose problem of the forward (shapelet_tc.cu).  With P = 16 shifts, window t = P r + j:
 //   Gsh[u,(k,j)] = sum_{(b,r)} x[b, P r + u] * a[b,k,P r + j],   u in [0, L+P-1),     G[k,l] = sum_j Gsh[l+j,(k,j)]
 // i.e. a GEMM with  M' = u (the TMEM lanes; up to 256/N' tiles of 128 per item),  N' = P K (padded to 16),  and the
 // contraction over the window-group rows (b, r) — the whole batch chunk accumulates into ONE resident set of
 // accumulators, so there is no epilogue per tile: only one small drain per (channel, shapelet block, batch chunk).
 // Longer shapelets split the lag axis into blocks of (128 MT - P) lags (the P extra lanes u feed the shift sum of the
 // block's last lags); each lag block is its own item with its own accumulators.
-// P = 16 halves the A' tiles, B' stages and MMA issue slots per sample (N' = 80 instead of 48 for K = 5) and is taken
-// whenever the shapelet fits ONE lag block that way (L + 15 <= 128 * (256 / N')); otherwise P = 8 (N' = 48, 4 tiles).
+// (P = 8 was the first version: twice the A' tiles, B' stages and MMA issue slots per sample at N' = 48 for K = 5.)
 //   A'[u][(b,r)]     = x[b, 8 r + u]   transposed Hankel rows: gathered by the producer warps (one LDS.32 per element,
 //                      conflict-free: consecutive lanes = consecutive u) straight into tensor memory (tcgen05.st), hi and
 //                      lo = x - trunc_tf32(x) columns, exactly as in the forward
@@ -102,7 +101,8 @@ __device__ __forceinline__ ItemCoord item_coord(const BwdTcGeo& g, int w) {
 
 // KQ: shapelets per block the builder threads hold in registers (5 covers the reference's default K = 5 without the
 // register pressure of the general 8)
-template <int kBShifts, int KQ>
+constexpr int kBShifts = 16;           // P
+template <int KQ>
 __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const BwdTcGeo g, const BwdTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -236,48 +236,54 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
     // Group `bgrp` (four warps) builds the tiles with (tile number & 1) == bgrp.  Work split inside a tile: thread
     // (quad = warp in group, r = lane) owns, for EVERY shapelet kl of the block, the four shifts j = 4 quad .. 4 quad + 3
     // of window group r — one 16-byte load and four (hi, lo) pairs of scattered 4-byte stores per shapelet, the same
-    // count for every thread (a (shapelet, window group) task per thread left a quarter of the threads with twice the
-    // work of the others at K = 5: 160 tasks on 128 threads).
+    // count for every thread.  All address arithmetic is hoisted: four swizzled row offsets per thread for the whole
+    // launch, one source pointer per tile (+ kl * Ts per shapelet), shapelet offsets as immediates — the first version
+    // recomputed them per element and spent ~490 instructions per warp and tile (ncu: 16 % of the builders' samples
+    // issuing, 39 % in fixed-latency dependencies), which made the builders, not the tensor pipe, pace L <= 200.
     // The coefficients stream from HBM: the loads of the group's next tile are in flight (registers) while the current
     // one is written, and the tile after that is pulled into L2 (prefetch.global.L2) at the same time.
+    static_assert(kBShifts == 16 && kBBuildWarps / kBBuildGroups == 4, "one quad of the 16 shifts per builder warp");
     const int bgrp = (warp - kBProdWarps) / (kBBuildWarps / kBBuildGroups);
-    const int quad = (warp - kBProdWarps) % (kBBuildWarps / kBBuildGroups);
-    static_assert(kBShifts / 4 == kBBuildWarps / kBBuildGroups || kBShifts == 8, "one quad of shifts per builder warp");
-    // 8 shifts: two quads only, so warps (quad >> 1) split the shapelets instead: warp handles kl = (quad >> 1), +2, ..
-    const int jq = kBShifts == 16 ? quad : (quad & 1);                // which quad of shifts
-    const int kl0 = kBShifts == 16 ? 0 : (quad >> 1), klstep = kBShifts == 16 ? 1 : 2;
-    struct Cursor { int cw, cb, cb1, ckb, m, kblk; };
-    Cursor cur{wbeg, 0, 0, 0, 0, 0};
+    const int jq = (warp - kBProdWarps) % (kBBuildWarps / kBBuildGroups);   // which quad of shifts
+    uint32_t rowoff[4];                                              // byte offset of (row 4 jq + jj, column lane) in a stage image
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) rowoff[jj] = sw128_off(4 * jq + jj, lane >> 2) + (uint32_t)((lane & 3) * 4);
+    struct Cursor { int cw, cb, cb1, ckb, kvalid; const float* base; };   // base: coefficient row of (cb, m, first shapelet)
+    Cursor cur{wbeg, 0, 0, 0, 0, nullptr};
     auto enter_item = [&](Cursor& c) {
       if (c.cw < wend) {
         const ItemCoord ic = item_coord(g, c.cw);
-        c.cb = ic.chunk * kBChunk; c.cb1 = min(g.B, c.cb + kBChunk); c.ckb = 0; c.m = ic.m; c.kblk = ic.kblk;
+        c.cb = ic.chunk * kBChunk; c.cb1 = min(g.B, c.cb + kBChunk); c.ckb = 0;
+        c.kvalid = min(g.KG, g.K - ic.kblk * g.KG);
+        c.base = a.coef + (((size_t)c.cb * g.M + ic.m) * g.K + (size_t)ic.kblk * g.KG) * g.Ts;
       }
     };
+    const size_t sample_pitch = (size_t)g.M * g.K * g.Ts;            // coefficient rows of the next sample, same (m, k)
     auto advance1 = [&](Cursor& c) {
       if (c.cw >= wend) return;
-      if (++c.ckb == g.NKB) { c.ckb = 0; if (++c.cb == c.cb1) { ++c.cw; enter_item(c); } }
+      if (++c.ckb == g.NKB) {
+        c.ckb = 0;
+        if (++c.cb == c.cb1) { ++c.cw; enter_item(c); } else c.base += sample_pitch;
+      }
     };
-    auto src_of = [&](const Cursor& c, int kl) -> const float* {     // nullptr: nothing to load (past the end / pad shapelet / pad windows)
-      const int k = c.kblk * g.KG + kl;
+    // this thread's source of shapelet 0 in the cursor's tile, or nullptr (past the end / pad windows)
+    auto src_of = [&](const Cursor& c) -> const float* {
       const int t = kBShifts * (kBKBlock * c.ckb + lane) + 4 * jq;
-      if (c.cw >= wend || k >= g.K || t >= g.Ts) return nullptr;
-      return a.coef + (((size_t)c.cb * g.M + c.m) * g.K + k) * g.Ts + t;
+      return (c.cw < wend && t < g.Ts) ? c.base + t : nullptr;
     };
     auto fetch = [&](const Cursor& c, float4 (&v)[KQ]) {
+      const float* src = src_of(c);
 #pragma unroll
       for (int q = 0; q < KQ; ++q) {
         v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int kl = kl0 + q * klstep;
-        if (kl < g.KG) { const float* src = src_of(c, kl); if (src) v[q] = __ldg(reinterpret_cast<const float4*>(src)); }
+        if (src && q < c.kvalid) v[q] = __ldg(reinterpret_cast<const float4*>(src + (size_t)q * g.Ts));
       }
     };
     auto prefetch_l2 = [&](const Cursor& c) {
+      const float* src = src_of(c);
 #pragma unroll
-      for (int q = 0; q < KQ; ++q) {
-        const int kl = kl0 + q * klstep;
-        if (kl < g.KG) { const float* src = src_of(c, kl); if (src) asm volatile("prefetch.global.L2 [%0];" ::"l"(src)); }
-      }
+      for (int q = 0; q < KQ; ++q)
+        if (src && q < c.kvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)q * g.Ts));
     };
     enter_item(cur);
     long long total = 0;                                             // tiles this CTA builds
@@ -292,19 +298,17 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
       long long t0 = BP_CLK();
       mbar_wait(&emptyB[sb], phb ^ 1);
       BP_ADD(2, t0);
-      uint8_t* st = stage0 + (size_t)sb * stage_bytes;
-      const uint32_t colb = (uint32_t)((lane & 3) * 4);
+      uint8_t* hi = stage0 + (size_t)sb * stage_bytes;
+      uint8_t* lo = hi + b_bytes;
 #pragma unroll
-      for (int q = 0; q < KQ; ++q) {
-        const int kl = kl0 + q * klstep;
-        if (kl >= g.KG) continue;
+      for (int q = 0; q < KQ; ++q) {                                 // pad shapelets (q >= KG) are never read back: rows of N'
+        if (q >= g.KG) break;                                        // beyond 16 KG do not exist
         const float vv[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const int n = kl * kBShifts + 4 * jq + jj;
-          const uint32_t off = sw128_off(n, lane >> 2) + colb;
-          *reinterpret_cast<float*>(st + off) = vv[jj];
-          if (g.split) *reinterpret_cast<float*>(st + b_bytes + off) = vv[jj] - __uint_as_float(__float_as_uint(vv[jj]) & 0xffffe000u);
+          const uint32_t off = rowoff[jj] + (uint32_t)(q * kBShifts * 128);   // row kl * 16 + 4 jq + jj: (n & 7) does not depend on kl
+          *reinterpret_cast<float*>(hi + off) = vv[jj];
+          if (g.split) *reinterpret_cast<float*>(lo + off) = vv[jj] - __uint_as_float(__float_as_uint(vv[jj]) & 0xffffe000u);
         }
       }
       fence_proxy_async_smem();                                      // generic-proxy writes -> visible to the MMA's async proxy
@@ -423,12 +427,10 @@ void bwd_tc_geo(const ign_shapelet_desc& d, BwdTcGeo& g) {
   g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb);
   // 16 shifts when the whole shapelet then fits one lag block (half the A' tiles, B' stages and MMA issue slots per
   // sample), else 8 shifts with up to four 128-lane tiles per block
-  g.P = 16;
-  g.N = 16 * g.KG;
-  // (measured at config 2, K = 5: L = 500 as two lag blocks of 16 shifts needs 10 A' tiles per sample, as one block of
-  //  8 shifts 16 — the A' producers pace that case; 8 shifts remain as the fallback for N' > 256, which K <= 8 per block
-  //  never reaches)
-  if (g.N > kBACol0) { g.P = 8; g.N = round_up(8 * g.KG, 16); }
+  // (an 8-shift variant, N' = 48 with four 128-lane tiles per block, was the first version: at config 2, K = 5 it needs
+  //  16 A' tiles per sample at L = 500 against 10 with two lag blocks of 16 shifts, and twice the stages everywhere)
+  g.P = kBShifts;
+  g.N = kBShifts * g.KG;                                             // <= 128: at least two accumulator tiles
   const int mtmax = max(1, min(kBMaxMT, kBACol0 / g.N));
   g.RI = ceil_div(g.Tw, g.P); g.NKB = ceil_div(g.RI, kBKBlock);
   g.lagstep = mtmax * kBRows - g.P;
@@ -479,8 +481,7 @@ int launch_shapelet_bwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   BwdTcGeo g;
   bwd_tc_geo(d, g);
   const size_t smem = max(bwd_tc_smem(g), (size_t)118 * 1024);       // > half the SM: one CTA per SM (it owns all of TMEM)
-  auto kern = g.P == 16 ? (g.KG <= 5 ? shapelet_bwd_tc_kernel<16, 5> : shapelet_bwd_tc_kernel<16, 8>)
-                        : shapelet_bwd_tc_kernel<8, 8>;
+  auto kern = g.KG <= 5 ? shapelet_bwd_tc_kernel<5> : shapelet_bwd_tc_kernel<8>;
   IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BwdTcArgs a{xn, coef, part};
   const int grid = min(sm_count(), g.nitems);
