@@ -17,13 +17,16 @@
 //                      128B-swizzled K-major stage image (hi | lo), then fence.proxy.async
 // Precision modes as in the forward: 3xTF32 (lo*hi + hi*lo + hi*hi) or single-pass TF32.
 //
-// Roles (448 threads, one persistent CTA per SM walking a contiguous range of (channel, shapelet block, chunk) items):
-//   warps 0-7   A' producers (two per TMEM lane quarter, alternating stages); warps 0-3 also drain the accumulators
-//   warps 8-15  B' builders: two groups of four warps that build ALTERNATE stages — a stage is a short latency chain
+// Roles (704 threads, one persistent CTA per SM walking a contiguous range of (channel, shapelet block, chunk) items):
+//   warps 0-11  A' producers: three groups of four warps (one warp per TMEM lane quarter), group g takes the stages
+//               with (stage number % 3) == g — a stage is a latency chain (32 gathers, split, two tcgen05.st, wait::st,
+//               arrive: ~1600 cycles for ~110 instructions), so three of them are kept in flight; warps 0-3 also drain
+//               the accumulators
+//   warps 12-19 B' builders: two groups of four warps that build ALTERNATE stages — a stage is a short latency chain
 //               (wait for the slot, 16-32 scattered stores, proxy fence, arrive), so two of them have to be in flight for
 //               the MMA thread not to wait for B' (it waited 45 % of the time at L = 100 with all eight warps on one stage)
-//   warp 12     one elected thread issues tcgen05.mma / tcgen05.commit
-//   warp 17     series-row loader: one elected thread streams the rows with 1-D bulk TMA copies into a ring of four
+//   warp 20     one elected thread issues tcgen05.mma / tcgen05.commit
+//   warp 21     series-row loader: one elected thread streams the rows with 1-D bulk TMA copies into a ring of four
 //               row buffers (completion counted on the row's mbarrier), so the DRAM latency of up to three rows is in
 //               flight while one is consumed (a cp.async + wait per row exposed ~1 us per sample: more than the 960 MMA
 //               cycles a sample needs at L = 100)
@@ -40,7 +43,11 @@ namespace {
 
 constexpr int kBRows = 128;            // UMMA M
 constexpr int kBKBlock = 32;           // window-group rows per stage (one 128-byte swizzle row of fp32)
-constexpr int kBProdWarps = 8, kBBuildWarps = 8, kBBuildGroups = 2;
+#ifndef IGN_BWD_PROD_GROUPS
+#define IGN_BWD_PROD_GROUPS 3
+#endif
+constexpr int kBProdGroups = IGN_BWD_PROD_GROUPS;                   // A' stages in production at once
+constexpr int kBProdWarps = 4 * kBProdGroups, kBBuildWarps = 8, kBBuildGroups = 2;
 constexpr int kBMmaWarp = kBProdWarps + kBBuildWarps, kBRowWarp = kBMmaWarp + 1;
 constexpr int kBThreads = (kBRowWarp + 1) * 32;
 constexpr int kBAStages = 4, kBBStages = 4;
@@ -167,22 +174,28 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
             const int s = sidx;
             const uint32_t ph = sph;
             if (++sidx == kBAStages) { sidx = 0; sph ^= 1; }
-            if ((int)(ia & 1) != grp) continue;
+            if ((int)(ia % kBProdGroups) != grp) continue;
             // this lane's row of A': x[P (32 kb + c) + 128 mt + up], c = 0..31 (zero beyond the series)
             const float* src = xs + kBShifts * (kBKBlock * kb) + kBRows * mt + up + ic.lb * g.lagstep;
-            uint32_t hi[32], lo[32];
+            float xv[32];                                            // the gather does not depend on the stage being free
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float v = src[kBShifts * c];
-              hi[c] = __float_as_uint(v);
-              lo[c] = __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u));
-            }
+            for (int c = 0; c < 32; ++c) xv[c] = src[kBShifts * c];
             t0 = BP_CLK();
             mbar_wait(&emptyA[s], ph ^ 1);
             BP_ADD(1, t0);
             tc_fence_after();
-            tmem_st32(a_lane + s * kBAStageCols, hi);
-            if (g.split) tmem_st32(a_lane + s * kBAStageCols + 32, lo);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                            // two halves of 16 columns: 64 live registers, not 96
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float v = xv[16 * h + c];
+                hi[c] = __float_as_uint(v);
+                lo[c] = __float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u));
+              }
+              tmem_st16(a_lane + s * kBAStageCols + 16 * h, hi);
+              if (g.split) tmem_st16(a_lane + s * kBAStageCols + 32 + 16 * h, lo);
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -319,20 +332,32 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
     };
     if (todo > 0) {
       if (bgrp) advance1(cur);                                       // group 1 starts at tile 1
-      float4 va[KQ], vb[KQ];
-      fetch(cur, va);
-      advance1(cur); advance1(cur);
-      while (true) {
-        fetch(cur, vb);                                              // the group's next tile -> registers
-        { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }   // the one after -> L2
-        emit(va);
-        if (--todo == 0) break;
-        advance1(cur); advance1(cur);
+      if constexpr (KQ <= 5) {
+        float4 va[KQ], vb[KQ];
         fetch(cur, va);
-        { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }
-        emit(vb);
-        if (--todo == 0) break;
         advance1(cur); advance1(cur);
+        while (true) {
+          fetch(cur, vb);                                            // the group's next tile -> registers
+          { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }   // the one after -> L2
+          emit(va);
+          if (--todo == 0) break;
+          advance1(cur); advance1(cur);
+          fetch(cur, va);
+          { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }
+          emit(vb);
+          if (--todo == 0) break;
+          advance1(cur); advance1(cur);
+        }
+      } else {                                                       // 6..8 shapelets per block: one register set (80 registers per
+        float4 va[KQ];                                               // thread), the next two tiles are pulled into L2 instead
+        { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }
+        while (true) {
+          fetch(cur, va);
+          advance1(cur); advance1(cur);
+          { Cursor nx = cur; advance1(nx); advance1(nx); prefetch_l2(nx); }
+          emit(va);
+          if (--todo == 0) break;
+        }
       }
     }
   } else if (warp == kBMmaWarp) {
