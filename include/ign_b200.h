@@ -199,6 +199,17 @@ int32_t ign_shapelet_backward_phases(const ign_shapelet_desc* desc, const float*
                                      const int32_t* argmin_dev, float* dW_dev, void* workspace_dev,
                                      size_t workspace_bytes, int32_t phases, void* stream);
 
+/* Gradient w.r.t. the normalised input series — what autograd gives a user of the reference who asks for input
+ * gradients (saliency, gradcheck) through Shapelet.forward; the training loop never does
+ * (experiment_classification.py:315).  Call AFTER ign_shapelet_backward (or its PREPARE phase) of the same group with
+ * the same workspace: it reads the per-window coefficients that call left there.
+ *   dxn_dev [B,M,Tp] += sum_k sum_t dLoss/dd[b,k,t] * d d_t / d xn[b,m,t*stride + l]     (ADDED: zero it once, call per group)
+ * L1 (Shapelet.py:74, sign(0) = 0), cosine (:64-66), pearson (:11-19,:67-69).  SQL2: nothing is added — the
+ * reference's ShapeletDistanceFunc.backward returns zeros for its input (Shapelet.py:40).  Stored-distance mode only. */
+int32_t ign_shapelet_backward_input(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,
+                                    const float* st1_dev, const float* W_dev, const float* dstore_dev, float* dxn_dev,
+                                    const void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* InterpGN gate + mixture (InterpGN.py:44-52): q=softmax(s), eta=(C*sum q^2-1)/(C-1),
  * if use_gate: eta=1 where eta>gating_value; out=eta*s+(1-eta)*z.  s,z,out [B,C]; eta [B]. */
 int32_t ign_gate_forward(const float* sbm_out_dev, const float* deep_out_dev, float* out_dev,

@@ -213,6 +213,21 @@ int32_t ign_shapelet_backward_phases(const ign_shapelet_desc* d, const float* xn
                                   (cudaStream_t)stream);
 }
 
+int32_t ign_shapelet_backward_input(const ign_shapelet_desc* d, const float* xn, const float* st0, const float* st1,
+                                    const float* W, const float* dstore, float* dxn, const void* ws, size_t ws_bytes,
+                                    void* stream) {
+  int rc = check_desc(d, "shapelet_backward_input");
+  if (rc) return rc;
+  IGN_REQUIRE(xn && W && dxn && ws, "shapelet_backward_input: null pointer");
+  IGN_REQUIRE(dstore, "shapelet_backward_input: stored-distance mode only (dstore from the forward is required)");
+  IGN_REQUIRE(d->dist < IGN_DIST_COSINE || st0, "shapelet_backward_input: dist %d needs the window statistics", d->dist);
+  IGN_REQUIRE(d->dist != IGN_DIST_PEARSON || st1, "shapelet_backward_input: PEARSON needs st1 (window means)");
+  size_t off = 0, total = 0;
+  if (!shapelet_bwd_coef_offset(*d, &off, &total)) { set_error("shapelet_backward_input: T=%d < L=%d or the problem does not fit shared memory", d->T, d->L); return IGN_ERR_INVALID; }
+  IGN_REQUIRE(ws_bytes >= total, "shapelet_backward_input: workspace %zu < %zu bytes (pass the workspace ign_shapelet_backward used)", ws_bytes, total);
+  return launch_shapelet_dx(*d, xn, st0, st1, W, reinterpret_cast<const float*>(ws) + off, dstore, dxn, (cudaStream_t)stream);
+}
+
 int32_t ign_diversity_partials(int32_t K) { return K <= 0 ? 0 : diversity_blocks(K) * diversity_blocks(K); }
 
 int32_t ign_diversity_forward(const float* W, float* coef, float* partial, int32_t K, int32_t M, int32_t L, void* stream) {

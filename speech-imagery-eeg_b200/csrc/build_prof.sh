@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")"
 mkdir -p build_prof ../lib
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-for f in api instnorm shapelet_simt shapelet_tc shapelet_tc_bwd gate regulariser; do
+for f in api instnorm shapelet_simt shapelet_dx shapelet_tc shapelet_tc_bwd gate regulariser; do
   $NVCC -O3 -std=c++17 -lineinfo -DIGN_TC_PROFILE -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -c $f.cu -o build_prof/$f.o &
 done
 wait

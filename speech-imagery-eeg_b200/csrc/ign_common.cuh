@@ -58,6 +58,9 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
                              const float* st1, const float* W, const float* g, int gK, int gk0, const float* dstore,
                              const float* dmin, const int* argmin, float* dW, void* ws, size_t ws_bytes,
                              int phases, cudaStream_t st);
+bool shapelet_bwd_coef_offset(const ign_shapelet_desc& d, size_t* off_floats, size_t* total_bytes);
+int launch_shapelet_dx(const ign_shapelet_desc& d, const float* xn, const float* st0, const float* st1, const float* W,
+                       const float* coef, const float* dstore, float* dxn, cudaStream_t st);
 size_t shapelet_bwd_recompute_workspace(const ign_shapelet_desc& d, size_t budget);
 int launch_shapelet_bwd_recompute(const ign_shapelet_desc& d, const float* xn, const float* st0, const float* st1,
                                   const float* W, const float* thr, const float* g, float* dW, void* ws,

@@ -1356,6 +1356,15 @@ BwdWorkspace bwd_workspace(const ign_shapelet_desc& d, const Geo& g, const BwdPl
   return w;
 }
 
+// where the pooling backward leaves the per-window coefficients inside the workspace (floats from its start)
+bool shapelet_bwd_coef_offset(const ign_shapelet_desc& d, size_t* off_floats, size_t* total_bytes) {
+  Geo g; BwdPlan bp;
+  if (!base_geo(d, g) || !plan_bwd(g, bp)) return false;
+  const BwdWorkspace w = bwd_workspace(d, g, bp);
+  *off_floats = w.coef; *total_bytes = w.total * sizeof(float);
+  return true;
+}
+
 size_t shapelet_bwd_workspace_simt(const ign_shapelet_desc& d) {
   Geo g; BwdPlan bp;
   if (!base_geo(d, g) || !plan_bwd(g, bp)) return 0;

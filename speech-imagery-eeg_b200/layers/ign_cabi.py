@@ -57,6 +57,7 @@ _SIGNATURES = {
     "ign_shapelet_backward_recompute_workspace": (c_size_t, [POINTER(ShapeletDesc), c_size_t]),
     "ign_shapelet_backward": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 11 + [c_size_t, _P]),
     "ign_shapelet_backward_phases": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 11 + [c_size_t, c_int32, _P]),
+    "ign_shapelet_backward_input": (c_int32, [POINTER(ShapeletDesc)] + [_P] * 7 + [c_size_t, _P]),
     "ign_diversity_partials": (c_int32, [c_int32]),
     "ign_diversity_forward": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
     "ign_diversity_backward": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),

@@ -106,8 +106,9 @@ class SeriesPack:
     """Instance-normalised series in the kernels' layout: xn [B,M,Tp] fp32 (time contiguous, zero padded
     to a multiple of 4) plus lazily built fp64 window prefix sums shared by all length groups."""
 
-    def __init__(self, xn: torch.Tensor, T: int):
-        self.xn = xn
+    def __init__(self, xn: torch.Tensor, T: int, xn_var: Optional[torch.Tensor] = None):
+        self.xn = xn               # the kernels' buffer (never tracked by autograd)
+        self.xn_var = xn_var       # the same values as an autograd variable when the caller wants dLoss/dx, else None
         self.T = T
         self._pre = None
         self._stats = {}
@@ -177,6 +178,11 @@ class SeriesPack:
         _require_cuda(x, "x")
         B, M, T = x.shape
         Tp = C.padded_len(T)
+        if x.requires_grad and torch.is_grad_enabled():      # input gradients wanted: keep a differentiable view
+            var = torch.nn.functional.pad(x.to(torch.float32), (0, Tp - T)).contiguous()
+            if var is x:
+                var = x.view_as(x)
+            return SeriesPack(var.detach(), T, xn_var=var)
         xn = x.detach().to(torch.float32)
         if Tp != T or not xn.is_contiguous():
             buf = torch.zeros((B, M, Tp), dtype=torch.float32, device=x.device)
@@ -185,15 +191,50 @@ class SeriesPack:
         return SeriesPack(xn, T)
 
 
+class _InstanceNorm(torch.autograd.Function):
+    """Instance norm with a gradient, for callers that ask for dLoss/dx (saliency, gradcheck).  The training loop never
+    does (experiment_classification.py:315) and takes the plain path of instance_norm() below."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = x.detach().to(torch.float32).contiguous()
+        B, T, M = xc.shape
+        xn = torch.empty((B, M, C.padded_len(T)), dtype=torch.float32, device=xc.device)
+        stat = torch.empty((2, B, M), dtype=torch.float32, device=xc.device)      # mean, 1 / (std + 1e-8)
+        with torch.cuda.device(xc.device):
+            C.check(STATS.call("instnorm", 1, lambda: C.lib.ign_instnorm_forward(
+                _ptr(xc), _ptr(xn), _ptr(stat[0]), _ptr(stat[1]), B, T, M, _stream())), "ign_instnorm_forward")
+        ctx.save_for_backward(xn, stat)
+        ctx.T = T
+        ctx.in_dtype = x.dtype
+        return xn
+
+    @staticmethod
+    def backward(ctx, g):
+        xn, stat = ctx.saved_tensors
+        T = ctx.T
+        # xn = (x - mu) r,  r = 1 / (sigma + 1e-8),  sigma = unbiased std over T   (Shapelet.py:187)
+        # dx_j = r (g_j - mean g) - xn_j * sum_i(g_i xn_i) / ((T - 1) sigma)
+        g = g[:, :, :T].to(torch.float32)
+        z = xn[:, :, :T]
+        r = stat[1].unsqueeze(-1)
+        sigma = 1.0 / r - 1e-8
+        dx = r * (g - g.mean(dim=-1, keepdim=True)) - z * (g * z).sum(dim=-1, keepdim=True) / ((T - 1) * sigma)
+        return dx.transpose(1, 2).contiguous().to(ctx.in_dtype)
+
+
 def instance_norm(x: torch.Tensor) -> SeriesPack:
-    """x [B,T,M] -> SeriesPack(xn [B,M,Tp]).  Shapelet.py:186-187.  No gradient w.r.t. x is produced:
-    in the reference's training loop the raw batch never requires grad (experiment_classification.py:315)."""
+    """x [B,T,M] -> SeriesPack(xn [B,M,Tp]).  Shapelet.py:186-187.  In the reference's training loop the raw batch never
+    requires grad (experiment_classification.py:315); when it does (saliency), the pack carries an autograd variable
+    and the shapelet transform returns dLoss/dxn through ign_shapelet_backward_input."""
     _require_cuda(x, "x")
     if x.dim() != 3:
         raise RuntimeError("instance_norm expects [B,T,M], got %s" % (tuple(x.shape),))
-    if x.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError("ign_b200: gradient w.r.t. the input series is not implemented")
     _check_device(x.device)
+    if x.requires_grad and torch.is_grad_enabled():
+        with torch.autocast(device_type="cuda", enabled=False):
+            var = _InstanceNorm.apply(x)
+        return SeriesPack(var.detach(), x.shape[1], xn_var=var)
     x = x.detach().to(torch.float32).contiguous()
     B, T, M = x.shape
     xn = torch.empty((B, M, C.padded_len(T)), dtype=torch.float32, device=x.device)
@@ -223,7 +264,7 @@ def _side_stream(device):
 
 class _Group:
     """One length group's forward state (what the backward needs)."""
-    __slots__ = ("desc", "dist", "pool", "stored", "thr_shape", "n_saved", "needs")
+    __slots__ = ("desc", "dist", "pool", "stored", "thr_shape", "n_saved", "needs")   # needs: (any, W, threshold)
 
 
 def _forward_group(pack: SeriesPack, W, threshold, stride, eps, dist, pool, precision, need_grad):
@@ -296,41 +337,12 @@ def _backward_group_args(rec: _Group, pack: SeriesPack, saved, g_p, need_dthr):
                 C.check(launch(), "ign_shapelet_backward_phases")
             else:
                 C.check(STATS.call(tag, 2, launch), "ign_shapelet_backward")
-    return dW, dthr, call, (g, ws, st0, st1)
-
-
-class _ShapeletTransform(torch.autograd.Function):
-    """One length group: window distance + pooling over time, with the saved-statistics backward."""
-
-    @staticmethod
-    def forward(ctx, W, threshold, pack: SeriesPack, stride, eps, dist, pool, precision, track):
-        # Grad mode is always off inside Function.forward and needs_input_grad mirrors requires_grad even under
-        # torch.no_grad(), so the caller's grad mode is passed in: evaluation loops must not pay for the 1.9 GB of
-        # saved window distances.
-        need_grad = bool(track and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]))
-        rec, outs, saved = _forward_group(pack, W, threshold, stride, eps, dist, pool, precision, need_grad)
-        ctx.set_materialize_grads(False)
-        ctx.rec, ctx.pack = rec, pack
-        if need_grad:
-            ctx.save_for_backward(*saved)
-        ctx.mark_non_differentiable(outs[2])
-        return outs
-
-    @staticmethod
-    def backward(ctx, g_p, g_dmin, _g_idx):
-        # d.min() (Shapelet.py:84) feeds reporting only; a gradient arriving there follows the hard argmin
-        # and is not produced by any loss of the reference (experiment_classification.py:325-329).
-        # (grads are not materialised, so None here means "unused" and costs no host sync.)
-        if g_dmin is not None:
-            raise NotImplementedError("ign_b200: gradient through the reported min distance is not implemented")
-        if g_p is None:
-            return (None,) * 9
-        dW, dthr, call, _keep = _backward_group_args(ctx.rec, ctx.pack, ctx.saved_tensors, g_p, ctx.needs_input_grad[1])
-        if ctx.needs_input_grad[0]:
-            call(C.BWD_PREPARE | C.BWD_CONTRACT)
-        else:
-            dW = None
-        return dW, dthr, None, None, None, None, None, None, None
+    def call_dx(dxn):      # after call(PREPARE): adds this group's dLoss/dxn (ign_shapelet_backward_input)
+        with torch.cuda.device(g.device):
+            C.check(STATS.call("shapelet_bwd_input/%s/L%d" % (rec.dist, desc.L), 1, lambda: C.lib.ign_shapelet_backward_input(
+                byref(desc), _ptr(pack.xn), _ptr(st0), _ptr(st1), _ptr(Wc), _ptr(dstore), _ptr(dxn), _ptr(ws),
+                int(nbytes), _stream())), "ign_shapelet_backward_input")
+    return dW, dthr, call, (g, ws, st0, st1), call_dx
 
 
 def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: float = 1.0, dist: str = "l1",
@@ -344,7 +356,8 @@ def shapelet_transform(pack: SeriesPack, W: torch.Tensor, stride: int = 1, eps: 
     # fp32 in / fp32 out regardless of autocast: the reference's distance math stays fp32 under bf16
     # autocast as well.
     with torch.autocast(device_type="cuda", enabled=False):
-        return _ShapeletTransform.apply(W, threshold, pack, stride, eps, dist, pool, precision, track)
+        outs = _SbmTransform.apply(pack, ((stride, eps, dist, pool, precision),), track, pack.xn_var, W, threshold)
+    return outs[0], outs[1], outs[2]
 
 
 class _SbmTransform(torch.autograd.Function):
@@ -353,16 +366,25 @@ class _SbmTransform(torch.autograd.Function):
     pipeline the groups' preparation phases against the contractions (see OVERLAP_BWD_PREPARE)."""
 
     @staticmethod
-    def forward(ctx, pack: SeriesPack, cfgs, track, *params):      # params = W_0, thr_0, W_1, thr_1, ...
+    def forward(ctx, pack: SeriesPack, cfgs, track, xn_var, *params):      # params = W_0, thr_0, W_1, thr_1, ...
+        # Grad mode is always off inside Function.forward and needs_input_grad mirrors requires_grad even under
+        # torch.no_grad(), so the caller's grad mode is passed in: evaluation loops must not pay for the 1.9 GB of
+        # saved window distances.
+        need_dx = bool(track and xn_var is not None and ctx.needs_input_grad[3])
         recs, outs, saved_all = [], [], []
         for gi, (stride, eps, dist, pool, precision) in enumerate(cfgs):
             W, thr = params[2 * gi], params[2 * gi + 1]
-            need = bool(track and (ctx.needs_input_grad[3 + 2 * gi] or ctx.needs_input_grad[4 + 2 * gi]))
+            nW, nT = bool(ctx.needs_input_grad[4 + 2 * gi]), bool(ctx.needs_input_grad[5 + 2 * gi])
+            need = bool(track and (nW or nT or need_dx))
             rec, o, saved = _forward_group(pack, W, thr, stride, eps, dist, pool, precision, need)
-            rec.needs = (need, bool(ctx.needs_input_grad[3 + 2 * gi]), bool(ctx.needs_input_grad[4 + 2 * gi]))
+            rec.needs = (need, nW, nT)
+            if need_dx and need and not rec.stored:
+                raise NotImplementedError("ign_b200: the input gradient needs the stored-distance backward; raise "
+                                          "IGN_BWD_STORE_BUDGET_GB (this group would keep %d bytes)" % (
+                                              2 * int(C.lib.ign_shapelet_dstore_bytes(byref(rec.desc)))))
             recs.append(rec); outs.extend(o); saved_all.extend(saved)
         ctx.set_materialize_grads(False)
-        ctx.recs, ctx.pack = recs, pack
+        ctx.recs, ctx.pack, ctx.need_dx = recs, pack, need_dx
         ctx.save_for_backward(*saved_all)
         ctx.mark_non_differentiable(*outs[2::3])
         return tuple(outs)
@@ -381,12 +403,21 @@ class _SbmTransform(torch.autograd.Function):
                 raise NotImplementedError("ign_b200: gradient through the reported min distance is not implemented")
             if g_p is None or not rec.needs[0]:
                 continue
-            dW, dthr, call, k = _backward_group_args(rec, pack, sv, g_p, rec.needs[2])
+            dW, dthr, call, k, call_dx = _backward_group_args(rec, pack, sv, g_p, rec.needs[2])
             keep.append(k)
             grads[2 * gi + 1] = dthr
             if rec.needs[1]:
                 grads[2 * gi] = dW
-                jobs.append((rec, call))
+            if rec.needs[1] or ctx.need_dx:
+                jobs.append((rec, call, call_dx, rec.needs[1]))
+        dxn = None
+        if ctx.need_dx:          # input gradients (saliency): per group the pooling backward, then dLoss/dxn from its coefficients
+            dxn = torch.zeros_like(pack.xn)
+            for rec, call, call_dx, want_w in jobs:
+                call((C.BWD_PREPARE | C.BWD_CONTRACT) if want_w else C.BWD_PREPARE)
+                call_dx(dxn)
+            return (None, None, None, dxn) + tuple(grads)
+        jobs = [(rec, call) for rec, call, _, _ in jobs]
         split = OVERLAP_BWD_PREPARE and len(jobs) > 1 and all(rec.stored for rec, _ in jobs)
         if not split:
             for _, call in jobs:
@@ -406,7 +437,7 @@ class _SbmTransform(torch.autograd.Function):
                 cur.wait_event(ev)                         # this group's coefficients (and tie flags) are written
                 call(C.BWD_CONTRACT)
             # every side-stream kernel precedes one of the waits above: the main stream is ordered after all of them
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 def sbm_transform(pack: SeriesPack, layers):
@@ -421,7 +452,7 @@ def sbm_transform(pack: SeriesPack, layers):
     _check_device(pack.xn.device)
     track = torch.is_grad_enabled()
     with torch.autocast(device_type="cuda", enabled=False):
-        outs = _SbmTransform.apply(pack, tuple(cfgs), track, *params)
+        outs = _SbmTransform.apply(pack, tuple(cfgs), track, pack.xn_var, *params)
     return [(outs[3 * i], outs[3 * i + 1], outs[3 * i + 2]) for i in range(len(layers))]
 
 

@@ -505,3 +505,50 @@ def test_engine_report_matches_what_runs():
     assert e["shapelet_fwd/cosine/L50"] == "tcgen05" and e["shapelet_bwd/cosine/L50"] == "tcgen05"
     assert e["shapelet_fwd/l1/L50"] == "fp32" and e["shapelet_bwd/l1/L50"] == "fp32"
     assert e["shapelet_fwd/cosine/L60"] == "fp32"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Input gradients (saliency / gradcheck): what autograd gives the reference's user for L1 / cosine / pearson
+# (Shapelet.py:64-74); the memory_efficient squared-L2 Function returns zeros for its input (Shapelet.py:40).
+# ---------------------------------------------------------------------------------------------------------------------
+DX_SHAPES = [(3, 4, 64, 5, 9, 1), (2, 3, 200, 10, 37, 1), (2, 2, 96, 3, 96, 1), (2, 3, 400, 4, 50, 3),
+             (2, 2, 1000, 5, 300, 1), (1, 2, 17, 1, 3, 1)]
+
+
+@pytest.mark.parametrize("flag,pool", [("euclidean", "rbf_max"), ("cosine", "rbf_max"), ("pearson", "rbf_max"),
+                                       ("euclidean", "lts_min")])
+@pytest.mark.parametrize("shape", DX_SHAPES)
+def test_input_gradient_vs_oracle_autograd(flag, pool, shape):
+    from layers.shapelet_ops import SeriesPack, shapelet_transform
+    B, M, T, K, L, stride = shape
+    mode, dist = MODES[flag]
+    torch.manual_seed(77 + T + L)
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    thr = torch.rand(1, K, M) if pool == "lts_min" else None
+    opool = O.POOL_LTS_MIN if pool == "lts_min" else O.POOL_RBF_MAX
+    dW_ref, _, dx_ref = O.shapelet_backward_autograd(xn.double(), W.double(), g.double(), stride, 0.9, mode, opool,
+                                                     None if thr is None else thr.double(), need_dx=True)
+    xd = xn.to(DEV).requires_grad_(True)
+    Wd = W.to(DEV).requires_grad_(True)
+    thd = None if thr is None else thr.to(DEV).requires_grad_(True)
+    p, dmin, idx = shapelet_transform(SeriesPack.from_channel_major(xd), Wd, stride, 0.9, dist, pool, thd)
+    (p * g.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert_close(xd.grad, dx_ref, 2e-4, 2e-4 * float(dx_ref.abs().max()), f"{flag}/{pool} {shape} dx")
+    assert_close(Wd.grad, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag}/{pool} {shape} dW (with dx requested)")
+    # the input gradient alone (weights frozen): same values, the contraction is skipped
+    xd2 = xn.to(DEV).requires_grad_(True)
+    p2, _, _ = shapelet_transform(SeriesPack.from_channel_major(xd2), W.to(DEV), stride, 0.9, dist, pool,
+                                  None if thr is None else thr.to(DEV))
+    (p2 * g.to(DEV)).sum().backward()
+    assert torch.equal(xd2.grad, xd.grad)
+
+
+def test_input_gradient_of_the_squared_l2_function_is_zero_as_in_the_reference():
+    from layers.shapelet_ops import SeriesPack, shapelet_transform
+    torch.manual_seed(1)
+    xd = torch.randn(2, 3, 80, device=DEV, requires_grad=True)
+    Wd = torch.randn(4, 3, 11, device=DEV, requires_grad=True)
+    p, _, _ = shapelet_transform(SeriesPack.from_channel_major(xd), Wd, 1, 1.0, "sql2")
+    p.sum().backward()
+    assert float(xd.grad.abs().sum()) == 0.0 and float(Wd.grad.abs().sum()) > 0.0      # Shapelet.py:40

@@ -220,3 +220,28 @@ def test_pipelined_backward_phases_give_identical_gradients(monkeypatch):
     serial = grads()
     for a, b, c in zip(base, piped, serial):
         assert torch.equal(a, b) and torch.equal(a, c)
+
+
+@pytest.mark.parametrize("name", ["model_jv_interpgn", "model_jv_interpgn_cos", "model_small_chisco"])
+def test_saliency_input_gradient_through_the_whole_model(name):
+    """dLoss/dx of the raw batch through instance norm, all length groups, the head, the gate and the deep expert —
+    against autograd through the oracle restatement of the shapelet expert (fp64) with the same deep-expert gradient."""
+    import ign_oracle as O
+    from helpers import MODES
+    model, g = build(name)
+    model.overlap_experts = False
+    x = t(g["x"], DEV).requires_grad_(True)
+    y = torch.as_tensor(g["y"]).to(DEV)
+    logits, info = model(x, torch.ones(x.shape[0], x.shape[1], device=DEV), None, None)
+    # isolate the shapelet expert's path: its logits only (the deep expert's input gradient is plain cuDNN autograd)
+    loss = torch.nn.functional.cross_entropy(info.shapelet_preds, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    kw = dict(zip(g["cfg_keys"].tolist(), g["cfg_vals"].tolist()))
+    mode = MODES[kw.get("distance_func", "euclidean")][0]
+    xr = t(g["x"]).double().requires_grad_(True)
+    Ws = [s.weights.detach().cpu().double() for s in model.sbm.shapelets]
+    Wc = model.sbm.output_layer.weight.detach().cpu().double()
+    ref_logits, _, _ = O.sbm_forward(xr, Ws, [s.stride for s in model.sbm.shapelets], Wc, 1.0, mode)
+    torch.nn.functional.cross_entropy(ref_logits, torch.as_tensor(g["y"])).backward()
+    assert_close(x.grad, xr.grad, 1e-3, 2e-4 * float(xr.grad.abs().max()), name + " dLoss/dx")
