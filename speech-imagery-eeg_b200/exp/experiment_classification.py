@@ -157,8 +157,10 @@ class Experiment(object):
 
     def _graph_applicable(self, x):
         a = self.args
-        if a.gradient_accumulation_steps != 1 or a.gradient_clip > 0 or (self.world > 1 and not self.independent):
-            return False            # accumulation / clipping / the NCCL exchange keep the eager path
+        if a.gradient_accumulation_steps != 1 or a.gradient_clip > 0 or (self.world > 1 and not self.independent) \
+                or getattr(a, "lr_decay", False):
+            return False            # accumulation / clipping / the NCCL exchange keep the eager path; so does a learning-
+                                    # rate schedule (the captured Adam kernel carries the rate it was captured with)
         return self._graph is None or tuple(x.shape) == tuple(self._graph[1].shape)     # ragged last batch: eager
 
     def _graphed_step(self, x, y, mask, epoch, step_index):

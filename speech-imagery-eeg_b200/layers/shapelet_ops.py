@@ -21,9 +21,10 @@ _DIST_OF_FLAG = {"cosine": "cosine", "pearson": "pearson"}
 # Memory the backward may spend per length group on the window distances it keeps from the forward plus the
 # coefficient workspace of the same size (stored-distance mode: fastest, 2 x 4*B*M*K*T' bytes).  Above it the layer
 # switches to the recompute backward (nothing saved, shapelets walked in chunks inside a workspace of at most this
-# size): config 2 at B=256 needs 1.2 GB per group and stores; the K = 1000 points of the config-4 sweep would need
-# 232 GB and recompute.
-STORE_BUDGET_BYTES = int(float(os.environ.get("IGN_BWD_STORE_BUDGET_GB", "12")) * 2 ** 30)
+# size): config 2 at B=256 needs 1.2 GB per group and stores, so do the K = 100 points of the config-4 sweep (23 GB);
+# the K = 1000 points would need 232 GB and recompute.  Four groups at the limit keep 4 x 16 GiB of distances plus one
+# 16 GiB coefficient buffer: under 80 GiB of the 180.
+STORE_BUDGET_BYTES = int(float(os.environ.get("IGN_BWD_STORE_BUDGET_GB", "32")) * 2 ** 30)
 
 
 def resolve_dist(distance_func: str, memory_efficient: bool) -> str:
