@@ -117,3 +117,53 @@ def test_synthetic_provider_contract_and_rank_sharding():
     ds3, _ = data_provider(b, "train")
     assert (ds3.enc_in, ds3.max_seq_len, ds3.num_class) == (125, 1000, 3)
     assert run.get_args(["--amp"]).amp is False and run.get_args([]).amp is True      # reference run.py:100
+
+
+UEA_TS = """@problemName Odd
+@timeStamps false
+@missing false
+@univariate false
+@dimensions 2
+@equalLength true
+@seriesLength 4
+@classLabel true a b
+@data
+"""
+
+
+def _epoch_worker(rank, world, port, root, ret):
+    """One epoch over a real (generated) UEA archive whose train split does not divide by world * batch: every step
+    does the one all-reduce of the training loop; ranks with different step counts would pair all-reduces of different
+    steps and hang at the final barrier."""
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "speech-imagery-eeg_b200"))
+    from data_provider.data_factory import data_provider
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    args = SimpleNamespace(data="UEA", dataset="Odd", root_path=root, batch_size=2, num_workers=0, world_size=world,
+                           rank=rank, seq_len=0)
+    ds, dl = data_provider(args, "train")
+    steps, seen = 0, 0
+    for X, y, m in dl:
+        t = torch.tensor([float(X.shape[0])])
+        dist.all_reduce(t)                       # the per-step gradient exchange
+        steps += 1
+        seen += X.shape[0]
+    dist.barrier()
+    ret[rank] = (len(ds), steps, seen)
+    dist.destroy_process_group()
+
+
+def test_uneven_real_archive_gives_every_rank_the_same_number_of_steps(tmp_path):
+    d = tmp_path / "Odd"
+    d.mkdir()
+    rows = "".join("%d,%d,%d,%d:%d,%d,%d,%d:%s\n" % (i, i + 1, i + 2, i + 3, i, i, i, i, "ab"[i % 2]) for i in range(9))
+    (d / "Odd_TRAIN.ts").write_text(UEA_TS + rows)            # 9 cases, world 2, batch 2: 5 and 4 before the fix
+    (d / "Odd_TEST.ts").write_text(UEA_TS + rows)
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_epoch_worker, args=(world, port, str(d), ret), nprocs=world, join=True)
+        r0, r1 = ret[0], ret[1]
+    assert r0[0] == r1[0] == 5 and r0[1] == r1[1] == 3          # equal shards (one sample wraps around), equal step counts
