@@ -77,6 +77,9 @@ __device__ __forceinline__ bool bp_any(long long) { return true; }
 
 struct BwdTcGeo {
   int B, M, T, Tp, K, L;
+  int s;               // window stride: residue r of the series / shapelet is its own unit-stride contraction (one item
+                       // dimension): G[k, q s + r] = sum_t a[k,t] x_r[t + q],  x_r[j] = x[j s + r],  q < Lr(r) = ceil((L - r) / s)
+  int L0;              // lags of the longest residue: ceil(L / s)
   int Tw, Ts;          // windows, coefficient row pitch
   int RI, NKB;         // window groups (of 8) per sample, 32-row k-blocks per sample
   int P;               // shifts: 16 or 8
@@ -92,7 +95,7 @@ struct BwdTcArgs {
   const float* xn; const float* coef; float* part;
 };
 
-struct ItemCoord { int m, kblk, chunk, lb, mt; };   // mt: M' tiles of this item's lag block
+struct ItemCoord { int m, kblk, chunk, lb, mt, res, Lr; };   // mt: M' tiles of this item's lag block; res / Lr: residue, its lags
 __device__ __forceinline__ ItemCoord item_coord(const BwdTcGeo& g, int w) {
   ItemCoord c;
   int mk = w / g.nchunk;
@@ -100,9 +103,15 @@ __device__ __forceinline__ ItemCoord item_coord(const BwdTcGeo& g, int w) {
   const int mkl = mk;
   mk = mkl / g.nlb;
   c.lb = mkl - mk * g.nlb;
+  const int mkr = mk;
+  mk = mkr / g.s;
+  c.res = mkr - mk * g.s;
   c.m = mk / g.nkb;
   c.kblk = mk - c.m * g.nkb;
-  c.mt = min(g.MT, (g.L + g.P - 1 - c.lb * g.lagstep + kBRows - 1) / kBRows);
+  c.Lr = (g.L - c.res + g.s - 1) / g.s;
+  // lag blocks past this residue's lags (the shorter residues of a strided group) get no tiles: nothing to do
+  c.mt = max(0, min(g.MT, (c.Lr + g.P - 1 - c.lb * g.lagstep + kBRows - 1) / kBRows));
+  if (c.lb * g.lagstep >= c.Lr) c.mt = 0;
   return c;
 }
 
@@ -230,12 +239,12 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
             }
           }
           bar_sync(3, 128);
-          const int l0 = ic.lb * g.lagstep, nl = min(g.lagstep, g.L - l0);            // this block's lags [l0, l0 + nl)
+          const int l0 = ic.lb * g.lagstep, nl = min(g.lagstep, ic.Lr - l0);          // this block's lags [l0, l0 + nl) of the residue
           for (int l = et; l < nl; l += 128) {
             float s = 0.f;
 #pragma unroll
             for (int j = 0; j < kBShifts; ++j) s += tk[j * TU + l + j];                // fixed order
-            a.part[(((size_t)ic.chunk * g.K + k) * g.M + ic.m) * g.L + l0 + l] = s;
+            a.part[(((size_t)ic.chunk * g.K + k) * g.M + ic.m) * g.L + (size_t)(l0 + l) * g.s + ic.res] = s;
           }
           bar_sync(3, 128);
         }
@@ -416,23 +425,56 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
     for (int i = lane; i < kBRowBufs * g.XR; i += 32) xrow[i] = 0.f;  // pads behind Tp stay zero for ever
     fence_proxy_async_smem();                                        // generic zero fill before the async-proxy row copies
     __syncwarp();
-    if (elect_one()) {
-      const uint32_t row_bytes = (uint32_t)g.Tp * sizeof(float);     // Tp % 4 == 0: a multiple of 16, rows 16-byte aligned
-      int nrow = 0;
+    if (g.s == 1) {
+      if (elect_one()) {
+        const uint32_t row_bytes = (uint32_t)g.Tp * sizeof(float);   // Tp % 4 == 0: a multiple of 16, rows 16-byte aligned
+        int nrow = 0;
+        for (int w = wbeg; w < wend; ++w) {
+          const ItemCoord ic = item_coord(g, w);
+          const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
+          for (int b = b0; b < b1; ++b, ++nrow) {
+            const int buf = nrow % kBRowBufs;
+            long long t0 = BP_CLK();
+            if (nrow >= kBRowBufs) mbar_wait(&rowempty[buf], ((nrow / kBRowBufs) - 1) & 1);   // row nrow - kBRowBufs is consumed
+            BP_ADD(7, t0);
+            mbar_arrive_expect_tx(&rowfull[buf], row_bytes);
+            tma_bulk_g2s(xrow + (size_t)buf * g.XR, a.xn + ((size_t)b * g.M + ic.m) * g.Tp, row_bytes, &rowfull[buf]);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      // strided group: the item's residue row x_r[j] = x[j s + r] is gathered with 4-byte cp.async (the row is re-read
+      // from L2 by the s residue items); rows nrow-1 and nrow-2 stay in flight while row nrow is issued
+      int nrow = 0, done = 0;                                        // rows issued / rows published
       for (int w = wbeg; w < wend; ++w) {
         const ItemCoord ic = item_coord(g, w);
         const int b0 = ic.chunk * kBChunk, b1 = min(g.B, b0 + kBChunk);
+        const int nq = (g.T - ic.res + g.s - 1) / g.s;              // samples of this residue
         for (int b = b0; b < b1; ++b, ++nrow) {
           const int buf = nrow % kBRowBufs;
-          long long t0 = BP_CLK();
-          if (nrow >= kBRowBufs) mbar_wait(&rowempty[buf], ((nrow / kBRowBufs) - 1) & 1);   // row nrow - kBRowBufs is consumed
-          BP_ADD(7, t0);
-          mbar_arrive_expect_tx(&rowfull[buf], row_bytes);
-          tma_bulk_g2s(xrow + (size_t)buf * g.XR, a.xn + ((size_t)b * g.M + ic.m) * g.Tp, row_bytes, &rowfull[buf]);
+          if (nrow >= kBRowBufs) mbar_wait(&rowempty[buf], ((nrow / kBRowBufs) - 1) & 1);
+          const float* src = a.xn + ((size_t)b * g.M + ic.m) * g.Tp + ic.res;
+          float* dst = xrow + (size_t)buf * g.XR;
+          for (int j = lane; j < nq; j += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + j)), "l"(src + (size_t)j * g.s) : "memory");
+          for (int j = nq + lane; j < g.XR && j < nq + 64; j += 32) dst[j] = 0.f;   // the slots a longer residue row left behind
+          cp_async_commit();
+          if (nrow - done >= 2) {                                    // publish the oldest row in flight
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rowfull[done % kBRowBufs]);
+            ++done;
+          }
         }
       }
+      cp_async_wait_all();
+      __threadfence_block();
+      __syncwarp();
+      for (; done < nrow; ++done)
+        if (lane == 0) mbar_arrive(&rowfull[done % kBRowBufs]);
     }
-    __syncwarp();
   }
 
   if (lane == 0 || (warp == kBMmaWarp)) {
@@ -448,7 +490,8 @@ __global__ void __launch_bounds__(kBThreads, 1) shapelet_bwd_tc_kernel(const Bwd
 
 void bwd_tc_geo(const ign_shapelet_desc& d, BwdTcGeo& g) {
   g.B = d.B; g.M = d.M; g.T = d.T; g.Tp = d.Tp; g.K = d.K; g.L = d.L;
-  g.Tw = num_windows(d.T, d.L, 1); g.Ts = round_up(g.Tw, 4);
+  g.s = d.stride; g.L0 = ceil_div(d.L, d.stride);
+  g.Tw = num_windows(d.T, d.L, d.stride); g.Ts = round_up(g.Tw, 4);
   g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb);
   // 16 shifts when the whole shapelet then fits one lag block (half the A' tiles, B' stages and MMA issue slots per
   // sample), else 8 shifts with up to four 128-lane tiles per block
@@ -459,11 +502,12 @@ void bwd_tc_geo(const ign_shapelet_desc& d, BwdTcGeo& g) {
   const int mtmax = max(1, min(kBMaxMT, kBACol0 / g.N));
   g.RI = ceil_div(g.Tw, g.P); g.NKB = ceil_div(g.RI, kBKBlock);
   g.lagstep = mtmax * kBRows - g.P;
-  g.nlb = ceil_div(d.L, g.lagstep);
-  g.MT = min(mtmax, ceil_div(d.L + g.P - 1, kBRows));
-  g.XR = round_up(max(d.Tp, g.P * kBKBlock * g.NKB + (g.nlb - 1) * g.lagstep + kBRows * g.MT) + 8, 4);
+  g.nlb = ceil_div(g.L0, g.lagstep);
+  g.MT = min(mtmax, ceil_div(g.L0 + g.P - 1, kBRows));
+  // one (residue) row: its samples, or the furthest A' gather (window groups + lag lanes), whichever is longer
+  g.XR = round_up(max(g.s == 1 ? d.Tp : ceil_div(d.T, g.s), g.P * kBKBlock * g.NKB + (g.nlb - 1) * g.lagstep + kBRows * g.MT) + 8, 4);
   g.nchunk = ceil_div(d.B, kBChunk);
-  g.nitems = d.M * g.nkb * g.nlb * g.nchunk;
+  g.nitems = d.M * g.nkb * g.s * g.nlb * g.nchunk;
   g.split = d.precision == IGN_PREC_3XTF32 ? 1 : 0;
 }
 
@@ -487,12 +531,12 @@ int bwd_tc_profile_read(unsigned long long* host16, int reset) {
 #endif
 }
 
-// the tensor-core contraction covers: cross-term distances, unit stride, the tcgen05 operand modes; any shapelet
-// length (lag blocks of 504) as long as one series row and its zero padding fit shared memory twice
+// the tensor-core contraction covers: cross-term distances in the tcgen05 operand modes, any stride (one item per
+// residue: s unit-stride contractions) and any shapelet length (lag blocks), as long as the row ring fits shared memory
 bool shapelet_bwd_tc_supported(const ign_shapelet_desc& d) {
-  if (d.dist == IGN_DIST_L1 || d.stride != 1) return false;
+  if (d.dist == IGN_DIST_L1) return false;
   if (d.precision != IGN_PREC_3XTF32 && d.precision != IGN_PREC_TF32) return false;
-  if (num_windows(d.T, d.L, 1) <= 0) return false;
+  if (num_windows(d.T, d.L, d.stride) <= 0) return false;
   BwdTcGeo g;
   bwd_tc_geo(d, g);
   if (g.MT * g.N > kBACol0) return false;
