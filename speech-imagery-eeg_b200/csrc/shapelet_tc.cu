@@ -26,6 +26,12 @@
 //    already in the 128B-swizzled K-major tile image (hi | lo), and a dedicated warp streams one tile per
 //    stage with a single 1-D bulk TMA copy (cp.async.bulk + mbarrier complete_tx).
 //
+// Strided windows (seq_len >= 3000, Shapelet.py:162): sum_l x[t s + l] w[l] = sum_r sum_q x_r[t + q] w_r[q] with the
+// residues x_r[j] = x[j s + r], w_r[q] = w[q s + r] — s unit-stride cross terms that accumulate into the SAME tile, so
+// their k-blocks simply concatenate (NKB = s * NKBr).  The series rows are streamed one RESIDUE at a time (a ring of
+// (tile, residue) units, each RB rows of T/s samples gathered with 4-byte cp.async), so shared memory holds a few KB
+// per unit instead of s whole rows per sample — which is what lets a tile keep its 4-8 samples at T = 4000.
+//
 // Persistent kernel: one CTA per SM walks a contiguous range of the (channel, shapelet block, sample tile) list,
 // so there is no wave-quantisation tail and the TMEM allocation, barriers and the pipeline state live for the
 // whole launch.
@@ -70,6 +76,7 @@ constexpr int kAccCols = 128;          // TMEM columns reserved per accumulator 
 constexpr int kAStageCols = 64;        // TMEM columns per A stage: 32 hi + 32 lo
 constexpr int kMaxAcc = 4;             // accumulators in flight (2, or 3-4 when N is small and the tiles are short)
 constexpr int kMaxRB = 8;              // samples per tile (bounds the arg-min cell arrays)
+constexpr int kMaxRowBufs = 4;         // ring of series-row units: 2 for unit stride (one unit per tile), 4 for strided groups
 constexpr unsigned long long kSlotEmpty = 0xffffffffffffffffull;
 
 struct TcGeo {
@@ -78,7 +85,10 @@ struct TcGeo {
   int RI, RB;          // window groups (of 16) per sample, samples per 128-row tile
   int KG, nkb;         // shapelets per N tile, number of shapelet blocks
   int N;               // 16*KG
-  int NKB;             // 32-wide k-blocks: ceil((L+15)/32)
+  int s;               // window stride; residue r of series and shapelet is its own group of k-blocks
+  int NKBr;            // 32-wide k-blocks per residue: ceil((ceil(L/s)+15)/32)
+  int NKB;             // k-blocks per tile: s * NKBr
+  int nrb;             // series-row units in the ring
   int XR;              // floats per series row in smem
   int nacc, accp;      // accumulators in flight and their TMEM column pitch
   int stack;           // 3xTF32 with [B_hi | B_lo] stacked along N: two MMAs per k-step (N and 2N) instead of three
@@ -128,7 +138,8 @@ __device__ long long g_tc_trace[12 * 32 * 4];
 //   SQL2 ||w||^2, COSINE 1/max(||w||,1e-8), PEARSON ||w-mean||.
 __global__ void __launch_bounds__(128) tc_build_b_kernel(const float* __restrict__ W, uint8_t* __restrict__ out,
                                                          float* __restrict__ wstat, int M, int K, int L, int KG,
-                                                         int nkb, int NKB, int N, int split, int dist) {
+                                                         int nkb, int NKB, int N, int split, int dist, int stride,
+                                                         int NKBr) {
   __shared__ float s_mean[16];
   const int m = blockIdx.x, kblk = blockIdx.y, kb = blockIdx.z;
   const int k0 = kblk * KG;
@@ -163,14 +174,16 @@ __global__ void __launch_bounds__(128) tc_build_b_kernel(const float* __restrict
   __syncthreads();
   const int b_bytes = N * 128;
   uint8_t* dst = out + (((size_t)m * nkb + kblk) * NKB + kb) * (size_t)(b_bytes * (split ? 2 : 1));
+  const int res = kb / NKBr, kbr = kb - res * NKBr;                  // k-block kb = residue res, its kbr-th block
   for (int task = threadIdx.x; task < N * 8; task += blockDim.x) {
     const int n = task >> 3, c = task & 7;
     const int u = n >> 4, j = n & 15;
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int l = kb * kKBlock + 4 * c + e - j;
-      v[e] = (k0 + u < K && l >= 0 && l < L) ? __ldg(W + ((size_t)(k0 + u) * M + m) * L + l) - s_mean[u] : 0.f;
+      const int q = kbr * kKBlock + 4 * c + e - j;                     // lag inside the residue
+      const int l = q * stride + res;
+      v[e] = (k0 + u < K && q >= 0 && l < L) ? __ldg(W + ((size_t)(k0 + u) * M + m) * L + l) - s_mean[u] : 0.f;
     }
     const float4 hi = make_float4(v[0], v[1], v[2], v[3]);
     const uint32_t off = sw128_off(n, c);
@@ -270,8 +283,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
   const int stage_bytes = b_bytes * (g.split ? 2 : 1);
   uint8_t* stage0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ptr = stage0 + (size_t)g.nbs * stage_bytes;
-  float* xbuf = reinterpret_cast<float*>(ptr);                      // [2][RB][XR] series rows (double buffered)
-  ptr += (size_t)2 * g.RB * g.XR * sizeof(float);
+  float* xbuf = reinterpret_cast<float*>(ptr);                      // [nrb][RB][XR] series-row units (ring)
+  ptr += (size_t)g.nrb * g.RB * g.XR * sizeof(float);
   float* celld = reinterpret_cast<float*>(ptr);                     // [ncb][4][RB][KG][16] winner rows' distances
   ptr += (size_t)g.ncb * 4 * g.RB * g.KG * 16 * sizeof(float);
   unsigned long long* cells = reinterpret_cast<unsigned long long*>(ptr);   // [ncb][4][RB][KG] ordered min | first window of the row
@@ -280,8 +293,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
   uint64_t* fullA = bars; uint64_t* emptyA = fullA + kAStages;
   uint64_t* fullB = emptyA + kAStages; uint64_t* emptyB = fullB + kMaxBStages;
   uint64_t* tfull = emptyB + kMaxBStages; uint64_t* tempty = tfull + kMaxAcc;
-  uint64_t* rowfull = tempty + kMaxAcc; uint64_t* rowempty = rowfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rowempty + 2);
+  uint64_t* rowfull = tempty + kMaxAcc; uint64_t* rowempty = rowfull + kMaxRowBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rowempty + kMaxRowBufs);
 
   const uint32_t tmem_cols = 512;                                   // nacc accumulators in columns [0,256) + kAStages A stages
 
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     for (int s = 0; s < kAStages; ++s) { mbar_init(&fullA[s], 4); mbar_init(&emptyA[s], 1); }   // 4 producer warps
     for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     for (int i = 0; i < kMaxAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&rowfull[i], 1); mbar_init(&rowempty[i], kProdWarps); }
+    for (int i = 0; i < kMaxRowBufs; ++i) { mbar_init(&rowfull[i], 1); mbar_init(&rowempty[i], kProdWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
@@ -316,17 +329,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g.acol0;
     uint32_t it = 0;                                                 // global stage counter
     int sidx = 0; uint32_t sph = 0;                                  // A ring slot / phase of stage `it`
+    int rbuf = 0; uint32_t rph = 0;                                  // row-unit ring slot / phase
     for (int w = wbeg; w < wend; ++w) {
-      const int buf = (w - wbeg) & 1;
       const TileCoord tc = tile_coord(g, w);
       const int nb = min(g.RB, g.B - tc.b0);
+      const bool a_live = a_off[0] >= 0 && a_bl < nb;
+      for (int res = 0; res < g.s; ++res) {                          // one row unit per residue (one per tile at unit stride)
+      const int buf = rbuf;
       long long tr0 = TC_CLK();
-      mbar_wait(&rowfull[buf], ((w - wbeg) >> 1) & 1);               // this tile's series rows are in shared memory
-      if (lane == 0 && (warp & 3) == 0) TC_TRACE(9 + grp, w - wbeg, 0);
+      mbar_wait(&rowfull[buf], rph);                                 // this unit's series rows are in shared memory
+      if (++rbuf == g.nrb) { rbuf = 0; rph ^= 1; }
+      if (lane == 0 && (warp & 3) == 0 && res == 0) TC_TRACE(9 + grp, w - wbeg, 0);
       if (p == 0) TC_ADD(3, tr0);
       const float* xb = xbuf + (size_t)buf * g.RB * g.XR;
-      const bool a_live = a_off[0] >= 0 && a_bl < nb;
-      for (int kb = 0; kb < g.NKB; ++kb, ++it) {
+      for (int kb = 0; kb < g.NKBr; ++kb, ++it) {
         const int s = sidx;
         const uint32_t ph = sph;
         if (++sidx == g.nast) { sidx = 0; sph ^= 1; }
@@ -363,7 +379,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
         if (p == 0) TC_ADD(1, tp0);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&rowempty[buf]);                    // this warp no longer reads the tile's rows
+      if (lane == 0) mbar_arrive(&rowempty[buf]);                    // this warp no longer reads the unit's rows
+      }   // residues
     }
   } else if (warp < kMmaWarp) {
     // =================================================================== EPILOGUE
@@ -597,27 +614,47 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
   if (warp == kRowWarp) {
     // =================================================================== SERIES-ROW LOADER (one warp)
     // Rows are stored bank-skewed (4 floats of padding after every 32) so that the 128 row owners, whose segments
-    // start 16 samples apart, read with conflict-free LDS.128.  Double buffered: tile n+1 loads under tile n.
-    for (int i = lane; i < 2 * g.RB * g.XR; i += 32) xbuf[i] = 0.f;
+    // start 16 samples apart, read with conflict-free LDS.128.  Ring of nrb (tile, residue) units; the unit issued two
+    // steps ago is published while the newer ones are still in flight (cp.async groups).
+    for (int i = lane; i < g.nrb * g.RB * g.XR; i += 32) xbuf[i] = 0.f;
     __syncwarp();
     const int chunks = g.Tp / 4;
-    int n = 0;
-    for (int w = wbeg; w < wend; ++w, ++n) {
-      const int buf = n & 1;
-      if (n >= 2) mbar_wait(&rowempty[buf], ((n >> 1) - 1) & 1);      // every producer warp is done with tile n-2
+    const int lag = g.s == 1 ? 0 : 2;                                // units kept in flight behind the one being issued
+    int u = 0, done = 0;                                             // units issued / published
+    for (int w = wbeg; w < wend; ++w) {
       const TileCoord tc = tile_coord(g, w);
-      for (int bl = 0; bl < g.RB; ++bl) {
-        if (tc.b0 + bl >= g.B) break;
-        float* dst = xbuf + ((size_t)buf * g.RB + bl) * g.XR;
-        const float* src = a.xn + ((size_t)(tc.b0 + bl) * g.M + tc.m) * g.Tp;
-        for (int c = lane; c < chunks; c += 32) cp_async16(dst + c * 4 + 4 * (c >> 3), src + c * 4);
+      for (int res = 0; res < g.s; ++res, ++u) {
+        const int buf = u % g.nrb;
+        if (u >= g.nrb) mbar_wait(&rowempty[buf], ((u / g.nrb) - 1) & 1);   // every producer warp is done with unit u - nrb
+        for (int bl = 0; bl < g.RB; ++bl) {
+          if (tc.b0 + bl >= g.B) break;
+          float* dst = xbuf + ((size_t)buf * g.RB + bl) * g.XR;
+          const float* src = a.xn + ((size_t)(tc.b0 + bl) * g.M + tc.m) * g.Tp;
+          if (g.s == 1) {
+            for (int c = lane; c < chunks; c += 32) cp_async16(dst + c * 4 + 4 * (c >> 3), src + c * 4);
+          } else {
+            const int nq = (g.T - res + g.s - 1) / g.s;             // x_r[j] = x[j s + res]
+            for (int j = lane; j < nq; j += 32)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + j + 4 * (j >> 5))), "l"(src + (size_t)j * g.s + res) : "memory");
+            if (lane == 0) dst[nq + 4 * (nq >> 5)] = 0.f;          // the sample a one-longer residue row left behind
+          }
+        }
+        cp_async_commit();
+        if (u - done >= lag) {
+          if (lag == 0) cp_async_wait_all();
+          else asm volatile("cp.async.wait_group 2;" ::: "memory");
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&rowfull[done % g.nrb]);
+          ++done;
+        }
       }
-      cp_async_commit();
-      cp_async_wait_all();
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rowfull[buf]);
     }
+    cp_async_wait_all();
+    __threadfence_block();
+    __syncwarp();
+    for (; done < u; ++done)
+      if (lane == 0) mbar_arrive(&rowfull[done % g.nrb]);
   }
 
   if (threadIdx.x == 0) TC_ADD(12, t_entry);         // producer thread 0 finished its loop
@@ -629,8 +666,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
 }
 
 size_t tc_smem_fixed(const TcGeo& g) {   // everything except the B ring
-  return (size_t)2 * g.RB * g.XR * 4 + (size_t)g.ncb * 4 * g.RB * g.KG * (8 + 64) +
-         (2 * kAStages + 2 * kMaxBStages + 2 * kMaxAcc + 4) * 8 + 16 + 1024;
+  return (size_t)g.nrb * g.RB * g.XR * 4 + (size_t)g.ncb * 4 * g.RB * g.KG * (8 + 64) +
+         (2 * kAStages + 2 * kMaxBStages + 2 * kMaxAcc + 2 * kMaxRowBufs) * 8 + 16 + 1024;
 }
 size_t tc_stage_bytes(const TcGeo& g) { return (size_t)(g.N * 128) * (g.split ? 2 : 1); }
 
@@ -672,12 +709,14 @@ int tc_profile_read(unsigned long long* host16, int reset) {
 
 static void tc_geo(const ign_shapelet_desc& d, TcGeo& g) {
   g.B = d.B; g.M = d.M; g.T = d.T; g.Tp = d.Tp; g.K = d.K; g.L = d.L;
-  g.Tw = num_windows(d.T, d.L, 1); g.Ts = round_up(g.Tw, 4);
+  g.s = d.stride; g.nrb = g.s == 1 ? 2 : kMaxRowBufs;
+  g.Tw = num_windows(d.T, d.L, d.stride); g.Ts = round_up(g.Tw, 4);
   g.RI = ceil_div(g.Tw, kShifts); g.RB = max(1, min(min(kRows / g.RI, d.B), kMaxRB));
   g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb); g.N = 16 * g.KG;   // N <= 128 = kAccCols
-  g.NKB = ceil_div(d.L + kShifts - 1, kKBlock);
-  {  // bank-skewed series rows: 36 floats per 32 samples
-    const int span = max(d.Tp, (g.RI - 1) * kShifts + g.NKB * kKBlock) + 32;
+  g.NKBr = ceil_div(ceil_div(d.L, g.s) + kShifts - 1, kKBlock);
+  g.NKB = g.s * g.NKBr;
+  {  // bank-skewed series rows (one residue per row unit): 36 floats per 32 samples
+    const int span = max(g.s == 1 ? d.Tp : ceil_div(d.T, g.s), (g.RI - 1) * kShifts + g.NKBr * kKBlock) + 32;
     g.XR = round_up(span + 4 * (span / 32) + 8, 4);
   }
   g.tpm = ceil_div(d.B, g.RB);
@@ -710,9 +749,9 @@ size_t shapelet_fwd_tc_workspace(const ign_shapelet_desc& d) {
 }
 
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d) {
-  if (d.dist == IGN_DIST_L1 || d.stride != 1) return false;
+  if (d.dist == IGN_DIST_L1) return false;
   if (d.precision != IGN_PREC_3XTF32 && d.precision != IGN_PREC_TF32) return false;
-  const int Tw = num_windows(d.T, d.L, 1);
+  const int Tw = num_windows(d.T, d.L, d.stride);
   if (Tw <= 0 || ceil_div(Tw, kShifts) > kRows) return false;     // one sample must fit a 128-row tile
   TcGeo g;
   tc_geo(d, g);
@@ -732,11 +771,11 @@ int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   float* wstat = reinterpret_cast<float*>(btiles + tc_btile_bytes(d, g));
   // 1. shifted-shapelet operand + shapelet statistics, once per launch, already in the swizzled tile image
   tc_build_b_kernel<<<dim3(d.M, g.nkb, g.NKB), 128, 0, st>>>(W, btiles, wstat, d.M, d.K, d.L, g.KG, g.nkb, g.NKB, g.N,
-                                                            g.split, d.dist);
+                                                            g.split, d.dist, g.s, g.NKBr);
   IGN_CUDA(cudaGetLastError());
   // 2. main kernel: persistent, one CTA per SM (the kernel owns all 512 TMEM columns of its SM)
   const size_t smem = max(tc_smem_fixed(g) + g.nbs * tc_stage_bytes(g), (size_t)118 * 1024);   // > half the SM: one CTA per SM
-  TcArgs a{xn, st0, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, 1), btiles, wstat};
+  TcArgs a{xn, st0, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, d.stride), btiles, wstat};
   const int grid = min(sm_count(), g.ntiles);
   auto kern = g.stack ? (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, true>
                          : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, true>

@@ -295,23 +295,25 @@ def test_tcgen05_training_path(flag):
     assert_close(dmin, d32, 2e-6, 2e-6, flag + " 3xtf32 vs fp32 engine")
 
 
-def test_tcgen05_forward_leaves_strided_windows_to_the_fp32_engine():
-    """stride > 1: the FORWARD stays on the exact-fp32 engine (the tile cannot hold enough de-interleaved
-    rows to beat it) and says so; same results as an fp32 request."""
+def test_tcgen05_runs_strided_windows_and_reports_it():
+    """stride > 1 (seq_len >= 3000 in the reference, Shapelet.py:162) runs on the tensor-core engine, forward and backward:
+    residue r of series and shapelet is its own unit-stride cross term / contraction; `ign_shapelet_engine` says so."""
     from ctypes import byref
     from layers import ign_cabi as C
     torch.manual_seed(3)
     xn, W = torch.randn(2, 2, 400), torch.randn(4, 2, 50)
     a = run_layer(xn, W, 3, 1.0, "cosine", precision="3xtf32")
     b = run_layer(xn, W, 3, 1.0, "cosine")
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert_close(a[1], b[1], 2e-6, 2e-6, "strided 3xtf32 vs fp32 engine dmin")
     desc = C.ShapeletDesc(2, 2, 400, 400, 4, 50, 3, 1.0, C.DIST["cosine"], 0, C.PRECISION["3xtf32"])
-    assert C.ENGINE[C.lib.ign_shapelet_engine(byref(desc), 0)] == "fp32"
-    assert C.ENGINE[C.lib.ign_shapelet_engine(byref(desc), 1)] == "tcgen05"        # the backward contraction does tile it
+    assert C.ENGINE[C.lib.ign_shapelet_engine(byref(desc), 0)] == "tcgen05"
+    assert C.ENGINE[C.lib.ign_shapelet_engine(byref(desc), 1)] == "tcgen05"
+    l1 = C.ShapeletDesc(2, 2, 400, 400, 4, 50, 3, 1.0, C.DIST["l1"], 0, C.PRECISION["3xtf32"])
+    assert C.ENGINE[C.lib.ign_shapelet_engine(byref(l1), 0)] == "fp32"              # L1 has no cross term
 
 
-# Strided groups on the tcgen05 BACKWARD: residue r of series and shapelet is its own unit-stride contraction (one item
-# per residue).  Covers strides that do / do not divide L, ragged residues, a residue that ends exactly at a lag-block
+# Strided groups on the tcgen05 engine: residue r of series and shapelet is its own unit-stride cross term (forward: the
+# residues' k-blocks concatenate into one tile) / contraction (backward: one item per residue).  Covers strides that do / do not divide L, ragged residues, a residue that ends exactly at a lag-block
 # boundary (its second block has no tiles) and several shapelet blocks.
 STRIDED_BWD = [
     # B, M, T,    K,  L,    stride
@@ -320,17 +322,22 @@ STRIDED_BWD = [
     (2, 3, 640, 13, 64, 8),
     (1, 1, 3900, 2, 3681, 10),     # L0 = 369 > 368: two lag blocks; residues 1..9 have 368 lags (block 2 empty)
     (2, 2, 4000, 10, 400, 8),
+    (37, 5, 4000, 5, 2000, 10),    # 13 window groups per sample: 8 samples per tile, ragged last tile, many tiles per CTA
 ]
 
 
 @pytest.mark.parametrize("flag", ["cosine", "pearson", "sql2"])
 @pytest.mark.parametrize("shape", STRIDED_BWD)
-def test_tcgen05_backward_strided_vs_oracle(flag, shape):
+def test_tcgen05_strided_forward_and_backward_vs_oracle(flag, shape):
     B, M, T, K, L, stride = shape
     mode, dist = MODES[flag]
     torch.manual_seed(5 + T + L)
     xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
     p, dmin, idx, dW, _ = run_layer(xn, W, stride, 1.0, dist, g=g, precision="3xtf32")
+    ref = O.shapelet_forward(xn, W, stride, 1.0, mode)
+    assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, f"{flag} {shape} strided tcgen05 p")
+    assert_close(dmin.reshape(B, -1), ref.dmin, RTOL, ATOL, f"{flag} {shape} strided tcgen05 dmin")
+    index_parity(idx, ref.argmin_d, ref.d, False, L, f"{flag} {shape} strided tcgen05 argmin")
     dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), stride, 1.0, mode)
     assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag} {shape} strided tcgen05 dW")
     _, _, _, dW32, _ = run_layer(xn, W, stride, 1.0, dist, g=g)
