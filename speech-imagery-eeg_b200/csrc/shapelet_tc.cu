@@ -82,7 +82,10 @@ constexpr unsigned long long kSlotEmpty = 0xffffffffffffffffull;
 struct TcGeo {
   int B, M, T, Tp, K, L;
   int Tw, Ts;          // windows, dstore pitch
-  int RI, RB;          // window groups (of 16) per sample, samples per 128-row tile
+  int RI, RB;          // window groups (of 16) per sample IN ONE TILE (<= 128), samples per 128-row tile
+  int RItot, nseg;     // window groups per sample in total; tiles per sample (1 unless a sample has more than 2048 windows:
+                       // then RB = 1, tile `seg` covers groups [128 seg, 128 seg + 128) and the arg-min is merged across the
+                       // sample's tiles with a 64-bit atomicMin on (ordered distance | window index), decoded by tc_finish_kernel)
   int KG, nkb;         // shapelets per N tile, number of shapelet blocks
   int N;               // 16*KG
   int s;               // window stride; residue r of series and shapelet is its own group of k-blocks
@@ -105,6 +108,7 @@ struct TcArgs {
   const float* xn; const float* st0; const float* thr;   // st0: window statistics [B,M,SP]
   float* p; float* dmin; int* argmin; float* dstore;
   int SP;
+  unsigned long long* packed;   // [B,K,M] cross-tile arg-min cells (nseg > 1 only)
   const uint8_t* btiles;   // [M][nkb][NKB][stage_bytes] pre-swizzled B stage images
   const float* wstat;      // [M][nkb][8] shapelet statistic of the distance mode (pre-pass)
 };
@@ -204,11 +208,13 @@ __device__ __forceinline__ float ordered_val(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-struct TileCoord { int m, kblk, b0; };
+struct TileCoord { int m, kblk, b0, seg; };
 __device__ __forceinline__ TileCoord tile_coord(const TcGeo& g, int w) {
   TileCoord c;
   const int mk = w / g.tpm;
-  c.b0 = (w - mk * g.tpm) * g.RB;
+  const int idx = w - mk * g.tpm;
+  if (g.nseg > 1) { c.b0 = idx / g.nseg; c.seg = idx - c.b0 * g.nseg; }
+  else { c.b0 = idx * g.RB; c.seg = 0; }
   c.m = mk / g.nkb;
   c.kblk = mk - c.m * g.nkb;
   return c;
@@ -260,12 +266,31 @@ __device__ __forceinline__ void finalize_tile(const TcGeo& g, const TcArgs& a, c
     }
     const int imn = (int)(uint32_t)pk + jj;
     const size_t o = ((size_t)(tc.b0 + rbl) * g.K + k) * g.M + tc.m;
+    if (g.nseg > 1) {            // the sample spans several tiles: smallest (distance, index) over them wins, order-independent
+      atomicMin(a.packed + o, (pk & 0xffffffff00000000ull) | (unsigned long long)(unsigned)imn);
+      continue;
+    }
     float pv;
     if (g.pool == IGN_POOL_RBF_MAX) { const float ed = g.eps * dmn; pv = expf(-(ed * ed)); }
     else pv = 1.f / (1.f + expf(-(a.thr[(size_t)k * g.M + tc.m] - dmn)));
     a.p[o] = pv; a.dmin[o] = dmn;
     if (a.argmin) a.argmin[o] = imn;
   }
+}
+
+// nseg > 1: decode the merged cells into the pooled outputs
+__global__ void __launch_bounds__(256) tc_finish_kernel(const unsigned long long* __restrict__ packed, const float* __restrict__ thr,
+                                                       float* __restrict__ p, float* __restrict__ dmin, int* __restrict__ argmin,
+                                                       int n, int K, int M, int pool, float eps) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const unsigned long long pk = packed[o];
+  const float dmn = ordered_val((uint32_t)(pk >> 32));
+  float pv;
+  if (pool == IGN_POOL_RBF_MAX) { const float ed = eps * dmn; pv = expf(-(ed * ed)); }
+  else { const int km = o % (K * M); pv = 1.f / (1.f + expf(-(thr[km] - dmn))); }
+  p[o] = pv; dmin[o] = dmn;
+  if (argmin) argmin[o] = (int)(uint32_t)pk;
 }
 
 template <int DIST, bool STACK>
@@ -333,7 +358,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     for (int w = wbeg; w < wend; ++w) {
       const TileCoord tc = tile_coord(g, w);
       const int nb = min(g.RB, g.B - tc.b0);
-      const bool a_live = a_off[0] >= 0 && a_bl < nb;
+      const bool a_live = a_off[0] >= 0 && a_bl < nb && tc.seg * kRows + a_i < g.RItot;
+      const int seg_off = tc.seg * (kRows * kShifts / 32) * 36;      // 2048 samples further along the bank-skewed row
       for (int res = 0; res < g.s; ++res) {                          // one row unit per residue (one per tile at unit stride)
       const int buf = rbuf;
       long long tr0 = TC_CLK();
@@ -353,7 +379,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a_live) v[c] = *reinterpret_cast<const float4*>(xb + a_off[c] + kb * 36);   // 32 samples + 4 pad
+          if (a_live) v[c] = *reinterpret_cast<const float4*>(xb + a_off[c] + seg_off + kb * 36);   // 32 samples + 4 pad
         }
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -391,9 +417,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     const int e = quarter * 32 + lane;                              // accumulator row
     const int et = threadIdx.x - kProducerThreads;                  // 0..255
     const int bl = e / g.RI, i = e - bl * g.RI;
-    const int t0 = i * kShifts;
     const float invL = 1.f / (float)g.L;
-    const int nst = min(4, max(0, (g.Ts - t0) / 4));                // float4 stores per distance row segment (Ts % 4 == 0)
     const int npair = g.RB * g.KG;
     const int cells_per_buf = 4 * npair;
     for (int q = et; q < g.ncb * cells_per_buf; q += kEpilogueThreads) cells[q] = kSlotEmpty;
@@ -409,7 +433,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       const TileCoord tc = tile_coord(g, w);
       const int m = tc.m, k0 = tc.kblk * g.KG;
       const int nb = min(g.RB, g.B - tc.b0);
-      const bool row_live = bl < nb;                                // (bl < RB is implied: nb <= RB)
+      const int gi = tc.seg * kRows + i;                            // this row's window group inside its sample
+      const bool row_live = bl < nb && gi < g.RItot;                // (bl < RB is implied: nb <= RB)
+      const int t0 = gi * kShifts;
+      const int nst = min(4, max(0, (g.Ts - t0) / 4));              // float4 stores per distance row segment (Ts % 4 == 0)
       const int b = tc.b0 + bl;
       unsigned long long* cbuf = cells + (size_t)(n & (g.ncb - 1)) * cells_per_buf;
       float* dbuf = celld + (size_t)(n & (g.ncb - 1)) * cells_per_buf * 16;
@@ -711,15 +738,18 @@ static void tc_geo(const ign_shapelet_desc& d, TcGeo& g) {
   g.B = d.B; g.M = d.M; g.T = d.T; g.Tp = d.Tp; g.K = d.K; g.L = d.L;
   g.s = d.stride; g.nrb = g.s == 1 ? 2 : kMaxRowBufs;
   g.Tw = num_windows(d.T, d.L, d.stride); g.Ts = round_up(g.Tw, 4);
-  g.RI = ceil_div(g.Tw, kShifts); g.RB = max(1, min(min(kRows / g.RI, d.B), kMaxRB));
+  g.RItot = ceil_div(g.Tw, kShifts);
+  g.nseg = ceil_div(g.RItot, kRows);
+  g.RI = min(g.RItot, kRows);
+  g.RB = g.nseg > 1 ? 1 : max(1, min(min(kRows / g.RI, d.B), kMaxRB));
   g.nkb = ceil_div(d.K, 8); g.KG = ceil_div(d.K, g.nkb); g.N = 16 * g.KG;   // N <= 128 = kAccCols
   g.NKBr = ceil_div(ceil_div(d.L, g.s) + kShifts - 1, kKBlock);
   g.NKB = g.s * g.NKBr;
   {  // bank-skewed series rows (one residue per row unit): 36 floats per 32 samples
-    const int span = max(g.s == 1 ? d.Tp : ceil_div(d.T, g.s), (g.RI - 1) * kShifts + g.NKBr * kKBlock) + 32;
+    const int span = max(g.s == 1 ? d.Tp : ceil_div(d.T, g.s), (g.RItot - 1) * kShifts + g.NKBr * kKBlock) + 32;
     g.XR = round_up(span + 4 * (span / 32) + 8, 4);
   }
-  g.tpm = ceil_div(d.B, g.RB);
+  g.tpm = g.nseg > 1 ? d.B * g.nseg : ceil_div(d.B, g.RB);
   g.ntiles = d.M * g.nkb * g.tpm;
   g.dist = d.dist; g.pool = d.pool; g.eps = d.eps;
   g.split = d.precision == IGN_PREC_3XTF32 ? 1 : 0;
@@ -741,18 +771,23 @@ static size_t tc_btile_bytes(const ign_shapelet_desc& d, const TcGeo& g) {
   return (size_t)d.M * g.nkb * g.NKB * (size_t)(g.N * 128) * (g.split ? 2 : 1);   // a multiple of 128
 }
 
-// bytes of workspace the tcgen05 forward needs: pre-swizzled B tiles, then the per-shapelet statistics
+static size_t tc_wstat_bytes(const ign_shapelet_desc& d, const TcGeo& g) {
+  return ((size_t)d.M * g.nkb * 8 * sizeof(float) + 127) / 128 * 128;
+}
+
+// bytes of workspace the tcgen05 forward needs: pre-swizzled B tiles, the per-shapelet statistics and (series with more
+// than 2048 windows only) the cross-tile arg-min cells
 size_t shapelet_fwd_tc_workspace(const ign_shapelet_desc& d) {
   TcGeo g;
   tc_geo(d, g);
-  return tc_btile_bytes(d, g) + (size_t)d.M * g.nkb * 8 * sizeof(float);
+  return tc_btile_bytes(d, g) + tc_wstat_bytes(d, g) + (g.nseg > 1 ? (size_t)d.B * d.K * d.M * sizeof(unsigned long long) : 0);
 }
 
 bool shapelet_fwd_tc_supported(const ign_shapelet_desc& d) {
   if (d.dist == IGN_DIST_L1) return false;
   if (d.precision != IGN_PREC_3XTF32 && d.precision != IGN_PREC_TF32) return false;
   const int Tw = num_windows(d.T, d.L, d.stride);
-  if (Tw <= 0 || ceil_div(Tw, kShifts) > kRows) return false;     // one sample must fit a 128-row tile
+  if (Tw <= 0 || ceil_div(Tw, kShifts) > 16 * kRows) return false;   // at most 16 tiles (32768 windows) per sample
   TcGeo g;
   tc_geo(d, g);
   return tc_plan_ring(g);
@@ -769,13 +804,15 @@ int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   if (!tc_plan_ring(g)) { set_error("shapelet_forward(tcgen05): L=%d K=%d does not fit shared memory", d.L, d.K); return IGN_ERR_UNSUPPORTED; }
   uint8_t* btiles = reinterpret_cast<uint8_t*>(ws);
   float* wstat = reinterpret_cast<float*>(btiles + tc_btile_bytes(d, g));
+  unsigned long long* packed = g.nseg > 1 ? reinterpret_cast<unsigned long long*>(btiles + tc_btile_bytes(d, g) + tc_wstat_bytes(d, g)) : nullptr;
+  if (packed) IGN_CUDA(cudaMemsetAsync(packed, 0xff, (size_t)d.B * d.K * d.M * sizeof(unsigned long long), st));
   // 1. shifted-shapelet operand + shapelet statistics, once per launch, already in the swizzled tile image
   tc_build_b_kernel<<<dim3(d.M, g.nkb, g.NKB), 128, 0, st>>>(W, btiles, wstat, d.M, d.K, d.L, g.KG, g.nkb, g.NKB, g.N,
                                                             g.split, d.dist, g.s, g.NKBr);
   IGN_CUDA(cudaGetLastError());
   // 2. main kernel: persistent, one CTA per SM (the kernel owns all 512 TMEM columns of its SM)
   const size_t smem = max(tc_smem_fixed(g) + g.nbs * tc_stage_bytes(g), (size_t)118 * 1024);   // > half the SM: one CTA per SM
-  TcArgs a{xn, st0, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, d.stride), btiles, wstat};
+  TcArgs a{xn, st0, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, d.stride), packed, btiles, wstat};
   const int grid = min(sm_count(), g.ntiles);
   auto kern = g.stack ? (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, true>
                          : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, true>
@@ -786,6 +823,11 @@ int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreadsTC, smem, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
+  if (packed) {
+    const int n = d.B * d.K * d.M;
+    tc_finish_kernel<<<ceil_div(n, 256), 256, 0, st>>>(packed, thr, p, dmin, argmin, n, d.K, d.M, d.pool, d.eps);
+    IGN_CUDA(cudaGetLastError());
+  }
   return IGN_OK;
 }
 

@@ -592,3 +592,35 @@ def test_input_gradient_of_the_squared_l2_function_is_zero_as_in_the_reference()
     p, _, _ = shapelet_transform(SeriesPack.from_channel_major(xd), Wd, 1, 1.0, "sql2")
     p.sum().backward()
     assert float(xd.grad.abs().sum()) == 0.0 and float(Wd.grad.abs().sum()) > 0.0      # Shapelet.py:40
+
+
+# Series with more than 2048 windows: a sample spans several 128-row tiles of the tcgen05 forward and its arg-min is
+# merged across them (64-bit atomicMin on (ordered distance | window index), then tc_finish_kernel).
+LONG_ROWS = [
+    # B, M, T,    K, L
+    (3, 2, 2999, 5, 300),      # config-4 geometry T = 2999, L = .1 T: 2700 windows, two tiles per sample
+    (2, 2, 5000, 3, 100),      # 4901 windows: three tiles, the last one short
+    (5, 3, 2200, 10, 120),     # 2081 windows: the second tile holds three window groups; two shapelet blocks
+]
+
+
+@pytest.mark.parametrize("flag", ["cosine", "sql2", "pearson"])
+@pytest.mark.parametrize("shape", LONG_ROWS)
+def test_tcgen05_more_than_2048_windows_vs_oracle(flag, shape):
+    from ctypes import byref
+    from layers import ign_cabi as C
+    B, M, T, K, L = shape
+    mode, dist = MODES[flag]
+    torch.manual_seed(9 + T + L)
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    desc = C.ShapeletDesc(B, M, T, C.padded_len(T), K, L, 1, 0.8, C.DIST[dist], 0, C.PRECISION["3xtf32"])
+    assert C.ENGINE[C.lib.ign_shapelet_engine(byref(desc), 0)] == "tcgen05"
+    ref = O.shapelet_forward(xn, W, 1, 0.8, mode)
+    p, dmin, idx, dW, _ = run_layer(xn, W, 1, 0.8, dist, g=g, precision="3xtf32")
+    assert_close(dmin.reshape(B, -1), ref.dmin, RTOL, ATOL, f"{flag} {shape} dmin")
+    assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, f"{flag} {shape} p")
+    index_parity(idx, ref.argmin_d, ref.d, False, L, f"{flag} {shape} argmin")
+    dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 0.8, mode)
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag} {shape} dW")
+    p2, d2, i2, _, _ = run_layer(xn, W, 1, 0.8, dist, precision="3xtf32")           # inference path, bit-deterministic
+    assert torch.equal(p, p2) and torch.equal(dmin, d2) and torch.equal(idx, i2)
