@@ -131,8 +131,8 @@ int32_t ign_window_stats(const float* xn_dev, int32_t B, int32_t M, int32_t T, i
 
 /* The engine ign_shapelet_forward (backward == 0) or the contraction of ign_shapelet_backward (backward != 0) runs
  * on for this descriptor.  `precision` is a request: IGN_DIST_L1 has no cross term and always runs on the FP32
- * engine, and so do the few geometries the tensor-core kernels do not tile (forward: more than 2048 windows per
- * series).  Callers that report an engine (bench.py, tools/sweep.py) must ask, not assume.
+ * engine; the tensor-core kernels tile every other geometry (any stride, up to 32768 windows per series; DESIGN.md
+ * 3.2).  Callers that report an engine (bench.py, tools/sweep.py) must ask, not assume.
  * Returns an ign_engine_t, or -1 for an invalid descriptor. */
 int32_t ign_shapelet_engine(const ign_shapelet_desc* desc, int32_t backward);
 
@@ -147,8 +147,8 @@ int32_t ign_shapelet_engine(const ign_shapelet_desc* desc, int32_t backward);
  *               ties of p in fp32; backward re-derives the reference's arg-max-of-p one-hot itself.
  *   dstore_dev  optional [B,M,K,Tw] (Tw = ign_padded_windows) all window distances, kept for backward
  *               (the soft-max statistics are recomputed from it); NULL in inference.
- * Engine: precision FP32 -> CUDA-core kernels; 3XTF32 / TF32 -> tcgen05 kernels (any stride; T' <= 2048 —
- * ign_shapelet_engine tells which one a descriptor gets).  The tcgen05 engine needs ign_shapelet_forward_workspace(desc)
+ * Engine: precision FP32 -> CUDA-core kernels; 3XTF32 / TF32 -> tcgen05 kernels (any stride, up to 32768 windows per
+ * series; ign_shapelet_engine tells which one a descriptor gets).  The tcgen05 engine needs ign_shapelet_forward_workspace(desc)
  * bytes of 128-byte-aligned scratch (the pre-swizzled shifted-shapelet tiles); 0 bytes / NULL otherwise. */
 size_t ign_shapelet_forward_workspace(const ign_shapelet_desc* desc);
 int32_t ign_shapelet_forward(const ign_shapelet_desc* desc, const float* xn_dev, const float* st0_dev,

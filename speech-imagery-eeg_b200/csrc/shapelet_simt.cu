@@ -44,6 +44,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 #include <utility>
 
@@ -53,7 +54,9 @@ namespace {
 constexpr int OP_L1 = 0;
 constexpr int OP_DOT = 1;
 constexpr int kMaxThreads = 256;
-constexpr int LT = 8;   // lags per thread in backward (16 was measured slower: fewer items, lower occupancy)
+// Lags per thread in the backward contraction: 8 (16 was measured slower: fewer items, lower occupancy) or 10, whichever
+// fills the thread block and the lag axis better (plan_bwd): L = 100 with K = 5 is 13 tiles x 5 shapelets = 65 threads
+// per slot at 8 lags (195 of 224 lanes, 104 lags computed for 100) and 10 x 5 = 50 at 10 lags (250 of 256, no lag padding).
 
 struct Geo {  // geometry shared by forward and backward
   int B, M, T, Tp, K, L, s;
@@ -63,7 +66,8 @@ struct Geo {  // geometry shared by forward and backward
   int CP;      // backward: pitch of coefficient rows in smem, DP skewed to 12 mod 32 words (conflict-free
                // LDS.128 when consecutive lanes read consecutive shapelets' rows)
   int XQ;      // pitch of one residue row of x in smem
-  int LQ;      // pitch of one residue row of w in smem (ceil(L/s) rounded to 8)
+  int LQ;      // pitch of one residue row of w in smem (ceil(L/s) rounded to 8; backward: to its lag tile LT)
+  int LT;      // backward: lags per thread (8 or 10)
   int KK, KB, nkb;
   int NB;      // series rows resident per pass
   int dbuf;    // forward: series rows double buffered (cp.async one pass ahead)
@@ -482,6 +486,9 @@ __device__ __forceinline__ void cp_async16_pool(void* dst, const void* src) {
 // Persistent warps: every warp walks rows  w, w + nwarps_total, ...  with the NEXT row's distances already in flight
 // (cp.async into the other half of its shared-memory slot) while it works on the current one — the kernel is
 // bound by how many bytes it keeps in flight, not by instructions (issue 70 %, 4.0 TB/s before this change).
+template <int DIST>
+__device__ __forceinline__ float pool_emit(float c, float d, float s0, float s1, float wst, float& sc0, float& sc1);
+
 template <int POOL, int DIST>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolArgs a, int rows) {
   extern __shared__ __align__(16) float prow[];          // [warps][2][DP]
@@ -513,37 +520,64 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
   int ih;
   if (POOL == IGN_POOL_LTS_MIN) { shift = a.dmin[o]; ih = a.argmin[o]; }
   __syncwarp();
+  // Both passes walk the row in float4 chunks (lane owns chunks lane, lane + 32, ...): 128-bit shared-memory reads and
+  // global stores, and in pass 2 the window-statistics loads of kPoolUnroll chunks are issued before any of them is
+  // used.  (Element-wise loops with one statistics load per window left 14 dependent L2 round trips per row: the cosine
+  // instantiation ran at 1.0-1.3 TB/s for T' = 1401 ... 1801, against 4.6 TB/s for L1, which loads no statistics.)
+  const float4* dr4 = reinterpret_cast<const float4*>(dr);
+  const int nvf = g.Tw >> 2;                             // whole chunks; chunk nvf (if Tw % 4) is masked
+  const int nv = g.Ts >> 2;
   if (POOL == IGN_POOL_RBF_MAX) {
     float pmx = -1.f; int imx = 0x7fffffff;
-#pragma unroll 4
-    for (int t = lane; t < g.Tw; t += 32) {
-      const float d = dr[t];
+    auto ev = [&](float d, int t) {
       const float p = fast_ex2(qscale * d * d);
       const float e = fast_ex2(p * kLog2e);
       Zs += e; S1s = fmaf(e, p, S1s);
       if (p > pmx) { pmx = p; imx = t; }
+    };
+#pragma unroll 2
+    for (int c = lane; c < nvf; c += 32) {
+      const float4 d = dr4[c];
+      ev(d.x, 4 * c); ev(d.y, 4 * c + 1); ev(d.z, 4 * c + 2); ev(d.w, 4 * c + 3);
+    }
+    if (nvf < nv && lane == (nvf & 31)) {                // the lane that owns the partial chunk (it comes last in its order)
+      const float4 d = dr4[nvf];
+      const int t = 4 * nvf;
+      ev(d.x, t);
+      if (t + 1 < g.Tw) ev(d.y, t + 1);
+      if (t + 2 < g.Tw) ev(d.z, t + 2);
     }
     ih = warp_argmax_first(pmx, imx).i;
   } else {
-#pragma unroll 4
-    for (int t = lane; t < g.Tw; t += 32) {
-      const float d = dr[t];
+    auto ev = [&](float d) {
       const float e = fast_ex2((shift - d) * kLog2e);
       Zs += e; S1s = fmaf(e, d, S1s);
+    };
+#pragma unroll 2
+    for (int c = lane; c < nvf; c += 32) {
+      const float4 d = dr4[c];
+      ev(d.x); ev(d.y); ev(d.z); ev(d.w);
+    }
+    if (nvf < nv && lane == (nvf & 31)) {
+      const float4 d = dr4[nvf];
+      const int t = 4 * nvf;
+      ev(d.x);
+      if (t + 1 < g.Tw) ev(d.y);
+      if (t + 2 < g.Tw) ev(d.z);
     }
   }
   Zs = warp_sum(Zs); S1s = warp_sum(S1s);
   const float invZ = 1.f / Zs, bar = S1s * invZ;
   const float wst = (DIST == IGN_DIST_PEARSON) ? a.wstat[(size_t)k * g.M + m] : 0.f;
-  const size_t srow = (size_t)bm * a.SP;
+  const size_t srow = (size_t)bm * a.SP;                 // SP % 16 == 0: float4-aligned rows
+  const float4* s0r4 = reinterpret_cast<const float4*>(a.st0 + srow);
+  const float4* s1r4 = reinterpret_cast<const float4*>(a.st1 + srow);
   float* dst = a.coef + (size_t)row * g.Ts;
   // constants folded once per row: c_t = gk * (hard_t + soft_t (p_t - bar)) * p_t * (-2 eps^2 d_t)   (rbf_max)
   //                                c_t = gk * (hard_t - soft_t (d_t - bar))                             (lts_min)
   const float gm = gk * (-2.f * eps * eps);
   float sc0 = 0.f, sc1 = 0.f;
-#pragma unroll 4
-  for (int t = lane; t < g.Tw; t += 32) {
-    const float d = dr[t];
+  auto emit = [&](float d, int t, float sxn, float mu) -> float {
     float c;
     if (POOL == IGN_POOL_RBF_MAX) {
       const float p = fast_ex2(qscale * d * d);
@@ -553,22 +587,44 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const Geo g, const PoolAr
       const float soft = fast_ex2((shift - d) * kLog2e) * invZ;
       c = gk * fmaf(-soft, d - bar, t == ih ? 1.f : 0.f);
     }
-    float coef;
-    if (DIST == IGN_DIST_L1 || DIST == IGN_DIST_SQL2) {
-      coef = c; sc0 += c;
-    } else if (DIST == IGN_DIST_COSINE) {
-      coef = c * a.st0[srow + t];
-      sc0 = fmaf(c, 1.f - d, sc0);
-    } else {
-      const float sxn = a.st0[srow + t], mu = a.st1[srow + t];     // ||x_w-mu||, mu
-      const float D = sxn * wst + 1e-8f;                            // wst = ||w-mean||
-      coef = __fdividef(c, D);
-      sc0 = fmaf(coef, mu, sc0);
-      sc1 += __fdividef(c * (1.f - d) * sxn, wst * D);              // Sx/(root*D) = ||x||/(||w|| D)
+    return pool_emit<DIST>(c, d, sxn, mu, wst, sc0, sc1);
+  };
+  constexpr bool kS0 = DIST == IGN_DIST_COSINE || DIST == IGN_DIST_PEARSON;
+  constexpr bool kS1 = DIST == IGN_DIST_PEARSON;
+  constexpr int kPoolUnroll = 4;
+  for (int c0 = lane; c0 < nvf; c0 += 32 * kPoolUnroll) {
+    float4 s0[kPoolUnroll], s1[kPoolUnroll];
+#pragma unroll
+    for (int u = 0; u < kPoolUnroll; ++u) {
+      const int c = min(c0 + 32 * u, nv - 1);            // clamped: in range, ignored below
+      s0[u] = kS0 ? __ldg(s0r4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s1[u] = kS1 ? __ldg(s1r4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    dst[t] = coef;
+#pragma unroll
+    for (int u = 0; u < kPoolUnroll; ++u) {
+      const int c = c0 + 32 * u;
+      if (c < nvf) {
+        const float4 d = dr4[c];
+        float4 o;
+        o.x = emit(d.x, 4 * c, s0[u].x, s1[u].x);
+        o.y = emit(d.y, 4 * c + 1, s0[u].y, s1[u].y);
+        o.z = emit(d.z, 4 * c + 2, s0[u].z, s1[u].z);
+        o.w = emit(d.w, 4 * c + 3, s0[u].w, s1[u].w);
+        *reinterpret_cast<float4*>(dst + 4 * c) = o;
+      }
+    }
   }
-  if (lane < g.Ts - g.Tw) dst[g.Tw + lane] = 0.f;                    // pad windows (at most 3)
+  if (nvf < nv && lane == (nvf & 31)) {                  // partial chunk: pad windows (at most 3) get 0
+    const float4 d = dr4[nvf];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 s0 = kS0 ? __ldg(s0r4 + nvf) : z, s1 = kS1 ? __ldg(s1r4 + nvf) : z;
+    const int t = 4 * nvf;
+    float4 o = z;
+    o.x = emit(d.x, t, s0.x, s1.x);
+    if (t + 1 < g.Tw) o.y = emit(d.y, t + 1, s0.y, s1.y);
+    if (t + 2 < g.Tw) o.z = emit(d.z, t + 2, s0.z, s1.z);
+    *reinterpret_cast<float4*>(dst + t) = o;
+  }
   sc0 = warp_sum(sc0); sc1 = warp_sum(sc1);
   if (lane == 0) { a.rowsc[(size_t)row * 2] = sc0; a.rowsc[(size_t)row * 2 + 1] = sc1; }
   __syncwarp();                                         // everyone is done reading this slot half before it is refilled
@@ -892,7 +948,7 @@ __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict_
 }
 
 // ---- contraction kernel: dW partials from the coefficients and the series (pure FP32-pipe work) ----
-template <int OP>
+template <int OP, int LT>
 __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int m = blockIdx.x;
@@ -924,7 +980,7 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     for (int i = threadIdx.x; i < 2 * cb_sz; i += nthr) cb0[i] = 0.f;
   }
 
-  // this thread's fixed tile: 8 lags of one shapelet, one (sample slot, t-segment)
+  // this thread's fixed tile: LT lags of one shapelet, one (sample slot, t-segment)
   const bool active = threadIdx.x < nitem;
   int lt = 0, kl = 0, seg = 0, bl = 0;
   if (active) {
@@ -991,45 +1047,63 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     }
     const float* xs = xs0 + buf * xs_sz;
     const float* cbuf = cb0 + buf * cb_sz;
-    // ---- contraction over windows, sliding along t with a 12-register ring of x
+    // ---- contraction over windows, sliding along t with a ring of LT + 4 registers of x: step j of a revolution
+    // (4 windows) reads the ring at base 4 j mod RING and refills the four slots it frees
     if (active && bl < nb && ta < tb && k0 + kl < g.K) {
       const float* xr = xs + ((size_t)bl * g.s + r) * g.XQ + q0;
       const float* cb = cbuf + ((size_t)bl * g.KB + kl) * g.CP;
       const bool exact = OP == OP_L1 && (a.tie == nullptr || a.tie[((size_t)(b0 + bl) * g.M + m) * g.nkb + kblk] != 0);
-      constexpr int RING = LT + 4;      // 12: three 4-window steps per ring revolution
-      static_assert(LT == 8, "the sweep below unrolls RING/4 == 3 steps");
+      constexpr int RING = LT + 4;
+      constexpr int NSTEP = RING % 4 == 0 ? RING / 4 : RING / 2;    // steps per ring revolution: 3 (LT = 8), 7 (LT = 10)
+      static_assert(LT % 2 == 0 && (4 * NSTEP) % RING == 0, "ring revolution");
       float xv[RING];
+      if (LT % 4 == 0) {
 #pragma unroll
-      for (int i = 0; i < LT; i += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + ta + i);
-        xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+        for (int i = 0; i < LT; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(xr + ta + i);
+          xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+        }
+      } else {                                          // q0 is a multiple of LT: 8-byte aligned only
+#pragma unroll
+        for (int i = 0; i < LT; i += 2) {
+          const float2 v = *reinterpret_cast<const float2*>(xr + ta + i);
+          xv[i] = v.x; xv[i + 1] = v.y;
+        }
       }
-#define IGN_BWD_STEP(EX, BASE, TQ)                                                           \
-      {                                                                                      \
-        float4 nx = *reinterpret_cast<const float4*>(xr + (TQ) + LT);                        \
-        xv[((BASE) + LT) % RING] = nx.x; xv[((BASE) + LT + 1) % RING] = nx.y;                \
-        xv[((BASE) + LT + 2) % RING] = nx.z; xv[((BASE) + LT + 3) % RING] = nx.w;            \
-        const float4 c4 = *reinterpret_cast<const float4*>(cb + (TQ));                       \
-        const float4 h4 = make_float4(0.5f * c4.x, 0.5f * c4.y, 0.5f * c4.z, 0.5f * c4.w);   \
-        _Pragma("unroll") for (int i = 0; i < LT; ++i) {                                     \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.x, h4.x, xv[((BASE) + i + 0) % RING], wreg[i]); \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.y, h4.y, xv[((BASE) + i + 1) % RING], wreg[i]); \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.z, h4.z, xv[((BASE) + i + 2) % RING], wreg[i]); \
-          acc[i] = bwd_op<OP, EX>(acc[i], c4.w, h4.w, xv[((BASE) + i + 3) % RING], wreg[i]); \
-        }                                                                                    \
-      }
-#define IGN_BWD_SWEEP(EX)                                                                    \
-      {                                                                                      \
-        int t = ta;                                                                          \
-        for (; t + 12 <= tb; t += 12) {                                                      \
-          IGN_BWD_STEP(EX, 0, t) IGN_BWD_STEP(EX, 4, t + 4) IGN_BWD_STEP(EX, 8, t + 8)       \
-        }                                                                                    \
-        if (t + 4 <= tb) { IGN_BWD_STEP(EX, 0, t) t += 4;                                    \
-          if (t + 4 <= tb) { IGN_BWD_STEP(EX, 4, t) t += 4; } }                              \
-      }
-      if (exact) IGN_BWD_SWEEP(true) else IGN_BWD_SWEEP(false)
-#undef IGN_BWD_SWEEP
-#undef IGN_BWD_STEP
+      auto step = [&](auto ex, int base, int tq) {       // `base` is a constant after unrolling: xv stays in registers
+        constexpr bool EX = decltype(ex)::value;
+        float n0, n1, n2, n3;
+        if (LT % 4 == 0) {
+          const float4 nx = *reinterpret_cast<const float4*>(xr + tq + LT);
+          n0 = nx.x; n1 = nx.y; n2 = nx.z; n3 = nx.w;
+        } else {
+          const float2 na = *reinterpret_cast<const float2*>(xr + tq + LT);
+          const float2 nb2 = *reinterpret_cast<const float2*>(xr + tq + LT + 2);
+          n0 = na.x; n1 = na.y; n2 = nb2.x; n3 = nb2.y;
+        }
+        xv[(base + LT) % RING] = n0; xv[(base + LT + 1) % RING] = n1;
+        xv[(base + LT + 2) % RING] = n2; xv[(base + LT + 3) % RING] = n3;
+        const float4 c4 = *reinterpret_cast<const float4*>(cb + tq);
+        const float4 h4 = make_float4(0.5f * c4.x, 0.5f * c4.y, 0.5f * c4.z, 0.5f * c4.w);
+#pragma unroll
+        for (int i = 0; i < LT; ++i) {
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.x, h4.x, xv[(base + i + 0) % RING], wreg[i]);
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.y, h4.y, xv[(base + i + 1) % RING], wreg[i]);
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.z, h4.z, xv[(base + i + 2) % RING], wreg[i]);
+          acc[i] = bwd_op<OP, EX>(acc[i], c4.w, h4.w, xv[(base + i + 3) % RING], wreg[i]);
+        }
+      };
+      auto sweep = [&](auto ex) {
+        int t = ta;
+        for (; t + 4 * NSTEP <= tb; t += 4 * NSTEP) {
+#pragma unroll
+          for (int j = 0; j < NSTEP; ++j) step(ex, (4 * j) % RING, t + 4 * j);
+        }
+#pragma unroll
+        for (int j = 0; j < NSTEP - 1; ++j)             // segment lengths are multiples of 4
+          if (t + 4 * (j + 1) <= tb) step(ex, (4 * j) % RING, t + 4 * j);
+      };
+      if (exact) sweep(std::true_type{}); else sweep(std::false_type{});
     }
     if (dbuf) buf ^= 1;
   }
@@ -1117,6 +1191,7 @@ bool base_geo(const ign_shapelet_desc& d, Geo& g) {
   g.CP = g.DP + ((12 - g.DP % 32) + 32) % 32;
   const int Lq = ceil_div(d.L, d.stride);
   g.LQ = round_up(Lq, 8);
+  g.LT = 8;
   g.XQ = round_up(max(g.DP + g.LQ + 8, ceil_div(d.T, d.stride) + 8), 4);   // covers t + LT + 3 + q0 < DP + LQ
   g.KK = pick_kk(d.K);
   g.dist = d.dist; g.pool = d.pool; g.eps = d.eps;
@@ -1176,6 +1251,7 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
   int KB = min(Kpad, 8 * g.KK);
   while (KB > g.KK && fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_soft) KB -= g.KK;
   if (fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_hard) return false;
+  KB = round_up(ceil_div(Kpad, ceil_div(Kpad, KB)), g.KK);    // balanced blocks: K = 100 as 35 + 35 + 30, not 40 + 40 + 20
   const size_t cap = fwd_smem_floats(g, 1, KB, ntile) * 4 > cap_soft ? cap_hard : cap_soft;
   const int nkc = KB / g.KK;
   // resident rows: fill whole rounds of the thread block (idle lanes in the last round are the waste).  Double
@@ -1220,18 +1296,23 @@ size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
   const size_t mult = g.s == 1 ? 2 : 1;       // double-buffered for unit stride
   const size_t xs = (size_t)NB * g.s * g.XQ, cb = (size_t)NB * KB * g.CP;
   size_t cbt = mult * cb;
-  if (cbt < (size_t)kMaxThreads * LT) cbt = (size_t)kMaxThreads * LT;
+  if (cbt < (size_t)kMaxThreads * g.LT) cbt = (size_t)kMaxThreads * g.LT;
   return mult * xs + cbt + (size_t)KB * g.s * g.LQ + KB;
 }
 
-bool plan_bwd(Geo& g, BwdPlan& bp) {
+// One candidate lag-tile width.  `eff` = share of the launched lanes x lags that are real work.
+bool plan_bwd_lt(Geo& g, BwdPlan& bp, int LT, double& eff) {
   const size_t cap = (size_t)max_optin_smem() - 1024;
   const size_t cap_soft = 56 * 1024;     // aim for >= 4 CTAs per SM
+  g.LT = LT;
+  g.LQ = round_up(ceil_div(g.L, g.s), LT);
+  g.XQ = round_up(max(g.DP + g.LQ + 8, ceil_div(g.T, g.s) + 8), 4);   // covers t + LT + 3 + q0 < DP + LQ
   const int ntl_all = g.s * g.LQ / LT;
   // shapelet block and lag block: KB * tlb threads cover one (sample, segment) slot
   int KB = min(g.K, 8);
   while (KB > 1 && bwd_smem_floats(g, 1, KB) * 4 > cap_soft) --KB;
   if (bwd_smem_floats(g, 1, KB) * 4 > cap) return false;
+  KB = ceil_div(g.K, ceil_div(g.K, KB));  // balanced blocks: K = 10 as 5 + 5, not 8 + 2 (idle lanes in the short block)
   int tlb = min(ntl_all, kMaxThreads / KB);
   const int nlb = ceil_div(ntl_all, tlb);
   tlb = ceil_div(ntl_all, nlb);          // balance the lag blocks
@@ -1257,7 +1338,21 @@ bool plan_bwd(Geo& g, BwdPlan& bp) {
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
   plan_chunks(g, g.M * g.nkb * nlb, bestNB);
   bp.nchunk = g.nchunk;
+  const int lags_done = g.s == 1 ? nlb * tlb * LT : g.s * g.LQ;
+  eff = (double)(bestNB * bestSeg * per_slot) / bp.threads * (double)g.L / (double)lags_done;
   return true;
+}
+
+// Lag tile: 8, or 10 where that wastes fewer lanes and padded lags (unit stride only; IGN_BWD_LT=8|10 forces one).
+bool plan_bwd(Geo& g, BwdPlan& bp) {
+  static const int lt_env = getenv("IGN_BWD_LT") ? atoi(getenv("IGN_BWD_LT")) : 0;
+  double e8 = 0.0, e10 = 0.0;
+  if (g.s != 1 || lt_env == 8) return plan_bwd_lt(g, bp, 8, e8);
+  Geo g10 = g; BwdPlan bp10;
+  const bool ok10 = plan_bwd_lt(g10, bp10, 10, e10);
+  const bool ok8 = plan_bwd_lt(g, bp, 8, e8);
+  if (ok10 && (!ok8 || lt_env == 10 || e10 > e8 + 0.02 || (e10 > e8 - 0.005 && bp10.nlb < bp.nlb))) { g = g10; bp = bp10; return true; }
+  return ok8;
 }
 
 template <typename Kern>
@@ -1293,7 +1388,10 @@ FwdKernel fwd_kernel(bool l1, int KK, int TT) {
   return TT == 8 ? shapelet_fwd_kernel<OP_DOT, 4, 8> : shapelet_fwd_kernel<OP_DOT, 4, 4>;
 }
 
-BwdKernel bwd_kernel(int dist) { return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1> : shapelet_bwd_kernel<OP_DOT>; }
+BwdKernel bwd_kernel(int dist, int LT) {
+  if (LT == 10) return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1, 10> : shapelet_bwd_kernel<OP_DOT, 10>;
+  return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1, 8> : shapelet_bwd_kernel<OP_DOT, 8>;
+}
 
 bool debug_plan_on() {
   static const bool on = getenv("IGN_DEBUG_PLAN") != nullptr;
@@ -1381,8 +1479,8 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   // current one (layers/shapelet_ops.py).
   Geo g; BwdPlan bp;
   if (!base_geo(d, g)) { set_error("shapelet_backward: T=%d < L=%d", d.T, d.L); return IGN_ERR_INVALID; }
-  const BwdKernel kern = bwd_kernel(d.dist);
   if (!plan_bwd(g, bp)) { set_error("shapelet_backward: problem does not fit shared memory (T=%d L=%d)", d.T, d.L); return IGN_ERR_UNSUPPORTED; }
+  const BwdKernel kern = bwd_kernel(d.dist, g.LT);
   const BwdWorkspace wo = bwd_workspace(d, g, bp);
   if (ws_bytes < wo.total * sizeof(float)) { set_error("shapelet_backward: workspace %zu < %zu bytes", ws_bytes, wo.total * sizeof(float)); return IGN_ERR_INVALID; }
   if (((uintptr_t)ws & 15) != 0) { set_error("shapelet_backward: workspace must be 16-byte aligned"); return IGN_ERR_INVALID; }
