@@ -464,7 +464,7 @@ __device__ __forceinline__ float bwd_op(float acc, float c, float hc, float x, f
 }
 
 constexpr unsigned kHashEmpty = 0x7fc00001u;   // a NaN payload: never equal to a series value
-constexpr int kTieBitmapLog2 = 19;             // 2^19-bit (64 KB) filter in front of the exact hash set
+constexpr int kTieBitmapLog2 = 18;             // 2^18-bit (32 KB) filter in front of the exact hash set (2500 values: 1 % false hits)
 constexpr int kTieBitmapWords = (1 << kTieBitmapLog2) / 32;
 __device__ __forceinline__ unsigned hash_key(float v) {
   unsigned b = __float_as_uint(v);
@@ -1008,18 +1008,18 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     const int nb = min(g.NB, bend - b0);
     float* xd = xs0 + buf * xs_sz;
     float* cd = cb0 + buf * cb_sz;
-    const int xrow = g.Tp / 4;
-    for (int i = threadIdx.x; i < nb * xrow; i += nthr) {
-      const int rbl = i / xrow, c = i - rbl * xrow;
-      cp_async16(xd + rbl * g.XQ + c * 4, a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp + c * 4);
-    }
-    const int crow = g.Ts / 4;
+    // row by row (a handful of rows per pass): no index division per 16-byte copy — the flat loop spent ~40 issue
+    // slots per copy, 5 % of the kernel's instructions at L = 100
+    const int xrow = g.Tp / 4, crow = g.Ts / 4;
     const int kvalid = min(g.KB, g.K - k0);
-    for (int i = threadIdx.x; i < nb * kvalid * crow; i += nthr) {
-      const int row = i / crow, c = i - row * crow;
-      const int rbl = row / kvalid, rkl = row - rbl * kvalid;
-      cp_async16(cd + ((size_t)rbl * g.KB + rkl) * g.CP + c * 4,
-                 a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0 + rkl) * g.Ts + c * 4);
+    for (int rbl = 0; rbl < nb; ++rbl) {
+      const float* xsrc = a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp;
+      float* xdst = xd + rbl * g.XQ;
+      for (int c = threadIdx.x; c < xrow; c += nthr) cp_async16(xdst + c * 4, xsrc + c * 4);
+      const float* csrc = a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0) * g.Ts;
+      float* cdst = cd + (size_t)rbl * g.KB * g.CP;
+      for (int rkl = 0; rkl < kvalid; ++rkl)
+        for (int c = threadIdx.x; c < crow; c += nthr) cp_async16(cdst + rkl * g.CP + c * 4, csrc + (size_t)rkl * g.Ts + c * 4);
     }
   };
 
@@ -1136,7 +1136,9 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   }
 }
 
-// dW[k,m,:] from the per-chunk partial contractions and the per-row scalars.  One warp per (k,m) row.
+// dW[k,m,:] from the per-chunk partial contractions and the per-row scalars.  One warp per (k,m) row and block of 128
+// lags (gridDim.y blocks); the chunk partials are summed in chunk order, eight loads in flight (one dependent load
+// per chunk left L = 500 with its 29 chunks at 0.5 TB/s).
 __global__ void __launch_bounds__(256) shapelet_bwd_finalize(const float* __restrict__ W,
                                                             const float* __restrict__ part,
                                                             const float* __restrict__ rowsc,
@@ -1162,9 +1164,18 @@ __global__ void __launch_bounds__(256) shapelet_bwd_finalize(const float* __rest
     inv_nw = 1.f / fmaxf(sqrtf(b2), 1e-8f);
   }
   const float Lf = (float)L;
-  for (int l = lane; l < L; l += 32) {
+  const int lbeg = blockIdx.y * 128, lend = min(L, lbeg + 128);
+  for (int l = lbeg + lane; l < lend; l += 32) {
     float G = 0.f;
-    for (int c = 0; c < nchunk; ++c) G += part[((size_t)c * K * M + row) * L + l];
+    const float* pl = part + (size_t)row * L + l;
+    const size_t cstride = (size_t)K * M * L;
+    for (int c = 0; c < nchunk; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = c + u < nchunk ? __ldg(pl + (size_t)(c + u) * cstride) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) G += v[u];         // chunk order; + 0.f past the end changes nothing
+    }
     float o;
     if (dist == IGN_DIST_L1) o = -(2.f * G - s0) / Lf;
     else if (dist == IGN_DIST_SQL2) o = (2.f / Lf) * (w[l] * s0 - G);
@@ -1287,9 +1298,9 @@ struct BwdPlan { int nseg, nlb, tlb, nchunk, threads, hcap; size_t smem_bytes; }
 
 int bwd_hash_cap(const Geo& g, int KB) {
   if (g.dist != IGN_DIST_L1) return 0;
-  size_t need = 4 * (size_t)KB * g.L, cap = 256;
+  size_t need = 2 * (size_t)KB * g.L, cap = 256;   // load factor <= 1/2; the set is probed only after a filter hit
   while (cap < need) cap <<= 1;
-  return cap <= 32768 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path (128 KB + 64 KB smem)
+  return cap <= 32768 ? (int)cap : 0;      // larger slabs: skip the check, always take the exact path (128 KB + 32 KB smem)
 }
 
 size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
@@ -1535,8 +1546,10 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   }
   if (use_tie) {     // L1: which series rows can hold a value equal to one of their shapelet block's values
     PhaseScope ph(PH_TIE, st);
-    const int bsplit = max(1, min(d.B, ceil_div(sm_count(), d.M * g.nkb)));
     const size_t hs = ((size_t)bp.hcap + kTieBitmapWords) * sizeof(unsigned);
+    // one warp walks a series row per load round trip: the scan is latency-bound, so fill every CTA slot the set leaves
+    const int per_sm = max(1, min(5, (int)((size_t)max_smem_per_sm() / (hs + 1024))));
+    const int bsplit = max(1, min(ceil_div(d.B, 8), ceil_div(per_sm * sm_count(), d.M * g.nkb)));
     int rc0 = set_smem(tie_check_kernel, hs);
     if (rc0) return rc0;
     tie_check_kernel<<<dim3(d.M, g.nkb, bsplit), 256, hs, st>>>(xn, W, tflags, d.B, d.M, d.T, d.Tp, d.K, d.L, g.KB,
@@ -1552,7 +1565,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
     { PhaseScope ph(PH_CONTRACT, st); rc = launch_shapelet_bwd_tc(d, xn, base + wo.coef, base + wo.part, st); }
     if (rc) return rc;
     PhaseScope ph(PH_FINALIZE, st);
-    shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
+    shapelet_bwd_finalize<<<dim3(ceil_div(d.K * d.M, 8), ceil_div(d.L, 128)), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
                                                                 d.M, d.L, shapelet_bwd_tc_chunks(d), d.dist);
     IGN_CUDA(cudaGetLastError());
     return IGN_OK;
@@ -1565,7 +1578,7 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   if (rc) return rc;
   // 3. combine
   PhaseScope ph(PH_FINALIZE, st);
-  shapelet_bwd_finalize<<<ceil_div(d.K * d.M, 8), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
+  shapelet_bwd_finalize<<<dim3(ceil_div(d.K * d.M, 8), ceil_div(d.L, 128)), 256, 0, st>>>(W, base + wo.part, base + wo.rowsc, dW, d.B, d.K,
                                                               d.M, d.L, bp.nchunk, d.dist);
   IGN_CUDA(cudaGetLastError());
   return IGN_OK;

@@ -120,7 +120,8 @@ def test_lts_layer_vs_oracle(flag, shape):
 # Pooling backward (pool_bwd_reg_kernel): the row is split into whole 128-window float4 chunks and a scalar tail of
 # 32-window sub-chunks, with one instantiation per register budget (NCH = 2, 4, 6, 8) and the generic two-pass kernel
 # above 1024 windows — cover every boundary of that split.
-POOL_TW = [1, 31, 32, 33, 127, 128, 129, 256, 300, 512, 517, 768, 769, 1023, 1024, 1025, 1500]
+# The generic kernel walks float4 chunks with a masked last chunk: 1, 2, 3 valid windows in it (1025, 1026, 1027, 2047).
+POOL_TW = [1, 31, 32, 33, 127, 128, 129, 256, 300, 512, 517, 768, 769, 1023, 1024, 1025, 1026, 1027, 1500, 2047, 2050]
 
 
 @pytest.mark.parametrize("flag", ["euclidean", "sql2", "cosine", "pearson", "lts"])
@@ -144,6 +145,20 @@ def test_pool_backward_row_geometries(flag, Tw):
         assert_close(p.reshape(B, -1), ref.p, RTOL, ATOL, f"{flag} p Tw={Tw}")
         dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 0.9, mode)
     assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag} dW Tw={Tw}")
+
+
+@pytest.mark.parametrize("flag", ["euclidean", "cosine"])
+@pytest.mark.parametrize("K,L", [(5, 10), (5, 50), (5, 95), (5, 100), (5, 101), (5, 250), (8, 100), (10, 30), (3, 64)])
+def test_backward_lag_tile_widths(flag, K, L):
+    """The FP32 contraction gives each thread 8 or 10 lags, whichever wastes fewer lanes and padded lags for the
+    (K, L) at hand (plan_bwd): shapelet lengths on and off both tile widths, block sizes that fill and do not fill."""
+    torch.manual_seed(77 + K * 1000 + L)
+    B, M, T = 3, 3, 300
+    xn, W, g = torch.randn(B, M, T), torch.randn(K, M, L), torch.randn(B, K, M)
+    mode, dist = MODES[flag]
+    _, _, _, dW, _ = run_layer(xn, W, 1, 0.8, dist, g=g)
+    dW_ref, _ = O.shapelet_backward_formula(xn.double(), W.double(), g.double(), 1, 0.8, mode)
+    assert_close(dW, dW_ref, 1e-4, 1e-4 * float(dW_ref.abs().max()), f"{flag} dW K={K} L={L}")
 
 
 def test_long_shapelet_needs_lag_blocks():
