@@ -303,6 +303,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -333,8 +336,8 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
   const int nitem = g.NB * ntile * nkc;
   const float Lf = 1.f / (float)g.L;   // 1/L
 
-  // Unit stride: series (and window-statistics) rows are double buffered and fetched with cp.async one pass ahead,
-  // so the load of pass i+1 hides under the distance loop of pass i (the exposed load + barrier phases cost short
+  // Series (and window-statistics) rows are double buffered and fetched with cp.async one pass ahead (strided groups
+  // de-interleave with 4-byte copies), so the load of pass i+1 hides under the distance loop of pass i (the exposed load + barrier phases cost short
   // shapelets ~8 %: FMA pipe 74 % at L=100 against 82 % at L=500 before this change).
   const bool dbuf = g.dbuf != 0;
   const int xs_sz = g.NB * g.s * g.XQ;
@@ -344,9 +347,24 @@ __global__ void __launch_bounds__(kMaxThreads, 2) shapelet_fwd_kernel(const Geo 
     const int nb = min(g.NB, bend - b0);
     float* xd = buf ? xs1 : xs;
     const int xrow = g.Tp / 4;
-    for (int i = threadIdx.x; i < nb * xrow; i += blockDim.x) {
-      const int rbl = i / xrow, c = i - rbl * xrow;
-      cp_async16(xd + rbl * g.XQ + c * 4, a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp + c * 4);
+    if (g.s == 1) {
+      for (int i = threadIdx.x; i < nb * xrow; i += blockDim.x) {
+        const int rbl = i / xrow, c = i - rbl * xrow;
+        cp_async16(xd + rbl * g.XQ + c * 4, a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp + c * 4);
+      }
+    } else {                                            // de-interleave: sample t -> residue row t % s, slot t / s
+      const int nthr = blockDim.x;
+      const int dq = nthr / g.s, dr = nthr - dq * g.s;
+      for (int rbl = 0; rbl < nb; ++rbl) {
+        const float* xsrc = a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp;
+        float* xdst = xd + (size_t)rbl * g.s * g.XQ;
+        int q = threadIdx.x / g.s, r = threadIdx.x - q * g.s;
+        for (int t = threadIdx.x; t < g.T; t += nthr) {
+          cp_async4(xdst + r * g.XQ + q, xsrc + t);
+          q += dq; r += dr;
+          if (r >= g.s) { r -= g.s; ++q; }
+        }
+      }
     }
     if (OP != OP_L1) {
       float* sd = buf ? st1 : st0;
@@ -464,7 +482,10 @@ __device__ __forceinline__ float bwd_op(float acc, float c, float hc, float x, f
 }
 
 constexpr unsigned kHashEmpty = 0x7fc00001u;   // a NaN payload: never equal to a series value
-constexpr int kTieBitmapLog2 = 18;             // 2^18-bit (32 KB) filter in front of the exact hash set (2500 values: 1 % false hits)
+// 2^18-bit (32 KB) two-hash Bloom filter in front of the exact hash set.  A false hit sends the whole warp through the
+// probe loop, so what matters is the rate per 32 elements: 2500 values (K = 5, L = 500) give 0.04 % per element with two
+// hashes (1 % per warp step) against 1 % (26 %) with one; 20000 values (L = 2000, strided groups) 2 % against 7 %.
+constexpr int kTieBitmapLog2 = 18;
 constexpr int kTieBitmapWords = (1 << kTieBitmapLog2) / 32;
 __device__ __forceinline__ unsigned hash_key(float v) {
   unsigned b = __float_as_uint(v);
@@ -916,8 +937,9 @@ __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict_
     const int hk = i / L, l = i - hk * L;
     if (k0 + hk >= K) continue;
     const unsigned key = hash_key(__ldg(W + ((size_t)(k0 + hk) * M + m) * L + l));
-    const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2);
+    const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2), hb2 = (key * 0xC2B2AE35u) >> (32 - kTieBitmapLog2);
     atomicOr(&bitmap[hb >> 5], 1u << (hb & 31));
+    atomicOr(&bitmap[hb2 >> 5], 1u << (hb2 & 31));
     unsigned h = hash_slot(key, mask);
     while (true) {
       const unsigned old = atomicCAS(&hset[h], kHashEmpty, key);
@@ -945,8 +967,8 @@ __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict_
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const unsigned key = hash_key(vv[e]);
-          const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2);
-          if ((bitmap[hb >> 5] >> (hb & 31)) & 1u) {          // rare: confirm in the exact set
+          const unsigned hb = (key * 0x85EBCA6Bu) >> (32 - kTieBitmapLog2), hb2 = (key * 0xC2B2AE35u) >> (32 - kTieBitmapLog2);
+          if ((bitmap[hb >> 5] >> (hb & 31)) & (bitmap[hb2 >> 5] >> (hb2 & 31)) & 1u) {   // rare: confirm in the exact set
             unsigned h = hash_slot(key, mask);
             while (true) {
               const unsigned q = hset[h];
@@ -981,16 +1003,13 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   const int nslot = g.NB * a.nseg;
   const int nitem = nslot * ntl * g.KB;                   // <= blockDim.x by construction
 
-  // unit stride: series and coefficient rows are double-buffered and prefetched with cp.async one pass ahead
-  const bool dbuf = g.s == 1;
+  // series and coefficient rows are double-buffered and prefetched with cp.async one pass ahead (strided groups
+  // de-interleave the series with 4-byte copies); single-buffered only when two buffers do not fit shared memory
+  const bool dbuf = g.dbuf != 0;
   const int xs_sz = g.NB * g.s * g.XQ;
   const int cb_sz = max(g.NB * g.KB * g.CP, dbuf ? 0 : kMaxThreads * LT);
   float* xs0 = smem;
   float* cb0 = xs0 + (dbuf ? 2 : 1) * xs_sz;
-  float* ws = cb0 + max((dbuf ? 2 : 1) * cb_sz, kMaxThreads * LT);
-  float* wstat = ws + g.KB * g.s * g.LQ;
-
-  if (OP == OP_L1) load_shapelets(g, a.W, m, k0, ws, wstat);
   if (dbuf) {   // zero once: pad columns (series tail, DP - Ts) are never written by the prefetch
     for (int i = threadIdx.x; i < 2 * xs_sz; i += nthr) xs0[i] = 0.f;
     for (int i = threadIdx.x; i < 2 * cb_sz; i += nthr) cb0[i] = 0.f;
@@ -1014,11 +1033,15 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
   float acc[LT], wreg[LT];
 #pragma unroll
   for (int i = 0; i < LT; ++i) { acc[i] = 0.f; wreg[i] = 0.f; }
-  __syncthreads();
-  if (OP == OP_L1 && active) {
+  if (OP == OP_L1 && active && k0 + kl < g.K) {           // this thread's LT shapelet values, once per CTA, straight from global
+    const float* wrow = a.W + ((size_t)(k0 + kl) * g.M + m) * g.L;
 #pragma unroll
-    for (int i = 0; i < LT; ++i) wreg[i] = ws[((size_t)kl * g.s + r) * g.LQ + q0 + i];
+    for (int i = 0; i < LT; ++i) {
+      const int l = (q0 + i) * g.s + r;
+      wreg[i] = l < g.L ? __ldg(wrow + l) : 0.f;
+    }
   }
+  __syncthreads();
 
   auto prefetch = [&](int b0, int buf) {
     const int nb = min(g.NB, bend - b0);
@@ -1030,8 +1053,19 @@ __global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo 
     const int kvalid = min(g.KB, g.K - k0);
     for (int rbl = 0; rbl < nb; ++rbl) {
       const float* xsrc = a.xn + ((size_t)(b0 + rbl) * g.M + m) * g.Tp;
-      float* xdst = xd + rbl * g.XQ;
-      for (int c = threadIdx.x; c < xrow; c += nthr) cp_async16(xdst + c * 4, xsrc + c * 4);
+      if (g.s == 1) {
+        float* xdst = xd + rbl * g.XQ;
+        for (int c = threadIdx.x; c < xrow; c += nthr) cp_async16(xdst + c * 4, xsrc + c * 4);
+      } else {                                          // sample t -> residue row t % s, slot t / s
+        float* xdst = xd + (size_t)rbl * g.s * g.XQ;
+        int q = threadIdx.x / g.s, r = threadIdx.x - q * g.s;
+        const int dq = nthr / g.s, dr = nthr - dq * g.s;
+        for (int t = threadIdx.x; t < g.T; t += nthr) {
+          cp_async4(xdst + r * g.XQ + q, xsrc + t);
+          q += dq; r += dr;
+          if (r >= g.s) { r -= g.s; ++q; }
+        }
+      }
       const float* csrc = a.coef + (((size_t)(b0 + rbl) * g.M + m) * g.K + k0) * g.Ts;
       float* cdst = cd + (size_t)rbl * g.KB * g.CP;
       for (int rkl = 0; rkl < kvalid; ++rkl)
@@ -1296,7 +1330,7 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
   };
   g.dbuf = 0;
   search(best, bthr, beff);
-  if (g.s == 1) {
+  {
     int b2, t2; double e2;
     g.dbuf = 1;
     search(b2, t2, e2);
@@ -1320,26 +1354,27 @@ int bwd_hash_cap(const Geo& g, int KB) {
 }
 
 size_t bwd_smem_floats(const Geo& g, int NB, int KB) {
-  const size_t mult = g.s == 1 ? 2 : 1;       // double-buffered for unit stride
+  const size_t mult = g.dbuf ? 2 : 1;         // rows double-buffered
   const size_t xs = (size_t)NB * g.s * g.XQ, cb = (size_t)NB * KB * g.CP;
   size_t cbt = mult * cb;
   if (cbt < (size_t)kMaxThreads * g.LT) cbt = (size_t)kMaxThreads * g.LT;
-  return mult * xs + cbt + (size_t)KB * g.s * g.LQ + KB;
+  return mult * xs + cbt;
 }
 
-// One candidate lag-tile width.  `eff` = share of the launched lanes x lags that are real work.
-bool plan_bwd_lt(Geo& g, BwdPlan& bp, int LT, double& eff) {
+// One candidate (lag tile LT, shapelet block KB).  `cost` = estimated seconds for contraction + tie pre-check.
+bool plan_bwd_cand(Geo& g, BwdPlan& bp, int LT, int KB, double& cost) {
   const size_t cap = (size_t)max_optin_smem() - 1024;
-  const size_t cap_soft = 56 * 1024;     // aim for >= 4 CTAs per SM
+  const size_t cap_soft = 56 * 1024;     // more than one series row per pass only while >= 4 CTAs per SM still fit
   g.LT = LT;
   g.LQ = round_up(ceil_div(g.L, g.s), LT);
   g.XQ = round_up(max(g.DP + g.LQ + 8, ceil_div(g.T, g.s) + 8), 4);   // covers t + LT + 3 + q0 < DP + LQ
   const int ntl_all = g.s * g.LQ / LT;
+  g.dbuf = 1;
+  if (bwd_smem_floats(g, 1, KB) * 4 > cap) {          // very long series: one buffer, loads between two barriers
+    g.dbuf = 0;
+    if (bwd_smem_floats(g, 1, KB) * 4 > cap) return false;
+  }
   // shapelet block and lag block: KB * tlb threads cover one (sample, segment) slot
-  int KB = min(g.K, 8);
-  while (KB > 1 && bwd_smem_floats(g, 1, KB) * 4 > cap_soft) --KB;
-  if (bwd_smem_floats(g, 1, KB) * 4 > cap) return false;
-  KB = ceil_div(g.K, ceil_div(g.K, KB));  // balanced blocks: K = 10 as 5 + 5, not 8 + 2 (idle lanes in the short block)
   int tlb = min(ntl_all, kMaxThreads / KB);
   const int nlb = ceil_div(ntl_all, tlb);
   tlb = ceil_div(ntl_all, nlb);          // balance the lag blocks
@@ -1365,21 +1400,54 @@ bool plan_bwd_lt(Geo& g, BwdPlan& bp, int LT, double& eff) {
   bp.smem_bytes = bwd_smem_floats(g, bestNB, KB) * 4;
   plan_chunks(g, g.M * g.nkb * nlb, bestNB);
   bp.nchunk = g.nchunk;
+  // Estimated time.  Useful share of the launched lane x lag slots: idle lanes of the last warp, lags padded to the
+  // tile, shapelet slots of a short last block (K = 10 in blocks of 3 is 10 of 12).  Splitting the lag axis over CTAs
+  // costs more than its lane count says (T = 4000, L = 2000, K = 10: 14.3 ms in blocks of 5 x 4 lag blocks against
+  // 11.9 ms in blocks of 1 with every lag in one CTA), fewer than 16 resident warps do not hide the pass barriers, and
+  // every shapelet block pays one tie pre-check scan of the series (L1).
   const int lags_done = g.s == 1 ? nlb * tlb * LT : g.s * g.LQ;
-  eff = (double)(bestNB * bestSeg * per_slot) / bp.threads * (double)g.L / (double)lags_done;
+  double eff = (double)(bestNB * bestSeg * per_slot) / bp.threads * (double)g.L / (double)lags_done *
+               (double)g.K / (double)(g.nkb * KB);
+  if (nlb > 1) eff *= 0.83;
+  // CTAs whose warp count is not a multiple of four load the SM's four schedulers unevenly (measured at equal lane
+  // efficiency, T = 2000, L = 600, K = 10: 5-warp CTAs 21.4 TFLOP/s, 8-warp CTAs 26.7; config 2, L = 100: 7 warps 14 %
+  // below what their lane count predicts; 6 warps ~5 %)
+  static const double kWarpShape[4] = {1.0, 0.80, 0.95, 0.87};
+  eff *= kWarpShape[(bp.threads / 32) & 3];
+  // one FFMA per element leaves the cross-term form closer to the shared-memory limit: lanes of one shapelet block
+  // share (broadcast) the series reads, so small blocks cost it more than they cost L1
+  if (g.dist != IGN_DIST_L1) eff *= 0.88 + 0.03 * min(KB, 4);
+  const int ctas = max(1, min((int)(((size_t)max_smem_per_sm()) / (bp.smem_bytes + 1024)), 65536 / (80 * bp.threads)));
+  const double warps = (double)ctas * bp.threads / 32.0;
+  if (warps < 16.0) eff *= warps / 16.0;
+  const double E = (double)g.B * g.M * g.K * g.Tw * g.L;
+  cost = 2.0 * E / (25e12 * eff);
+  if (g.dist == IGN_DIST_L1) {
+    if (bp.hcap) cost += (double)g.nkb * g.B * g.M * g.Tp * 4.0 / 3.4e12;
+    else cost *= 1.5;                                  // no pre-check (block too large for the hash set): always the 3-instruction path
+  }
   return true;
 }
 
-// Lag tile: 8, or 10 where that wastes fewer lanes and padded lags (unit stride only; IGN_BWD_LT=8|10 forces one).
+// Lag tile (8 or 10 lags per thread) and shapelet block (1..8) by estimated time; on ties the larger block (fewer tie
+// scans, more reuse of a staged series row).  IGN_BWD_LT=8|10 and IGN_BWD_KB=n force one (experiments).
 bool plan_bwd(Geo& g, BwdPlan& bp) {
   static const int lt_env = getenv("IGN_BWD_LT") ? atoi(getenv("IGN_BWD_LT")) : 0;
-  double e8 = 0.0, e10 = 0.0;
-  if (g.s != 1 || lt_env == 8) return plan_bwd_lt(g, bp, 8, e8);
-  Geo g10 = g; BwdPlan bp10;
-  const bool ok10 = plan_bwd_lt(g10, bp10, 10, e10);
-  const bool ok8 = plan_bwd_lt(g, bp, 8, e8);
-  if (ok10 && (!ok8 || lt_env == 10 || e10 > e8 + 0.02 || (e10 > e8 - 0.005 && bp10.nlb < bp.nlb))) { g = g10; bp = bp10; return true; }
-  return ok8;
+  static const int kb_env = getenv("IGN_BWD_KB") ? atoi(getenv("IGN_BWD_KB")) : 0;
+  bool found = false; double best = 0.0;
+  Geo gb = g; BwdPlan bb{};
+  for (int KB = min(g.K, 8); KB >= 1; --KB) {
+    if (kb_env > 0 && KB != min(g.K, kb_env)) continue;
+    if (ceil_div(g.K, ceil_div(g.K, KB)) != KB) continue;          // only balanced block sizes (K = 10: 5, 4, 3 -> 5, 4->x)
+    for (int LT = 8; LT <= 10; LT += 2) {
+      if (lt_env != 0 && LT != lt_env) continue;
+      Geo gc = g; BwdPlan bc{}; double c = 0.0;
+      if (!plan_bwd_cand(gc, bc, LT, KB, c)) continue;
+      if (!found || c < best * 0.99) { found = true; best = c; gb = gc; bb = bc; }
+    }
+  }
+  if (found) { g = gb; bp = bb; }
+  return found;
 }
 
 template <typename Kern>
