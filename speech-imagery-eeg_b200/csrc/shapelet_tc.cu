@@ -209,11 +209,15 @@ __device__ __forceinline__ float ordered_val(uint32_t k) {
 }
 
 struct TileCoord { int m, kblk, b0, seg; };
+// GEN = false is the unit-stride, one-tile-per-sample case (every BASELINE config below T = 2276): stride, tile segment
+// and residue loops are compile-time constants there — carrying them as run-time values cost the epilogue-bound
+// L = 100 group 8 % (registers are at the 96 cap of a 19-warp CTA).
+template <bool GEN>
 __device__ __forceinline__ TileCoord tile_coord(const TcGeo& g, int w) {
   TileCoord c;
   const int mk = w / g.tpm;
   const int idx = w - mk * g.tpm;
-  if (g.nseg > 1) { c.b0 = idx / g.nseg; c.seg = idx - c.b0 * g.nseg; }
+  if (GEN && g.nseg > 1) { c.b0 = idx / g.nseg; c.seg = idx - c.b0 * g.nseg; }
   else { c.b0 = idx * g.RB; c.seg = 0; }
   c.m = mk / g.nkb;
   c.kblk = mk - c.m * g.nkb;
@@ -234,10 +238,11 @@ __device__ __forceinline__ RunFlags run_flags(const TcGeo& g, int w, int wbeg, i
 
 // Merge the four lane-quarter cells of every (sample, shapelet) pair of tile `w` (local index n) and write the pooled
 // outputs.  Executed by one warp, after all eight epilogue warps have published the tile (named barrier).
+template <bool GEN>
 __device__ __forceinline__ void finalize_tile(const TcGeo& g, const TcArgs& a, const unsigned long long* cells,
                                               const float* celld, int n, int w, int lane) {
   bar_sync(2 + (n & (g.ncb - 1)), kEpilogueThreads);
-  const TileCoord tc = tile_coord(g, w);
+  const TileCoord tc = tile_coord<GEN>(g, w);
   const int npair = g.RB * g.KG;
   const int nb = min(g.RB, g.B - tc.b0);
   const unsigned long long* cbuf = cells + (size_t)(n & (g.ncb - 1)) * 4 * npair;
@@ -266,7 +271,7 @@ __device__ __forceinline__ void finalize_tile(const TcGeo& g, const TcArgs& a, c
     }
     const int imn = (int)(uint32_t)pk + jj;
     const size_t o = ((size_t)(tc.b0 + rbl) * g.K + k) * g.M + tc.m;
-    if (g.nseg > 1) {            // the sample spans several tiles: smallest (distance, index) over them wins, order-independent
+    if (GEN && g.nseg > 1) {     // the sample spans several tiles: smallest (distance, index) over them wins, order-independent
       atomicMin(a.packed + o, (pk & 0xffffffff00000000ull) | (unsigned long long)(unsigned)imn);
       continue;
     }
@@ -293,9 +298,10 @@ __global__ void __launch_bounds__(256) tc_finish_kernel(const unsigned long long
   if (argmin) argmin[o] = (int)(uint32_t)pk;
 }
 
-template <int DIST, bool STACK>
+template <int DIST, bool STACK, bool GEN>
 __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const TcGeo g, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int g_s = GEN ? g.s : 1, g_nrb = GEN ? g.nrb : 2, g_NKBr = GEN ? g.NKBr : g.NKB;
   const long long t_entry = TC_CLK();
   TC_DECL();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
   uint8_t* stage0 = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ptr = stage0 + (size_t)g.nbs * stage_bytes;
   float* xbuf = reinterpret_cast<float*>(ptr);                      // [nrb][RB][XR] series-row units (ring)
-  ptr += (size_t)g.nrb * g.RB * g.XR * sizeof(float);
+  ptr += (size_t)g_nrb * g.RB * g.XR * sizeof(float);
   float* celld = reinterpret_cast<float*>(ptr);                     // [ncb][4][RB][KG][16] winner rows' distances
   ptr += (size_t)g.ncb * 4 * g.RB * g.KG * 16 * sizeof(float);
   unsigned long long* cells = reinterpret_cast<unsigned long long*>(ptr);   // [ncb][4][RB][KG] ordered min | first window of the row
@@ -356,19 +362,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     int sidx = 0; uint32_t sph = 0;                                  // A ring slot / phase of stage `it`
     int rbuf = 0; uint32_t rph = 0;                                  // row-unit ring slot / phase
     for (int w = wbeg; w < wend; ++w) {
-      const TileCoord tc = tile_coord(g, w);
+      const TileCoord tc = tile_coord<GEN>(g, w);
       const int nb = min(g.RB, g.B - tc.b0);
-      const bool a_live = a_off[0] >= 0 && a_bl < nb && tc.seg * kRows + a_i < g.RItot;
-      const int seg_off = tc.seg * (kRows * kShifts / 32) * 36;      // 2048 samples further along the bank-skewed row
-      for (int res = 0; res < g.s; ++res) {                          // one row unit per residue (one per tile at unit stride)
+      const bool a_live = a_off[0] >= 0 && a_bl < nb && (!GEN || tc.seg * kRows + a_i < g.RItot);
+      const int seg_off = GEN ? tc.seg * (kRows * kShifts / 32) * 36 : 0;      // 2048 samples further along the bank-skewed row
+      for (int res = 0; res < g_s; ++res) {                          // one row unit per residue (one per tile at unit stride)
       const int buf = rbuf;
       long long tr0 = TC_CLK();
       mbar_wait(&rowfull[buf], rph);                                 // this unit's series rows are in shared memory
-      if (++rbuf == g.nrb) { rbuf = 0; rph ^= 1; }
+      if (++rbuf == g_nrb) { rbuf = 0; rph ^= 1; }
       if (lane == 0 && (warp & 3) == 0 && res == 0) TC_TRACE(9 + grp, w - wbeg, 0);
       if (p == 0) TC_ADD(3, tr0);
       const float* xb = xbuf + (size_t)buf * g.RB * g.XR;
-      for (int kb = 0; kb < g.NKBr; ++kb, ++it) {
+      for (int kb = 0; kb < g_NKBr; ++kb, ++it) {
         const int s = sidx;
         const uint32_t ph = sph;
         if (++sidx == g.nast) { sidx = 0; sph ^= 1; }
@@ -430,11 +436,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     for (int w = wbeg; w < wend; ++w, ++n) {
       const int acc = n % g.nacc;
       const int half = (ew >> 2) ^ (n & 1);
-      const TileCoord tc = tile_coord(g, w);
+      const TileCoord tc = tile_coord<GEN>(g, w);
       const int m = tc.m, k0 = tc.kblk * g.KG;
       const int nb = min(g.RB, g.B - tc.b0);
-      const int gi = tc.seg * kRows + i;                            // this row's window group inside its sample
-      const bool row_live = bl < nb && gi < g.RItot;                // (bl < RB is implied: nb <= RB)
+      const int gi = GEN ? tc.seg * kRows + i : i;                  // this row's window group inside its sample
+      const bool row_live = bl < nb && (!GEN || gi < g.RItot);      // (bl < RB is implied: nb <= RB)
       const int t0 = gi * kShifts;
       const int nst = min(4, max(0, (g.Ts - t0) / 4));              // float4 stores per distance row segment (Ts % 4 == 0)
       const int b = tc.b0 + bl;
@@ -530,12 +536,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
       if ((n & (kEpiWarps - 1)) != ew) bar_arrive(2 + (n & (g.ncb - 1)), kEpilogueThreads);
       if (n > 0 && ((n - 1) & (kEpiWarps - 1)) == ew) {
         te0 = TC_CLK();
-        finalize_tile(g, a, cells, celld, n - 1, w - 1, lane);
+        finalize_tile<GEN>(g, a, cells, celld, n - 1, w - 1, lane);
         if (lane == 0) TC_TRACE(ew, n, 2);
         if (lane == 0) TC_ADD(9, te0);
       }
     }
-    if (n > 0 && ((n - 1) & (kEpiWarps - 1)) == ew) finalize_tile(g, a, cells, celld, n - 1, wend - 1, lane);
+    if (n > 0 && ((n - 1) & (kEpiWarps - 1)) == ew) finalize_tile<GEN>(g, a, cells, celld, n - 1, wend - 1, lane);
     if (lane == 0) TC_FLUSH();
   } else if (warp == kMmaWarp) {
     // =================================================================== MMA ISSUER (one elected thread)
@@ -623,7 +629,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
         const RunFlags rf = run_flags(g, w, wbeg, wend);
         if (rf.first) ++run;
         if (g.resident && !rf.first) continue;
-        const TileCoord tc = tile_coord(g, w);
+        const TileCoord tc = tile_coord<GEN>(g, w);
         const uint8_t* bsrc = a.btiles + ((size_t)tc.m * g.nkb + tc.kblk) * g.NKB * (size_t)stage_bytes;
         for (int kb = 0; kb < g.NKB; ++kb, ++itb) {
           int sbi; uint32_t par;
@@ -643,21 +649,21 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     // Rows are stored bank-skewed (4 floats of padding after every 32) so that the 128 row owners, whose segments
     // start 16 samples apart, read with conflict-free LDS.128.  Ring of nrb (tile, residue) units; the unit issued two
     // steps ago is published while the newer ones are still in flight (cp.async groups).
-    for (int i = lane; i < g.nrb * g.RB * g.XR; i += 32) xbuf[i] = 0.f;
+    for (int i = lane; i < g_nrb * g.RB * g.XR; i += 32) xbuf[i] = 0.f;
     __syncwarp();
     const int chunks = g.Tp / 4;
-    const int lag = g.s == 1 ? 0 : 2;                                // units kept in flight behind the one being issued
+    const int lag = g_s == 1 ? 0 : 2;                                // units kept in flight behind the one being issued
     int u = 0, done = 0;                                             // units issued / published
     for (int w = wbeg; w < wend; ++w) {
-      const TileCoord tc = tile_coord(g, w);
-      for (int res = 0; res < g.s; ++res, ++u) {
-        const int buf = u % g.nrb;
-        if (u >= g.nrb) mbar_wait(&rowempty[buf], ((u / g.nrb) - 1) & 1);   // every producer warp is done with unit u - nrb
+      const TileCoord tc = tile_coord<GEN>(g, w);
+      for (int res = 0; res < g_s; ++res, ++u) {
+        const int buf = u % g_nrb;
+        if (u >= g_nrb) mbar_wait(&rowempty[buf], ((u / g_nrb) - 1) & 1);   // every producer warp is done with unit u - nrb
         for (int bl = 0; bl < g.RB; ++bl) {
           if (tc.b0 + bl >= g.B) break;
           float* dst = xbuf + ((size_t)buf * g.RB + bl) * g.XR;
           const float* src = a.xn + ((size_t)(tc.b0 + bl) * g.M + tc.m) * g.Tp;
-          if (g.s == 1) {
+          if (g_s == 1) {
             for (int c = lane; c < chunks; c += 32) cp_async16(dst + c * 4 + 4 * (c >> 3), src + c * 4);
           } else {
             const int nq = (g.T - res + g.s - 1) / g.s;             // x_r[j] = x[j s + res]
@@ -672,7 +678,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
           else asm volatile("cp.async.wait_group 2;" ::: "memory");
           __threadfence_block();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&rowfull[done % g.nrb]);
+          if (lane == 0) mbar_arrive(&rowfull[done % g_nrb]);
           ++done;
         }
       }
@@ -681,7 +687,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) shapelet_fwd_tc_kernel(const Tc
     __threadfence_block();
     __syncwarp();
     for (; done < u; ++done)
-      if (lane == 0) mbar_arrive(&rowfull[done % g.nrb]);
+      if (lane == 0) mbar_arrive(&rowfull[done % g_nrb]);
   }
 
   if (threadIdx.x == 0) TC_ADD(12, t_entry);         // producer thread 0 finished its loop
@@ -814,12 +820,16 @@ int launch_shapelet_fwd_tc(const ign_shapelet_desc& d, const float* xn, const fl
   const size_t smem = max(tc_smem_fixed(g) + g.nbs * tc_stage_bytes(g), (size_t)118 * 1024);   // > half the SM: one CTA per SM
   TcArgs a{xn, st0, thr, p, dmin, argmin, dstore, stats_pitch(d.T, d.L, d.stride), packed, btiles, wstat};
   const int grid = min(sm_count(), g.ntiles);
-  auto kern = g.stack ? (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, true>
-                         : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, true>
-                                                     : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON, true>)
-                      : (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, false>
-                         : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, false>
-                                                     : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON, false>);
+  const bool gen = g.s != 1 || g.nseg != 1;
+#define IGN_TC_PICK(GEN)                                                                                   \
+  (g.stack ? (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, true, GEN>                    \
+              : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, true, GEN>              \
+                                          : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON, true, GEN>)            \
+           : (d.dist == IGN_DIST_SQL2 ? shapelet_fwd_tc_kernel<IGN_DIST_SQL2, false, GEN>                   \
+              : d.dist == IGN_DIST_COSINE ? shapelet_fwd_tc_kernel<IGN_DIST_COSINE, false, GEN>             \
+                                          : shapelet_fwd_tc_kernel<IGN_DIST_PEARSON, false, GEN>))
+  auto kern = gen ? IGN_TC_PICK(true) : IGN_TC_PICK(false);
+#undef IGN_TC_PICK
   IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreadsTC, smem, st>>>(g, a);
   IGN_CUDA(cudaGetLastError());
