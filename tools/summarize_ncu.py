@@ -1,7 +1,7 @@
 """Turn gpurun_out ncu artefacts into small, committed summaries under profiles/.
 
   python tools/summarize_ncu.py launches gpurun_out/launches_X.csv profiles/NAME_launches.txt
-  python tools/summarize_ncu.py full gpurun_out/prof_X.ncu-rep profiles/NAME_full.csv [profiles/traffic.json]
+  python tools/summarize_ncu.py full gpurun_out/prof_X.ncu-rep|prof_X_raw.csv profiles/NAME_full.csv [profiles/traffic.json]
 """
 import collections
 import csv
@@ -46,8 +46,13 @@ def launches(src, dst):
 
 
 def full(src, dst, traffic=None):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    # src: an .ncu-rep, or the `ncu -i X.ncu-rep --page raw --csv` export made on the GPU box (reports of a whole step
+    # exceed what a gpurun call may bring back; the export is a few hundred KB)
+    raw = open(src).read() if src.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(raw.splitlines()) if r]
+    first = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
+    rows = rows[first:]
     hdr, units = rows[0], rows[1]
     cols = [h for h in KEEP if h in hdr]
     with open(dst, "w", newline="") as f:
