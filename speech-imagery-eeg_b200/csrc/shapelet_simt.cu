@@ -987,7 +987,9 @@ __global__ void __launch_bounds__(256) tie_check_kernel(const float* __restrict_
 
 // ---- contraction kernel: dW partials from the coefficients and the series (pure FP32-pipe work) ----
 template <int OP, int LT>
-__global__ void __launch_bounds__(kMaxThreads, 3) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
+// 8-lag tiles fit 64 registers (four 256-thread CTAs per SM: L = 300 2.68 -> 2.55 ms); 10-lag tiles spill there and
+// run slower with four CTAs than with three at 80 registers (L = 100 1.15 -> 1.19 ms)
+__global__ void __launch_bounds__(kMaxThreads, LT == 8 ? 4 : 3) shapelet_bwd_kernel(const Geo g, const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int m = blockIdx.x;
   const int kblk = blockIdx.y / a.nlb, lblk = blockIdx.y - kblk * a.nlb;
@@ -1417,7 +1419,7 @@ bool plan_bwd_cand(Geo& g, BwdPlan& bp, int LT, int KB, double& cost) {
   // one FFMA per element leaves the cross-term form closer to the shared-memory limit: lanes of one shapelet block
   // share (broadcast) the series reads, so small blocks cost it more than they cost L1
   if (g.dist != IGN_DIST_L1) eff *= 0.88 + 0.03 * min(KB, 4);
-  const int ctas = max(1, min((int)(((size_t)max_smem_per_sm()) / (bp.smem_bytes + 1024)), 65536 / (80 * bp.threads)));
+  const int ctas = max(1, min((int)(((size_t)max_smem_per_sm()) / (bp.smem_bytes + 1024)), 65536 / ((LT == 8 ? 64 : 80) * bp.threads)));
   const double warps = (double)ctas * bp.threads / 32.0;
   if (warps < 16.0) eff *= warps / 16.0;
   const double E = (double)g.B * g.M * g.K * g.Tw * g.L;
