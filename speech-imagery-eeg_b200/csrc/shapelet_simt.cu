@@ -1325,7 +1325,8 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
     for (int NB = 1; NB <= min(g.B, 64); ++NB) {
       if (fwd_smem_floats(g, NB, KB, ntile) * 4 > cap) break;
       const int nitem = NB * ntile * nkc;
-      const int thr = min(kMaxThreads, round_up(nitem, 32));
+      static const int thr_env = getenv("IGN_FWD_MAXTHR") ? atoi(getenv("IGN_FWD_MAXTHR")) : 0;   // experiments
+      const int thr = min(thr_env > 0 ? thr_env : kMaxThreads, round_up(nitem, 32));
       const double e = (double)nitem / (double)(ceil_div(nitem, thr) * thr);
       if (e > oeff + 0.01) { oeff = e; obest = NB; othr = thr; }
     }
@@ -1634,9 +1635,16 @@ int launch_shapelet_bwd_simt(const ign_shapelet_desc& d, const float* xn, const 
   if (use_tie) {     // L1: which series rows can hold a value equal to one of their shapelet block's values
     PhaseScope ph(PH_TIE, st);
     const size_t hs = ((size_t)bp.hcap + kTieBitmapWords) * sizeof(unsigned);
-    // one warp walks a series row per load round trip: the scan is latency-bound, so fill every CTA slot the set leaves
-    const int per_sm = max(1, min(5, (int)((size_t)max_smem_per_sm() / (hs + 1024))));
-    const int bsplit = max(1, min(ceil_div(d.B, 8), ceil_div(per_sm * sm_count(), d.M * g.nkb)));
+    // one warp walks a series row per load round trip: the scan is latency-bound, so it wants about three CTAs per SM
+    // (each CTA rebuilds the filter and the set: more, shorter CTAs lose to that setup — 0.063 ms at six per SM against
+    // 0.052 at three, L = 100) and never a second, nearly empty wave (L = 500: 500 CTAs on 444 slots 0.091 ms, 375 CTAs
+    // 0.066 ms)
+    static const int tie_env = getenv("IGN_TIE_PER_SM") ? atoi(getenv("IGN_TIE_PER_SM")) : 0;   // experiments
+    const int resident = max(1, min(8, (int)((size_t)max_smem_per_sm() / (hs + 1024))));
+    const int target = min(tie_env > 0 ? tie_env : 3, resident);
+    const int cols = d.M * g.nkb;
+    const int bsplit = max(1, min(min(ceil_div(d.B, 8), ceil_div(target * sm_count(), cols)),
+                                  max(1, resident * sm_count() / cols)));
     int rc0 = set_smem(tie_check_kernel, hs);
     if (rc0) return rc0;
     tie_check_kernel<<<dim3(d.M, g.nkb, bsplit), 256, hs, st>>>(xn, W, tflags, d.B, d.M, d.T, d.Tp, d.K, d.L, g.KB,
