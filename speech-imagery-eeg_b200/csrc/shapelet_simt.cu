@@ -67,7 +67,7 @@ struct Geo {  // geometry shared by forward and backward
                // LDS.128 when consecutive lanes read consecutive shapelets' rows)
   int XQ;      // pitch of one residue row of x in smem
   int LQ;      // pitch of one residue row of w in smem (ceil(L/s) rounded to 8; backward: to its lag tile LT)
-  int LT;      // backward: lags per thread (8 or 10)
+  int LT;      // backward: lags per thread (8, 10 or 12)
   int KK, KB, nkb;
   int NB;      // series rows resident per pass
   int dbuf;    // forward: series rows double buffered (cp.async one pass ahead)
@@ -1432,8 +1432,8 @@ bool plan_bwd_cand(Geo& g, BwdPlan& bp, int LT, int KB, double& cost) {
   return true;
 }
 
-// Lag tile (8 or 10 lags per thread) and shapelet block (1..8) by estimated time; on ties the larger block (fewer tie
-// scans, more reuse of a staged series row).  IGN_BWD_LT=8|10 and IGN_BWD_KB=n force one (experiments).
+// Lag tile (8, 10 or 12 lags per thread) and shapelet block (1..8) by estimated time; on ties the larger block (fewer tie
+// scans, more reuse of a staged series row).  IGN_BWD_LT=8|10|12 and IGN_BWD_KB=n force one (experiments).
 bool plan_bwd(Geo& g, BwdPlan& bp) {
   static const int lt_env = getenv("IGN_BWD_LT") ? atoi(getenv("IGN_BWD_LT")) : 0;
   static const int kb_env = getenv("IGN_BWD_KB") ? atoi(getenv("IGN_BWD_KB")) : 0;
@@ -1442,7 +1442,7 @@ bool plan_bwd(Geo& g, BwdPlan& bp) {
   for (int KB = min(g.K, 8); KB >= 1; --KB) {
     if (kb_env > 0 && KB != min(g.K, kb_env)) continue;
     if (ceil_div(g.K, ceil_div(g.K, KB)) != KB) continue;          // only balanced block sizes (K = 10: 5, 4, 3 -> 5, 4->x)
-    for (int LT = 8; LT <= 10; LT += 2) {
+    for (int LT = 8; LT <= 12; LT += 2) {
       if (lt_env != 0 && LT != lt_env) continue;
       Geo gc = g; BwdPlan bc{}; double c = 0.0;
       if (!plan_bwd_cand(gc, bc, LT, KB, c)) continue;
@@ -1488,6 +1488,7 @@ FwdKernel fwd_kernel(bool l1, int KK, int TT) {
 
 BwdKernel bwd_kernel(int dist, int LT) {
   if (LT == 10) return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1, 10> : shapelet_bwd_kernel<OP_DOT, 10>;
+  if (LT == 12) return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1, 12> : shapelet_bwd_kernel<OP_DOT, 12>;
   return dist == IGN_DIST_L1 ? shapelet_bwd_kernel<OP_L1, 8> : shapelet_bwd_kernel<OP_DOT, 8>;
 }
 
