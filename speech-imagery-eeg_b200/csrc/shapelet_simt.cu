@@ -1327,7 +1327,9 @@ bool plan_fwd(Geo& g, int TT, FwdPlan& fp) {
       const int nitem = NB * ntile * nkc;
       static const int thr_env = getenv("IGN_FWD_MAXTHR") ? atoi(getenv("IGN_FWD_MAXTHR")) : 0;   // experiments
       const int thr = min(thr_env > 0 ? thr_env : kMaxThreads, round_up(nitem, 32));
-      const double e = (double)nitem / (double)(ceil_div(nitem, thr) * thr);
+      // CTAs whose warp count is not a multiple of four load the SM's schedulers unevenly (see plan_bwd_cand)
+      static const double kWarpShape[4] = {1.0, 0.80, 0.95, 0.87};
+      const double e = (double)nitem / (double)(ceil_div(nitem, thr) * thr) * kWarpShape[(thr / 32) & 3];
       if (e > oeff + 0.01) { oeff = e; obest = NB; othr = thr; }
     }
   };
