@@ -1443,7 +1443,7 @@ bool plan_bwd(Geo& g, BwdPlan& bp) {
   Geo gb = g; BwdPlan bb{};
   for (int KB = min(g.K, 8); KB >= 1; --KB) {
     if (kb_env > 0 && KB != min(g.K, kb_env)) continue;
-    if (ceil_div(g.K, ceil_div(g.K, KB)) != KB) continue;          // only balanced block sizes (K = 10: 5, 4, 3 -> 5, 4->x)
+    if (kb_env <= 0 && ceil_div(g.K, ceil_div(g.K, KB)) != KB) continue;   // only balanced block sizes (K = 10: 8, 7, 6 are 5 + 5 anyway)
     for (int LT = 8; LT <= 12; LT += 2) {
       if (lt_env != 0 && LT != lt_env) continue;
       Geo gc = g; BwdPlan bc{}; double c = 0.0;
