@@ -190,3 +190,34 @@ def test_cuda_graph_replay_is_the_same_training_as_the_eager_step(tmp_path, monk
         params[mode] = ([p.detach().clone() for p in exp.model.parameters()], losses)
     for le, lg in zip(params["eager"][1], params["graph"][1]):
         assert abs(le - lg) <= 1e-4 * abs(le) + 1e-6, (params["eager"][1], params["graph"][1])
+
+
+def test_bench_line_contract_of_our_arm():
+    """`python bench.py` on one GPU (small batch, few steps, no extras): ONE JSON line with every key the measurement
+    contract names — whole-job value, end-to-end object with its copy sizes, launch count, clocks, a roofline for the
+    dominant kernel with live timing, per-kernel entries, engines as the library reported them."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--batch", "16",
+                          "--no_extras", "--no_cpu_baseline"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "train samples/sec" and d["unit"] == "samples/s" and d["n_gpus"] == 1
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32"
+    assert d["value"] > 0 and abs(d["value"] - 16 * 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
+    assert d["config"]["workload"].startswith("InterpGN(FCN)") and "model" not in d["config"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == "samples/s" and e["d2h_bytes_per_step"] == 4
+    assert e["h2d_bytes_per_step"] == 16 * 1000 * 125 * 4 + 16 * 8 + 16 * 1000
+    assert e["value"] != d["value"]
+    assert d["gpu_launches"] > 0 and "sm_mhz" in d["clocks"] and isinstance(d["clocks"]["reasons"], list)
+    r = d["roofline"]
+    assert r["kernel"] == "bwd.contraction" and r["bound"] == "fp32_alu" and r["unit"] == "TFLOP/s"
+    assert 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["avg_ms"] > 0
+    names = {k["kernel"] for k in d["rooflines"]}
+    assert {"shapelet_fwd", "shapelet_bwd", "bwd.pool_bwd", "bwd.tie_check", "bwd.contraction", "instnorm"} <= names
+    assert set(d["engines"].values()) == {"fp32"}               # the default L1 distance has no tensor-core form
