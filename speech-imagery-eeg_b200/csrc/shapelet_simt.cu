@@ -1430,7 +1430,7 @@ bool plan_bwd_cand(Geo& g, BwdPlan& bp, int LT, int KB, double& cost) {
   cost = 2.0 * E / (25e12 * eff);
   if (g.dist == IGN_DIST_L1) {
     if (bp.hcap) cost += (double)g.nkb * g.B * g.M * g.Tp * 4.0 / 3.4e12;
-    else cost *= 1.5;                                  // no pre-check (block too large for the hash set): always the 3-instruction path
+    else cost *= 2.0;                                  // no pre-check (block too large for the hash set): always the exact 4-instruction path
   }
   return true;
 }
